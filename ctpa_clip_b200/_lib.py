@@ -1,0 +1,59 @@
+"""ctypes binding of libctclip_sm100.so (the C-ABI declared in include/ctclip_b200.h).
+
+There is no CPU fallback: if the shared library is missing, `lib()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libctclip_sm100.so"
+_lib = None
+
+
+class CtclipError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("a_mn_major", C.c_int),
+        ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_mn_major", C.c_int),
+        ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_is_f32", C.c_int),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p), ("ldr", C.c_longlong),
+        ("alpha", C.c_float),
+        ("atomic", C.c_int),
+        ("splits", C.c_int),
+    ]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CtclipError(
+                f"{LIB_PATH} not built: run `python -m ctpa_clip_b200.build` (there is no CPU/PyTorch fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.ctclip_version.restype = C.c_int
+        _lib.ctclip_last_error.restype = C.c_int
+        _lib.ctclip_last_error.argtypes = [C.c_char_p, C.c_size_t]
+        _lib.ctclip_launch_count.restype = C.c_longlong
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().ctclip_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise CtclipError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().ctclip_launch_count())

@@ -1,0 +1,362 @@
+// tcgen05 / TMEM / TMA GEMM for the CT-CLIP hot path (sm_100a only).
+//
+//   C[M,N] (op)= alpha * sum_k A(m,k) * B(n,k)  (+ bias[n]) (+ resid[m,n])
+//
+// bf16 operands, fp32 accumulation in tensor memory. Each operand may be stored K-major
+// (rows = M or N, K contiguous) or MN-major (rows = K, M/N contiguous), so that forward
+// (x W^T), dgrad (dy W) and wgrad (dy^T x) all run from the natural row-major tensors
+// without transposes. Replaces the cuBLAS calls behind nn.Linear on the path
+// (reference: CTPA_CLIP/ct_clip/ctvit.py:172, attention.py:48,51,119,120,125).
+//
+// Structure: persistent CTAs (one per SM), warp-specialised:
+//   warp 0   : TMA producer (one elected lane)         smem ring: full/empty mbarriers
+//   warp 1   : tcgen05.mma issuer (one elected lane)   TMEM ring: tmem_full/tmem_empty
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue, tcgen05.ld 32x32b (one accumulator row per thread) -> global
+// Tile 128 x BN x 64, SWIZZLE_128B operand tiles, 2 accumulator buffers (2*BN TMEM columns).
+#include "ptx.cuh"
+#include "ctclip_internal.h"
+
+namespace {
+
+using namespace ptx;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
+};
+
+struct GemmKernelParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  void* C;
+  long long ldc;
+  int c_is_f32;
+  int atomic;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+  float alpha;
+  int gelu_glu;  // reserved
+};
+
+// ---------------------------------------------------------------- epilogue helpers
+__device__ __forceinline__ void store_row_chunk(const GemmKernelParams& p, int row, int col0, float (&v)[32]) {
+  if (row >= p.M || col0 >= p.N) return;
+  const int ncols = min(32, p.N - col0);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+  }
+  if (p.c_is_f32) {
+    float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+    if (p.atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(c + j, v[j]);
+      return;
+    }
+    const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
+                     (p.resid == nullptr ||
+                      ((reinterpret_cast<uintptr_t>(p.resid + (long long)row * p.ldr + col0) & 15) == 0));
+    if (vec) {
+      if (p.resid != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r = r4[j];
+          v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      }
+      float4* c4 = reinterpret_cast<float4*>(c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) {
+          float x = v[j];
+          if (p.resid != nullptr) x += p.resid[(long long)row * p.ldr + col0 + j];
+          c[j] = x;
+        }
+    }
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+    const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0);
+    if (vec) {
+      uint4* c4 = reinterpret_cast<uint4*>(c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        c4[j] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmKernelParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_work = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int n_t = w % p.n_tiles;
+        const int m_t = (w / p.n_tiles) % p.m_tiles;
+        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(full_bar + stage, L::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, m_t * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar + stage, m_t * BM + j * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, full_bar + stage, kb * BK, n_t * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar + stage, n_t * BN + j * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 8-row groups are 1024 B apart (SBO); a 16-element k step is +32 B inside the swizzle atom.
+            // MN-major: 64-element MN atoms are BK*128 B apart (LBO), 8-row k groups 1024 B apart (SBO);
+            //           a 16-row k step is +2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tmem_full + acc);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int n_t = w % p.n_tiles;
+      const int m_t = (w / p.n_tiles) % p.m_tiles;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const int row = m_t * BM + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n_t * BN + c >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        store_row_chunk(p, row, n_t * BN + c, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+int encode_operand_map(CUtensorMap* map, const void* ptr, bool mn_major, long long rows_mn, long long k,
+                       long long ld_elems, int box_mn) {
+  // K-major: global tensor is [rows_mn][k] (k contiguous): dims {k, rows_mn}, box {64, box_mn}
+  // MN-major: global tensor is [k][rows_mn] (mn contiguous): dims {rows_mn, k}, box {64, 64}
+  cuuint64_t dims[2];
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2];
+  cuuint32_t estr[2] = {1, 1};
+  if (!mn_major) {
+    dims[0] = k; dims[1] = rows_mn; box[0] = BK; box[1] = box_mn;
+  } else {
+    dims[0] = rows_mn; dims[1] = k; box[0] = 64; box[1] = BK;
+  }
+  return ctclip::encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                             estr, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const ctclip_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta, const CUtensorMap& tb,
+           int grid, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, kp);
+  (void)d;
+  return ctclip::check_launch("gemm launch");
+}
+
+}  // namespace
+
+extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (d == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: null descriptor");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: M,N,K must be positive");
+  if ((d->lda % 8) || (d->ldb % 8)) return ctclip::fail(CTCLIP_E_ALIGN, "gemm: lda/ldb must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(d->A) & 15) || (reinterpret_cast<uintptr_t>(d->B) & 15))
+    return ctclip::fail(CTCLIP_E_ALIGN, "gemm: A/B must be 16-byte aligned");
+  if (d->A == nullptr || d->B == nullptr || d->C == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: null pointer");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+
+  const int BN = (d->N <= 128) ? 128 : 256;
+  GemmKernelParams kp{};
+  kp.M = d->M; kp.N = d->N; kp.K = d->K;
+  kp.m_tiles = (d->M + BM - 1) / BM;
+  kp.n_tiles = (d->N + BN - 1) / BN;
+  kp.kb_total = (d->K + BK - 1) / BK;
+  int splits = d->splits;
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int sms = ctclip::sm_count();
+  if (splits <= 0) {  // auto: only when the caller allows atomic accumulation
+    splits = 1;
+    if (d->atomic && tiles < sms) {
+      splits = (sms + tiles - 1) / tiles;
+      const int max_splits = kp.kb_total / 4 > 0 ? kp.kb_total / 4 : 1;
+      if (splits > max_splits) splits = max_splits;
+    }
+  }
+  if (splits > 1 && !(d->atomic && d->c_is_f32))
+    return ctclip::fail(CTCLIP_E_SHAPE, "gemm: split-K requires atomic fp32 output");
+  if (d->atomic && !d->c_is_f32) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: atomic output must be fp32");
+  kp.kb_per_split = (kp.kb_total + splits - 1) / splits;
+  kp.splits = (kp.kb_total + kp.kb_per_split - 1) / kp.kb_per_split;  // no empty splits
+  kp.C = d->C; kp.ldc = d->ldc; kp.c_is_f32 = d->c_is_f32; kp.atomic = d->atomic;
+  kp.bias = d->bias; kp.resid = d->resid; kp.ldr = d->ldr;
+  kp.alpha = d->alpha;
+  if (kp.splits > 1 && (d->bias || d->resid))
+    return ctclip::fail(CTCLIP_E_SHAPE, "gemm: bias/resid not supported with split-K");
+
+  CUtensorMap ta, tb;
+  rc = encode_operand_map(&ta, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM);
+  if (rc) return rc;
+  rc = encode_operand_map(&tb, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, BN);
+  if (rc) return rc;
+
+  const int num_work = tiles * kp.splits;
+  const int grid = num_work < sms ? num_work : sms;
+  const int sel = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+  switch (sel) {
+    case 0: return launch<128, false, false>(d, kp, ta, tb, grid, stream);
+    case 1: return launch<128, false, true>(d, kp, ta, tb, grid, stream);
+    case 2: return launch<128, true, false>(d, kp, ta, tb, grid, stream);
+    case 3: return launch<128, true, true>(d, kp, ta, tb, grid, stream);
+    case 4: return launch<256, false, false>(d, kp, ta, tb, grid, stream);
+    case 5: return launch<256, false, true>(d, kp, ta, tb, grid, stream);
+    case 6: return launch<256, true, false>(d, kp, ta, tb, grid, stream);
+    default: return launch<256, true, true>(d, kp, ta, tb, grid, stream);
+  }
+}
