@@ -57,3 +57,19 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().ctclip_launch_count())
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("t", C.c_int), ("h", C.c_int), ("w", C.c_int), ("heads", C.c_int),
+        ("dim_head", C.c_int), ("temporal", C.c_int),
+        ("q", C.c_void_p), ("ldq", C.c_int),
+        ("kv", C.c_void_p), ("ldkv", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int),
+        ("lse", C.c_void_p),
+        ("q_scale", C.c_void_p), ("k_scale", C.c_void_p),
+        ("bias_table", C.c_void_p), ("bias_rowmax", C.c_void_p),
+        ("d_o", C.c_void_p),
+        ("dq", C.c_void_p), ("dkv", C.c_void_p),
+        ("dq_scale", C.c_void_p), ("dk_scale", C.c_void_p), ("dbias_table", C.c_void_p),
+    ]

@@ -1,0 +1,684 @@
+// Cosine-sim attention of the CTViT transformer blocks on tcgen05 / TMEM (reference attention.py:127-181):
+//   q = l2norm(q) * q_scale ; k = l2norm(k) * k_scale ; P = softmax(8 q k^T + bias) ; O = P v      (dim_head = 32)
+//
+// One CTA owns one (sequence block, head): its K^, V (and, in the backward, Q^, dO) live in shared memory as bf16
+// 8x8 "core matrices" (SWIZZLE_NONE UMMA layout), written by the threads that normalise them, so the same bytes
+// serve as K-major or MN-major operands. S = Q^ K^T and O = P V are tcgen05.mma with accumulators in tensor
+// memory; tcgen05.ld 32x32b hands every thread one full query row, so the softmax needs no shuffles.
+// No running max: |8 q^.k^| <= 8 max_d|qs_d ks_d| and the additive bias has a per-query-position maximum known
+// from the (2h-1)(2w-1) relative-position table, so exp2(s - M_i) can never overflow and never fully underflows.
+//
+// Both factorised attentions share this kernel: "spatial" blocks are one frame of n = h*w tokens (bias from the
+// continuous-position-bias table); "temporal" blocks pack floor(128/t) sequences of t tokens (gathered with stride
+// h*w from the canonical (b,t,h,w,d) layout) and mask pairs from different sequences.
+#include "ptx.cuh"
+#include "ctclip_internal.h"
+
+namespace {
+using namespace ptx;
+
+constexpr int DH = 32;            // head dim
+constexpr int QT = 128;           // query rows per tile
+constexpr int KC = 64;            // keys per chunk (forward)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kScale = 8.0f;    // attention.py:99
+
+struct AttnParams {
+  const __nv_bfloat16* q;   // [tokens][ldq]
+  const __nv_bfloat16* kv;  // [tokens][ldkv]  k = cols [0,inner), v = cols [inner, 2 inner)
+  __nv_bfloat16* o;         // [tokens][ldo]
+  float* lse;               // [tokens][heads]  (log2 domain, includes the offset)
+  const float* q_scale;     // [32]
+  const float* k_scale;     // [32]
+  const float* bias_table;  // [heads][(2h-1)*(2w-1)] or null
+  const float* bias_rowmax; // [heads][h*w] or null
+  int heads, inner, ldq, ldkv, ldo;
+  int mode;                 // 0 spatial, 1 temporal
+  int n;                    // tokens per sequence
+  int ns;                   // sequences per block
+  int num_seqs;             // total sequences
+  int gh, gw, gt;           // token grid
+  int r_pad;                // rows per block padded to a multiple of 64
+};
+
+__device__ __forceinline__ long long row_token(const AttnParams& p, int blk, int r, bool& valid) {
+  const int sl = r / p.n, pos = r - sl * p.n;
+  const long long seq = (long long)blk * p.ns + sl;
+  valid = (sl < p.ns) && (seq < p.num_seqs);
+  if (!valid) return 0;
+  if (p.mode == 0) return seq * p.n + pos;
+  const int hw = p.gh * p.gw;
+  const long long b = seq / hw;
+  const int ph = (int)(seq - b * hw);
+  return (b * p.gt + pos) * hw + ph;
+}
+
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// byte offset of the 16-byte group (row r, column group c8) in a core-matrix tile with `cols` columns
+__device__ __forceinline__ uint32_t cm_off(int r, int c8, int cols) {
+  return (uint32_t)((r >> 3) * (cols >> 3) * 128 + c8 * 128 + (r & 7) * 16);
+}
+
+// loads one 32-wide bf16 head slice, returns fp32 values and the inverse l2 norm (F.normalize eps 1e-12)
+__device__ __forceinline__ float load_head_row(const __nv_bfloat16* src, float (&v)[DH]) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = s4[j];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[8 * j + 2 * k] = bf16_lo(w[k]);
+      v[8 * j + 2 * k + 1] = bf16_hi(w[k]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DH; ++j) ss = fmaf(v[j], v[j], ss);
+  return 1.f / fmaxf(sqrtf(ss), 1e-12f);
+}
+
+__device__ __forceinline__ void store_row_cm(uint8_t* tile, int r, const float (&v)[DH]) {
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * c8 + 0], v[8 * c8 + 1]);
+    u.y = pack_bf16(v[8 * c8 + 2], v[8 * c8 + 3]);
+    u.z = pack_bf16(v[8 * c8 + 4], v[8 * c8 + 5]);
+    u.w = pack_bf16(v[8 * c8 + 6], v[8 * c8 + 7]);
+    *reinterpret_cast<uint4*>(tile + cm_off(r, c8, DH)) = u;
+  }
+}
+__device__ __forceinline__ void store_zero_row_cm(uint8_t* tile, int r) {
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(tile + cm_off(r, c8, DH)) = make_uint4(0, 0, 0, 0);
+}
+
+// =============================================================================================== forward
+// grid.x = num_blocks * heads (head fastest), 128 threads.
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int head = blockIdx.x % p.heads;
+  const int blk = blockIdx.x / p.heads;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int R = p.ns * p.n;
+  const int nchunks = (R + KC - 1) / KC;
+  const int ntiles = (R + QT - 1) / QT;
+
+  uint8_t* sK = smem;                        // r_pad x 32 bf16
+  uint8_t* sV = sK + p.r_pad * DH * 2;       // r_pad x 32
+  uint8_t* sQ = sV + p.r_pad * DH * 2;       // 128 x 32
+  uint8_t* sP = sQ + QT * DH * 2;            // 128 x 64
+  float* sTab = reinterpret_cast<float*>(sP + QT * KC * 2);
+  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
+  float* sRowMax = sTab + tab_n;
+  float* sScale = sRowMax + ((p.bias_table != nullptr) ? p.n : 0);  // [64]: q_scale*8*log2e , k_scale
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sScale + 64) + 15) & ~uintptr_t(15));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  if (tid < DH) {
+    sScale[tid] = p.q_scale[tid] * (kScale * kLog2e);
+    sScale[DH + tid] = p.k_scale[tid];
+  }
+  for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
+  if (p.bias_table != nullptr)
+    for (int i = tid; i < p.n; i += blockDim.x) sRowMax[i] = p.bias_rowmax[(long long)head * p.n + i] * kLog2e;
+  __syncthreads();
+  // bound of |8 log2e q^.k^|
+  float cmax = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) cmax = fmaxf(cmax, fabsf(sScale[d] * sScale[DH + d]));
+
+  // ---- K^ and V for the whole block
+  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+    bool valid = false;
+    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    if (valid) {
+      float v[DH];
+      const float inv = load_head_row(p.kv + tok * p.ldkv + head * DH, v);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[DH + d];
+      store_row_cm(sK, r, v);
+      const uint4* s4 = reinterpret_cast<const uint4*>(p.kv + tok * p.ldkv + p.inner + head * DH);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sV + cm_off(r, c8, DH)) = s4[c8];
+    } else {
+      store_zero_row_cm(sK, r);
+      store_zero_row_cm(sV, r);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem;         // 2 x 64 columns
+  const uint32_t tO = tmem + 128;   // 32 columns
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(QT, KC, false, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
+  uint32_t phase = 0;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int r = tile * QT + tid;
+    bool valid = false;
+    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    if (valid) {
+      float v[DH];
+      const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d];
+      store_row_cm(sQ, tid, v);
+    } else {
+      store_zero_row_cm(sQ, tid);
+    }
+    const int my_seq = r / p.n;
+    const int my_pos = r - my_seq * p.n;
+    const int qy = my_pos / p.gw, qx = my_pos - qy * p.gw;
+    const float m_i = cmax + ((p.bias_table != nullptr && valid) ? sRowMax[my_pos] : 0.f);
+    float l = 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // restrict key chunks to those that can hold keys of this tile's sequences (packed temporal blocks: all)
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)
+        mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512),
+                   idesc_s, k > 0);
+      mma_commit(bars);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(bars, phase);
+      phase ^= 1;
+      tc_fence_after();
+      const uint32_t tSc = tS + (c & 1) * KC;
+      uint32_t pk[KC / 2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32];
+        tmem_ld_32x32(tSc + lane_off + half * 32, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float e[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kr = c * KC + half * 32 + j + u;  // key row in block
+            float x = __uint_as_float(s[j + u]) - m_i;
+            bool ok = valid && kr < R;
+            if (p.ns > 1) ok = ok && (kr / p.n == my_seq);
+            if (p.bias_table != nullptr) {
+              const int kp = kr % p.n;
+              const int ky = kp / p.gw, kx = kp - ky * p.gw;
+              x += sTab[(qy - ky + p.gh - 1) * (2 * p.gw - 1) + (qx - kx + p.gw - 1)];
+            }
+            e[u] = ok ? exp2f(x) : 0.f;
+            l += e[u];
+          }
+          pk[(half * 32 + j) >> 1] = pack_bf16(e[0], e[1]);
+        }
+      }
+      // P tile (128 x 64) as K-major core matrices
+#pragma unroll
+      for (int c8 = 0; c8 < KC / 8; ++c8)
+        *reinterpret_cast<uint4*>(sP + cm_off(tid, c8, KC)) =
+            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        // O += P V_c     A: P [128 x 64] K-major ; B: V_c [N=32][K=64] MN-major (rows = keys)
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)
+          mma_f16_ss(tO, desc_nosw(smem_u32(sP) + k * 256, 128, (KC / 8) * 128),
+                     desc_nosw(smem_u32(sV) + (c * KC + k * 16) * (DH * 2), 512, 128), idesc_o, (c > 0 || k > 0));
+        if (c + 1 < nchunks) {
+          const uint32_t tSn = tS + ((c + 1) & 1) * KC;
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            mma_f16_ss(tSn, desc_nosw(smem_u32(sQ) + k * 256, 128, 512),
+                       desc_nosw(smem_u32(sK) + (c + 1) * KC * (DH * 2) + k * 256, 128, 512), idesc_s, k > 0);
+        }
+        mma_commit(bars);
+      }
+    }
+    // ---- epilogue of this query tile
+    mbar_wait(bars, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + lane_off, o);
+      tmem_wait_ld();
+      if (valid) {
+        const float inv_l = 1.f / l;
+        uint4* dst = reinterpret_cast<uint4*>(p.o + tok * p.ldo + head * DH);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
+          dst[j] = u;
+        }
+        if (p.lse != nullptr) p.lse[tok * p.heads + head] = m_i + log2f(l);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+
+// =============================================================================================== backward
+// One CTA per (sequence block, head), 128 threads. Q~ (= 8 log2e q^), dO, lse and delta = rowsum(dO*O) stay in
+// shared memory for the whole block; key chunks of 128 rows stream through. Per (chunk c, query tile i):
+//   S = Q~_i K^_c^T, dP = dO_i V_c^T               (TMEM, 128 columns each)
+//   p = exp2(S + log2e*bias - lse), dz = p*(dP - delta)   -> smem as bf16 core matrices (P, dS)
+//   dV_c += P^T dO_i ; dK^_c += dS^T Q~_i ; dQ_i += dS K^_c      (TMEM; dQ keeps one 32-column slot per query tile)
+// One mbarrier: every tcgen05.commit covers all MMAs issued so far, so a single wait per step orders everything.
+struct AttnBwdParams {
+  AttnParams f;
+  const __nv_bfloat16* d_o;
+  __nv_bfloat16* dq;
+  __nv_bfloat16* dkv;
+  float* dq_scale;
+  float* dk_scale;
+  float* dbias_table;
+};
+
+constexpr int BKC = 128;  // keys per chunk (backward)
+
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const AttnBwdParams bp) {
+  const AttnParams& p = bp.f;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int head = blockIdx.x % p.heads;
+  const int blk = blockIdx.x / p.heads;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int R = p.ns * p.n;
+  const int nchunks = (R + BKC - 1) / BKC;
+  const int ntiles = (R + QT - 1) / QT;
+  const bool has_bias = p.bias_table != nullptr;
+  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
+
+  uint8_t* sQ = smem;                              // r_pad x 32
+  uint8_t* sdO = sQ + p.r_pad * DH * 2;            // r_pad x 32
+  uint8_t* sK = sdO + p.r_pad * DH * 2;            // 128 x 32
+  uint8_t* sV = sK + BKC * DH * 2;                 // 128 x 32
+  uint8_t* sP = sV + BKC * DH * 2;                 // 128 x 128
+  uint8_t* sdS = sP + QT * BKC * 2;                // 128 x 128
+  float* sLse = reinterpret_cast<float*>(sdS + QT * BKC * 2);
+  float* sDelta = sLse + p.r_pad;
+  float* sTab = sDelta + p.r_pad;
+  float* sdTab = sTab + tab_n;
+  float* sScale = sdTab + tab_n;                   // [64]
+  float* sRed = sScale + 64;                       // [64] dq_scale | dk_scale partial sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRed + 64) + 15) & ~uintptr_t(15));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (tid < DH) {
+    sScale[tid] = p.q_scale[tid];
+    sScale[DH + tid] = p.k_scale[tid];
+  }
+  if (tid < 64) sRed[tid] = 0.f;
+  for (int i = tid; i < tab_n; i += blockDim.x) {
+    sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
+    sdTab[i] = 0.f;
+  }
+  __syncthreads();
+
+  // ---- Q~, dO, lse, delta for the whole block
+  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+    bool valid = false;
+    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    if (valid) {
+      float v[DH];
+      const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d] * (kScale * kLog2e);
+      store_row_cm(sQ, r, v);
+      float go[DH], oo[DH];
+      load_head_row(bp.d_o + tok * p.ldo + head * DH, go);
+      load_head_row(p.o + tok * p.ldo + head * DH, oo);
+      store_row_cm(sdO, r, go);
+      float dl = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) dl = fmaf(go[d], oo[d], dl);
+      sDelta[r] = dl;
+      sLse[r] = p.lse[tok * p.heads + head];
+    } else {
+      store_zero_row_cm(sQ, r);
+      store_zero_row_cm(sdO, r);
+      sDelta[r] = 0.f;
+      sLse[r] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 288, tdQ = tmem + 320;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKC, false, false);   // [128 q] x [128 keys], K = 32
+  constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
+  constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
+  constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
+  uint32_t phase = 0;
+
+  for (int c = 0; c < nchunks; ++c) {
+    // ---- K^_c, V_c (thread = key row)
+    const int kr = c * BKC + tid;
+    bool kvalid = false;
+    const long long ktok = (kr < R) ? row_token(p, blk, kr, kvalid) : 0;
+    float kraw[DH];
+    float kinv = 0.f;
+    if (kvalid) {
+      kinv = load_head_row(p.kv + ktok * p.ldkv + head * DH, kraw);
+      float v[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) v[d] = kraw[d] * kinv * sScale[DH + d];
+      store_row_cm(sK, tid, v);
+      const uint4* s4 = reinterpret_cast<const uint4*>(p.kv + ktok * p.ldkv + p.inner + head * DH);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sV + cm_off(tid, c8, DH)) = s4[c8];
+    } else {
+      store_zero_row_cm(sK, tid);
+      store_zero_row_cm(sV, tid);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) {
+        mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512),
+                   idesc_s, k > 0);
+        mma_f16_ss(tdP, desc_nosw(smem_u32(sdO) + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512),
+                   idesc_s, k > 0);
+      }
+      mma_commit(bars);
+    }
+    for (int i = 0; i < ntiles; ++i) {
+      const int r = i * QT + tid;
+      const int my_seq = r / p.n;
+      const int my_pos = r - my_seq * p.n;
+      const bool valid = (r < R) && (my_seq < p.ns) && ((long long)blk * p.ns + my_seq < p.num_seqs);
+      const int qy = my_pos / p.gw, qx = my_pos - qy * p.gw;
+      const float lse_i = sLse[r], delta_i = sDelta[r];
+      mbar_wait(bars, phase);
+      phase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int piece = 0; piece < BKC / 32; ++piece) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(tS + lane_off + piece * 32, s);
+        tmem_ld_32x32(tdP + lane_off + piece * 32, dp);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float pe[2], de[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kk = c * BKC + piece * 32 + j + u;
+            bool ok = valid && kk < R;
+            if (p.ns > 1) ok = ok && (kk / p.n == my_seq);
+            float x = __uint_as_float(s[j + u]) - lse_i;
+            int idx = 0;
+            if (has_bias) {
+              const int kp = kk % p.n;
+              const int ky = kp / p.gw, kx = kp - ky * p.gw;
+              idx = (qy - ky + p.gh - 1) * (2 * p.gw - 1) + (qx - kx + p.gw - 1);
+              x += sTab[idx];
+            }
+            pe[u] = ok ? exp2f(x) : 0.f;
+            de[u] = pe[u] * (__uint_as_float(dp[j + u]) - delta_i);
+            if (has_bias && ok) atomicAdd(&sdTab[idx], de[u]);
+          }
+          pk[j >> 1] = pack_bf16(pe[0], pe[1]);
+          dk[j >> 1] = pack_bf16(de[0], de[1]);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          *reinterpret_cast<uint4*>(sP + cm_off(tid, piece * 4 + c8, BKC)) =
+              make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+          *reinterpret_cast<uint4*>(sdS + cm_off(tid, piece * 4 + c8, BKC)) =
+              make_uint4(dk[4 * c8], dk[4 * c8 + 1], dk[4 * c8 + 2], dk[4 * c8 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t qoff = (uint32_t)i * QT * (DH * 2);
+#pragma unroll
+        for (int k = 0; k < QT / 16; ++k) {  // reduction over the 128 queries of this tile
+          const uint64_t dPt = desc_nosw(smem_u32(sP) + k * 2 * P_RS, P_RS, 128);     // P^T  (MN-major A)
+          const uint64_t dSt = desc_nosw(smem_u32(sdS) + k * 2 * P_RS, P_RS, 128);    // dS^T (MN-major A)
+          const uint64_t ddO = desc_nosw(smem_u32(sdO) + qoff + k * 1024, 512, 128);  // dO_i  (MN-major B)
+          const uint64_t dQt = desc_nosw(smem_u32(sQ) + qoff + k * 1024, 512, 128);   // Q~_i  (MN-major B)
+          mma_f16_ss(tdV, dPt, ddO, idesc_kv, (i > 0 || k > 0));
+          mma_f16_ss(tdK, dSt, dQt, idesc_kv, (i > 0 || k > 0));
+        }
+#pragma unroll
+        for (int k = 0; k < BKC / 16; ++k)  // reduction over the 128 keys of this chunk
+          mma_f16_ss(tdQ + i * DH, desc_nosw(smem_u32(sdS) + k * 256, 128, P_RS),
+                     desc_nosw(smem_u32(sK) + k * 1024, 512, 128), idesc_q, (c > 0 || k > 0));
+        if (i + 1 < ntiles) {
+          const uint32_t qn = (uint32_t)(i + 1) * QT * (DH * 2);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) {
+            mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + qn + k * 256, 128, 512),
+                       desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
+            mma_f16_ss(tdP, desc_nosw(smem_u32(sdO) + qn + k * 256, 128, 512),
+                       desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
+          }
+        }
+        mma_commit(bars);
+      }
+    }
+    // ---- chunk epilogue: dV_c, dK^_c -> dkv rows (thread = key row)
+    mbar_wait(bars, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t a[32], b[32];
+      tmem_ld_32x32(tdV + lane_off, a);
+      tmem_ld_32x32(tdK + lane_off, b);
+      tmem_wait_ld();
+      if (kvalid) {
+        uint4* dv = reinterpret_cast<uint4*>(bp.dkv + ktok * p.ldkv + p.inner + head * DH);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dv[j] = make_uint4(pack_bf16(__uint_as_float(a[8 * j + 0]), __uint_as_float(a[8 * j + 1])),
+                             pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
+                             pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
+                             pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+        // k^ = ks * k / |k| : dk = (g - kbar (kbar.g)) / |k|, g = ks * dk^ ; dks += dk^ * kbar
+        float g[DH], dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) {
+          const float dkh = __uint_as_float(b[d]) * (1.f / kLog2e);
+          const float kbar = kraw[d] * kinv;
+          atomicAdd(&sRed[DH + d], dkh * kbar);
+          g[d] = dkh * sScale[DH + d];
+          dot = fmaf(g[d], kbar, dot);
+        }
+        uint4* dkp = reinterpret_cast<uint4*>(bp.dkv + ktok * p.ldkv + head * DH);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o8[e] = (g[8 * j + e] - kraw[8 * j + e] * kinv * dot) * kinv;
+          dkp[j] = make_uint4(pack_bf16(o8[0], o8[1]), pack_bf16(o8[2], o8[3]), pack_bf16(o8[4], o8[5]),
+                              pack_bf16(o8[6], o8[7]));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- dQ epilogue (thread = query row)
+  tc_fence_after();
+  for (int i = 0; i < ntiles; ++i) {
+    const int r = i * QT + tid;
+    bool valid = false;
+    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    uint32_t a[32];
+    tmem_ld_32x32(tdQ + i * DH + lane_off, a);
+    tmem_wait_ld();
+    if (valid) {
+      float qraw[DH];
+      const float qinv = load_head_row(p.q + tok * p.ldq + head * DH, qraw);
+      float g[DH], dot = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) {
+        const float dqh = __uint_as_float(a[d]) * kScale;  // d/dq^ = 8 * dz K^
+        const float qbar = qraw[d] * qinv;
+        atomicAdd(&sRed[d], dqh * qbar);
+        g[d] = dqh * sScale[d];
+        dot = fmaf(g[d], qbar, dot);
+      }
+      uint4* dqp = reinterpret_cast<uint4*>(bp.dq + tok * p.ldq + head * DH);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = (g[8 * j + e] - qraw[8 * j + e] * qinv * dot) * qinv;
+        dqp[j] = make_uint4(pack_bf16(o8[0], o8[1]), pack_bf16(o8[2], o8[3]), pack_bf16(o8[4], o8[5]),
+                            pack_bf16(o8[6], o8[7]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < DH) {
+    if (bp.dq_scale != nullptr) atomicAdd(bp.dq_scale + tid, sRed[tid]);
+    if (bp.dk_scale != nullptr) atomicAdd(bp.dk_scale + tid, sRed[DH + tid]);
+  }
+  if (has_bias && bp.dbias_table != nullptr)
+    for (int i = tid; i < tab_n; i += blockDim.x) atomicAdd(bp.dbias_table + (long long)head * tab_n + i, sdTab[i]);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+size_t bwd_smem_bytes(const AttnParams& p) {
+  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
+  return (size_t)p.r_pad * DH * 2 * 2 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 2 +
+         (size_t)tab_n * 4 * 2 + 128 * 4 + 64 + 16;
+}
+
+size_t fwd_smem_bytes(const AttnParams& p) {
+  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) + p.n : 0;
+  return (size_t)p.r_pad * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 64 + 16;
+}
+
+int fill_params(AttnParams& p, const ctclip_attn_desc* d, const char* what) {
+  if (d == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "%s: null descriptor", what);
+  if (d->dim_head != DH) return ctclip::fail(CTCLIP_E_SHAPE, "%s: dim_head must be 32 (got %d)", what, d->dim_head);
+  if (d->heads <= 0 || d->batch <= 0 || d->t <= 0 || d->h <= 0 || d->w <= 0)
+    return ctclip::fail(CTCLIP_E_SHAPE, "%s: empty problem", what);
+  p.heads = d->heads;
+  p.inner = d->heads * DH;
+  p.ldq = d->ldq; p.ldkv = d->ldkv; p.ldo = d->ldo;
+  if ((p.ldq % 8) || (p.ldkv % 8) || (p.ldo % 8)) return ctclip::fail(CTCLIP_E_ALIGN, "%s: row strides must be multiples of 8", what);
+  p.mode = d->temporal ? 1 : 0;
+  p.gh = d->h; p.gw = d->w; p.gt = d->t;
+  if (p.mode == 0) {
+    p.n = d->h * d->w; p.ns = 1; p.num_seqs = d->batch * d->t;
+  } else {
+    p.n = d->t;
+    if (p.n > QT) return ctclip::fail(CTCLIP_E_SHAPE, "%s: temporal sequences longer than 128 are not supported", what);
+    p.ns = QT / p.n; p.num_seqs = d->batch * d->h * d->w;
+  }
+  p.r_pad = (p.ns * p.n + 127) / 128 * 128;
+  p.q_scale = d->q_scale; p.k_scale = d->k_scale;
+  p.bias_table = d->temporal ? nullptr : d->bias_table;
+  p.bias_rowmax = d->temporal ? nullptr : d->bias_rowmax;
+  if (p.bias_table != nullptr && p.bias_rowmax == nullptr)
+    return ctclip::fail(CTCLIP_E_SHAPE, "%s: bias_rowmax is required with bias_table", what);
+  return ctclip::require_sm100();
+}
+
+}  // namespace
+
+extern "C" int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream) {
+  AttnParams p{};
+  int rc = fill_params(p, d, "attn_fwd");
+  if (rc) return rc;
+  p.q = (const __nv_bfloat16*)d->q; p.kv = (const __nv_bfloat16*)d->kv; p.o = (__nv_bfloat16*)d->o; p.lse = d->lse;
+  if (!p.q || !p.kv || !p.o) return ctclip::fail(CTCLIP_E_SHAPE, "attn_fwd: null pointer");
+  const size_t smem = fwd_smem_bytes(p);
+  if (smem > 227 * 1024) return ctclip::fail(CTCLIP_E_SHAPE, "attn_fwd: sequence too long for shared memory (%zu B)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
+  attn_fwd_kernel<<<(unsigned)(blocks * p.heads), 128, smem, (cudaStream_t)stream>>>(p);
+  return ctclip::check_launch("attn_fwd");
+}
+
+extern "C" int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream) {
+  AttnBwdParams bp{};
+  AttnParams& p = bp.f;
+  int rc = fill_params(p, d, "attn_bwd");
+  if (rc) return rc;
+  p.q = (const __nv_bfloat16*)d->q; p.kv = (const __nv_bfloat16*)d->kv; p.o = (__nv_bfloat16*)d->o; p.lse = d->lse;
+  bp.d_o = (const __nv_bfloat16*)d->d_o; bp.dq = (__nv_bfloat16*)d->dq; bp.dkv = (__nv_bfloat16*)d->dkv;
+  bp.dq_scale = d->dq_scale; bp.dk_scale = d->dk_scale; bp.dbias_table = d->dbias_table;
+  if (!p.q || !p.kv || !p.o || !p.lse || !bp.d_o || !bp.dq || !bp.dkv)
+    return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: null pointer");
+  if (p.r_pad / QT > 6) return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: sequences longer than 768 tokens are not supported");
+  const size_t smem = bwd_smem_bytes(p);
+  if (smem > 227 * 1024) return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: sequence too long for shared memory (%zu B)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
+  attn_bwd_kernel<<<(unsigned)(blocks * p.heads), 128, smem, (cudaStream_t)stream>>>(bp);
+  return ctclip::check_launch("attn_bwd");
+}

@@ -1,0 +1,186 @@
+// PEG: depth-wise causal 3x3x3 convolution over the token grid + residual (reference attention.py:56-84).
+//
+// Tokens stay in ONE canonical HBM layout (b, t, h, w, d) for the whole encoder; channels-last, so every tap is a
+// coalesced 128-bit load across channels. The reference feeds the temporal transformer a '(b h w) t d' tensor and
+// PEG *reshapes* (does not permute) it to (b, t, h, w, d) (attention.py:69-70 with ctvit.py:325-327): the stencil
+// then runs over a re-interpretation of the flat (h, w, t) order. `temporal=1` reproduces exactly that
+// re-interpretation through index arithmetic (valid for any t, h, w, not only the cubic production grid).
+#include "ptx.cuh"
+#include "ctclip_internal.h"
+
+namespace {
+
+struct PegGrid {
+  int t, h, w, temporal;
+};
+
+__device__ __forceinline__ void canon_to_virtual(int c, const PegGrid& g, int& vt, int& vh, int& vw) {
+  int f = c;
+  if (g.temporal) {
+    const int wi = c % g.w, hi = (c / g.w) % g.h, ti = c / (g.w * g.h);
+    f = (hi * g.w + wi) * g.t + ti;
+  }
+  vw = f % g.w;
+  vh = (f / g.w) % g.h;
+  vt = f / (g.w * g.h);
+}
+__device__ __forceinline__ int virtual_to_canon(int vt, int vh, int vw, const PegGrid& g) {
+  const int f = (vt * g.h + vh) * g.w + vw;
+  if (!g.temporal) return f;
+  const int ti = f % g.t, wi = (f / g.t) % g.w, hi = f / (g.t * g.w);
+  return (ti * g.h + hi) * g.w + wi;
+}
+
+// out[c] = in[c] + (bias) + sum_taps w27[tap] * in[nbr(c, tap)]
+//   flip = 0: forward stencil, neighbour offsets (kt-2, kh-1, kw-1)
+//   flip = 1: transposed stencil (gradient w.r.t. the input), offsets (2-kt, 1-kh, 1-kw), no bias
+__global__ void __launch_bounds__(256)
+peg_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w27,
+           const float* __restrict__ bias, int batch, PegGrid g, int dim, int flip,
+           __nv_bfloat16* __restrict__ out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int per_b = g.t * g.h * g.w;
+  const long long token = (long long)blockIdx.x * 8 + warp;
+  if (token >= (long long)batch * per_b) return;
+  const int v4 = blockIdx.y * 32 + lane;  // float4 channel index
+  if (v4 >= (dim >> 2)) return;
+  const int b = (int)(token / per_b);
+  const int c = (int)(token - (long long)b * per_b);
+  int vt, vh, vw;
+  canon_to_virtual(c, g, vt, vh, vw);
+  const float4* base = reinterpret_cast<const float4*>(in + (long long)b * per_b * dim);
+  const int dv = dim >> 2;
+  float4 acc = base[(long long)c * dv + v4];
+  if (!flip && bias != nullptr) {
+    const float4 bb = reinterpret_cast<const float4*>(bias)[v4];
+    acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+  }
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) {
+    const int nt = vt + (flip ? 2 - kt : kt - 2);
+    if (nt < 0 || nt >= g.t) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int nh = vh + (flip ? 1 - kh : kh - 1);
+      if (nh < 0 || nh >= g.h) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int nw = vw + (flip ? 1 - kw : kw - 1);
+        if (nw < 0 || nw >= g.w) continue;
+        const int nc = virtual_to_canon(nt, nh, nw, g);
+        const float4 xv = base[(long long)nc * dv + v4];
+        const float4 wv = reinterpret_cast<const float4*>(w27 + ((kt * 3 + kh) * 3 + kw) * dim)[v4];
+        acc.x = fmaf(wv.x, xv.x, acc.x); acc.y = fmaf(wv.y, xv.y, acc.y);
+        acc.z = fmaf(wv.z, xv.z, acc.z); acc.w = fmaf(wv.w, xv.w, acc.w);
+      }
+    }
+  }
+  reinterpret_cast<float4*>(out)[token * dv + v4] = acc;
+  if (out_bf16 != nullptr)
+    reinterpret_cast<uint2*>(out_bf16)[token * dv + v4] =
+        make_uint2(ptx::pack_bf16(acc.x, acc.y), ptx::pack_bf16(acc.z, acc.w));
+}
+
+// dw27[tap][ch] += sum_tokens dy[c][ch] * x[nbr(c,tap)][ch] ; dbias[ch] += sum_tokens dy[c][ch]
+__global__ void __launch_bounds__(128)
+peg_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw27,
+                 float* __restrict__ dbias, int batch, PegGrid g, int dim, int tokens_per_block) {
+  const int v4 = blockIdx.y * blockDim.x + threadIdx.x;
+  const int dv = dim >> 2;
+  if (v4 >= dv) return;
+  const int per_b = g.t * g.h * g.w;
+  const long long total = (long long)batch * per_b;
+  const long long t0 = (long long)blockIdx.x * tokens_per_block;
+  const long long t1 = min(total, t0 + tokens_per_block);
+  float4 acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long token = t0; token < t1; ++token) {
+    const int b = (int)(token / per_b);
+    const int c = (int)(token - (long long)b * per_b);
+    int vt, vh, vw;
+    canon_to_virtual(c, g, vt, vh, vw);
+    const float4 d = reinterpret_cast<const float4*>(dy)[token * dv + v4];
+    accb.x += d.x; accb.y += d.y; accb.z += d.z; accb.w += d.w;
+    const float4* base = reinterpret_cast<const float4*>(x + (long long)b * per_b * dim);
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      const int nt = vt + kt - 2;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int nh = vh + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int nw = vw + kw - 1;
+          if (nt < 0 || nt >= g.t || nh < 0 || nh >= g.h || nw < 0 || nw >= g.w) continue;
+          const int nc = virtual_to_canon(nt, nh, nw, g);
+          const float4 xv = base[(long long)nc * dv + v4];
+          float4& a = acc[(kt * 3 + kh) * 3 + kw];
+          a.x = fmaf(d.x, xv.x, a.x); a.y = fmaf(d.y, xv.y, a.y);
+          a.z = fmaf(d.z, xv.z, a.z); a.w = fmaf(d.w, xv.w, a.w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 27; ++i) {
+    float* p = dw27 + i * dim + 4 * v4;
+    atomicAdd(p + 0, acc[i].x); atomicAdd(p + 1, acc[i].y); atomicAdd(p + 2, acc[i].z); atomicAdd(p + 3, acc[i].w);
+  }
+  if (dbias != nullptr) {
+    float* p = dbias + 4 * v4;
+    atomicAdd(p + 0, accb.x); atomicAdd(p + 1, accb.y); atomicAdd(p + 2, accb.z); atomicAdd(p + 3, accb.w);
+  }
+}
+
+int check(int batch, int t, int h, int w, int dim, const char* what) {
+  if (batch <= 0 || t <= 0 || h <= 0 || w <= 0) return ctclip::fail(CTCLIP_E_SHAPE, "%s: empty grid", what);
+  if (dim % 4 || dim <= 0) return ctclip::fail(CTCLIP_E_SHAPE, "%s: dim must be a multiple of 4", what);
+  return ctclip::require_sm100();
+}
+
+}  // namespace
+
+extern "C" int ctclip_peg_fwd(const float* x, float* y, const float* w27, const float* bias, int batch, int t, int h,
+                              int w, int dim, int temporal, void* stream) {
+  int rc = check(batch, t, h, w, dim, "peg_fwd");
+  if (rc) return rc;
+  const long long tokens = (long long)batch * t * h * w;
+  dim3 grid((unsigned)((tokens + 7) / 8), (unsigned)((dim / 4 + 31) / 32));
+  peg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, w27, bias, batch, PegGrid{t, h, w, temporal}, dim, 0,
+                                                     nullptr);
+  return ctclip::check_launch("peg_fwd");
+}
+
+// dx = dy + conv^T(dy); optional bf16 copy of dx
+extern "C" int ctclip_peg_bwd_data(const float* dy, float* dx, void* dx_bf16, const float* w27, int batch, int t, int h,
+                                   int w, int dim, int temporal, void* stream) {
+  int rc = check(batch, t, h, w, dim, "peg_bwd_data");
+  if (rc) return rc;
+  const long long tokens = (long long)batch * t * h * w;
+  dim3 grid((unsigned)((tokens + 7) / 8), (unsigned)((dim / 4 + 31) / 32));
+  peg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, w27, nullptr, batch, PegGrid{t, h, w, temporal}, dim, 1,
+                                                     (__nv_bfloat16*)dx_bf16);
+  return ctclip::check_launch("peg_bwd_data");
+}
+
+// dw27 += ..., dbias += ...   (x = the PEG input, dy = gradient of the PEG output)
+extern "C" int ctclip_peg_bwd_weight(const float* x, const float* dy, float* dw27, float* dbias, int batch, int t, int h,
+                                     int w, int dim, int temporal, void* stream) {
+  int rc = check(batch, t, h, w, dim, "peg_bwd_weight");
+  if (rc) return rc;
+  const long long tokens = (long long)batch * t * h * w;
+  int tokens_per_block = 128;
+  long long blocks = (tokens + tokens_per_block - 1) / tokens_per_block;
+  const long long cap = (long long)ctclip::sm_count() * 8;
+  if (blocks > cap) {
+    tokens_per_block = (int)((tokens + cap - 1) / cap);
+    blocks = (tokens + tokens_per_block - 1) / tokens_per_block;
+  }
+  dim3 grid((unsigned)blocks, (unsigned)((dim / 4 + 127) / 128));
+  peg_wgrad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy, dw27, dbias, batch, PegGrid{t, h, w, temporal}, dim,
+                                                           tokens_per_block);
+  return ctclip::check_launch("peg_bwd_weight");
+}

@@ -1,0 +1,317 @@
+// Memory-bound row-wise kernels of the CT-CLIP hot path: LayerNorm forward/backward, GEGLU forward/backward,
+// fp32->bf16 casts. One warp per token row, 128-bit loads/stores, warp-shuffle reductions.
+// Reference operators: attention.py:28-35 (gamma-only LayerNorm), :39-52 (nn.LayerNorm + GEGLU), ctvit.py:173.
+#include "ptx.cuh"
+#include "ctclip_internal.h"
+
+namespace {
+
+constexpr int kMaxVec = 8;  // float4 per lane -> dim <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm fwd
+// y = (x - mean) * rstd * gamma (+ beta). Optional outputs: bf16 normalised, bf16 raw copy of x, fp32 normalised.
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int dim, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y_bf16,
+                     __nv_bfloat16* __restrict__ raw_bf16, float* __restrict__ y_f32) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = dim >> 2;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float4 v[kMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        v[j] = xr[i];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    const float mean = warp_sum(s) / dim;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+        float4 o;
+        o.x = (v[j].x - mean) * rstd * g.x;
+        o.y = (v[j].y - mean) * rstd * g.y;
+        o.z = (v[j].z - mean) * rstd * g.z;
+        o.w = (v[j].w - mean) * rstd * g.w;
+        if (beta != nullptr) {
+          const float4 b = reinterpret_cast<const float4*>(beta)[i];
+          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (y_f32 != nullptr) reinterpret_cast<float4*>(y_f32 + row * dim)[i] = o;
+        if (y_bf16 != nullptr) {
+          uint2 p;
+          p.x = ptx::pack_bf16(o.x, o.y);
+          p.y = ptx::pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(y_bf16 + row * dim)[i] = p;
+        }
+        if (raw_bf16 != nullptr) {
+          uint2 p;
+          p.x = ptx::pack_bf16(v[j].x, v[j].y);
+          p.y = ptx::pack_bf16(v[j].z, v[j].w);
+          reinterpret_cast<uint2*>(raw_bf16 + row * dim)[i] = p;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx_out = (add_in ? add_in : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy  (fp32 atomics, one per column per block)
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long rows, int dim,
+                     const float* __restrict__ gamma, float eps, const float* __restrict__ add_in,
+                     float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  extern __shared__ float red[];  // [2][dim]
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * warps_per_block;
+  const int nvec = dim >> 2;
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 acc_g[kMaxVec], acc_b[kMaxVec];
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) acc_g[j] = acc_b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * dim);
+    float4 v[kMaxVec], d[kMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        v[j] = xr[i];
+        d[j] = dr[i];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    const float mean = warp_sum(s) / dim;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+        // v <- xhat ; d stays dy ; accumulate parameter grads
+        v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd;
+        v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
+        acc_g[j].x += d[j].x * v[j].x; acc_g[j].y += d[j].y * v[j].y;
+        acc_g[j].z += d[j].z * v[j].z; acc_g[j].w += d[j].w * v[j].w;
+        acc_b[j].x += d[j].x; acc_b[j].y += d[j].y; acc_b[j].z += d[j].z; acc_b[j].w += d[j].w;
+        d[j].x *= g.x; d[j].y *= g.y; d[j].z *= g.z; d[j].w *= g.w;  // g = dy * gamma
+        sg += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+        sgx += (d[j].x * v[j].x + d[j].y * v[j].y) + (d[j].z * v[j].z + d[j].w * v[j].w);
+      }
+    }
+    const float mg = warp_sum(sg) / dim, mgx = warp_sum(sgx) / dim;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float4 o;
+        o.x = rstd * (d[j].x - mg - v[j].x * mgx);
+        o.y = rstd * (d[j].y - mg - v[j].y * mgx);
+        o.z = rstd * (d[j].z - mg - v[j].z * mgx);
+        o.w = rstd * (d[j].w - mg - v[j].w * mgx);
+        if (add_in != nullptr) {
+          const float4 a = reinterpret_cast<const float4*>(add_in + row * dim)[i];
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        if (dx_out != nullptr) reinterpret_cast<float4*>(dx_out + row * dim)[i] = o;
+        if (dx_bf16 != nullptr) {
+          uint2 p;
+          p.x = ptx::pack_bf16(o.x, o.y);
+          p.y = ptx::pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_bf16 + row * dim)[i] = p;
+        }
+      }
+    }
+  }
+  // block reduction of the parameter gradients through shared memory, then one atomic per column
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      atomicAdd(&red[4 * i + 0], acc_g[j].x); atomicAdd(&red[4 * i + 1], acc_g[j].y);
+      atomicAdd(&red[4 * i + 2], acc_g[j].z); atomicAdd(&red[4 * i + 3], acc_g[j].w);
+      atomicAdd(&red[dim + 4 * i + 0], acc_b[j].x); atomicAdd(&red[dim + 4 * i + 1], acc_b[j].y);
+      atomicAdd(&red[dim + 4 * i + 2], acc_b[j].z); atomicAdd(&red[dim + 4 * i + 3], acc_b[j].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    if (dgamma != nullptr) atomicAdd(dgamma + i, red[i]);
+    if (dbeta != nullptr) atomicAdd(dbeta + i, red[dim + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ GEGLU
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float g) {
+  return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
+}
+
+// h: [rows][2*ld_half] bf16 = [x | gate];  u: [rows][ld_half] bf16 = x * gelu(gate)
+__global__ void __launch_bounds__(256)
+geglu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ u, long long rows, int half_vec /* ld_half/8 */) {
+  const long long total = rows * half_vec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / half_vec;
+    const int c = (int)(idx - row * half_vec);
+    const uint4 xv = h[row * 2 * half_vec + c];
+    const uint4 gv = h[row * 2 * half_vec + half_vec + c];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = ptx::pack_bf16(ptx::bf16_lo(xs[k]) * gelu_erf(ptx::bf16_lo(gs[k])),
+                            ptx::bf16_hi(xs[k]) * gelu_erf(ptx::bf16_hi(gs[k])));
+    u[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// dh = [du * gelu(gate) | du * x * gelu'(gate)]
+__global__ void __launch_bounds__(256)
+geglu_bwd_kernel(const uint4* __restrict__ h, const uint4* __restrict__ du, uint4* __restrict__ dh, long long rows,
+                 int half_vec) {
+  const long long total = rows * half_vec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / half_vec;
+    const int c = (int)(idx - row * half_vec);
+    const uint4 xv = h[row * 2 * half_vec + c];
+    const uint4 gv = h[row * 2 * half_vec + half_vec + c];
+    const uint4 dv = du[idx];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w},
+                   ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t ox[4], og[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = ptx::bf16_lo(xs[k]), x1 = ptx::bf16_hi(xs[k]);
+      const float g0 = ptx::bf16_lo(gs[k]), g1 = ptx::bf16_hi(gs[k]);
+      const float d0 = ptx::bf16_lo(ds[k]), d1 = ptx::bf16_hi(ds[k]);
+      ox[k] = ptx::pack_bf16(d0 * gelu_erf(g0), d1 * gelu_erf(g1));
+      og[k] = ptx::pack_bf16(d0 * x0 * gelu_erf_grad(g0), d1 * x1 * gelu_erf_grad(g1));
+    }
+    dh[row * 2 * half_vec + c] = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+    dh[row * 2 * half_vec + half_vec + c] = make_uint4(og[0], og[1], og[2], og[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ casts
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(ptx::pack_bf16(v.x, v.y), ptx::pack_bf16(v.z, v.w));
+  }
+}
+
+int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)ctclip::sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" int ctclip_layernorm_fwd(const float* x, long long rows, int dim, const float* gamma, const float* beta,
+                                    float eps, void* y_bf16, void* raw_bf16, float* y_f32, void* stream) {
+  if (rows <= 0) return CTCLIP_OK;
+  if (dim % 4 || dim > kMaxVec * 128 || dim <= 0)
+    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_fwd: dim must be a multiple of 4 and <= %d", kMaxVec * 128);
+  if (x == nullptr || gamma == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_fwd: null pointer");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, rows, dim, gamma, beta, eps, (__nv_bfloat16*)y_bf16, (__nv_bfloat16*)raw_bf16, y_f32);
+  return ctclip::check_launch("layernorm_fwd");
+}
+
+extern "C" int ctclip_layernorm_bwd(const float* dy, const float* x, long long rows, int dim, const float* gamma,
+                                    float eps, const float* add_in, float* dx_out, void* dx_bf16, float* dgamma,
+                                    float* dbeta, void* stream) {
+  if (rows <= 0) return CTCLIP_OK;
+  if (dim % 4 || dim > kMaxVec * 128 || dim <= 0)
+    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: dim must be a multiple of 4 and <= %d", kMaxVec * 128);
+  if (dy == nullptr || x == nullptr || gamma == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: null pointer");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  long long blocks = (rows + 63) / 64;  // each warp walks >= 8 rows so the column reductions amortise
+  const long long cap = (long long)ctclip::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  layernorm_bwd_kernel<<<(int)blocks, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      dy, x, rows, dim, gamma, eps, add_in, dx_out, (__nv_bfloat16*)dx_bf16, dgamma, dbeta);
+  return ctclip::check_launch("layernorm_bwd");
+}
+
+extern "C" int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_half, void* stream) {
+  if (rows <= 0) return CTCLIP_OK;
+  if (ld_half % 8 || ld_half <= 0) return ctclip::fail(CTCLIP_E_ALIGN, "geglu_fwd: ld_half must be a multiple of 8");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  geglu_fwd_kernel<<<grid_for(rows * (ld_half / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)h, (uint4*)u, rows, ld_half / 8);
+  return ctclip::check_launch("geglu_fwd");
+}
+
+extern "C" int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, int ld_half, void* stream) {
+  if (rows <= 0) return CTCLIP_OK;
+  if (ld_half % 8 || ld_half <= 0) return ctclip::fail(CTCLIP_E_ALIGN, "geglu_bwd: ld_half must be a multiple of 8");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  geglu_bwd_kernel<<<grid_for(rows * (ld_half / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)h, (const uint4*)du, (uint4*)dh, rows, ld_half / 8);
+  return ctclip::check_launch("geglu_bwd");
+}
+
+extern "C" int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+  if (n <= 0) return CTCLIP_OK;
+  if (n % 4) return ctclip::fail(CTCLIP_E_ALIGN, "cast_f32_bf16: n must be a multiple of 4");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y, n / 4);
+  return ctclip::check_launch("cast_f32_bf16");
+}

@@ -76,3 +76,137 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_t: bool = False, b_t: bool = Fal
     d.splits = splits
     _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16")
     return out
+
+
+def _call(name: str, *args):
+    fn = getattr(_lib.lib(), name)
+    _lib.check(fn(*args), name)
+
+
+def _f(x: float):
+    return C.c_float(x)
+
+
+def _ll(x: int):
+    return C.c_longlong(x)
+
+
+def layernorm_fwd(x, gamma, beta=None, *, eps=1e-5, want_bf16=True, want_raw_bf16=False, want_f32=False):
+    """x fp32 [rows, dim] -> (y_bf16 | None, raw_bf16 | None, y_f32 | None)"""
+    _req(x, torch.float32, "layernorm_fwd.x")
+    rows, dim = x.shape
+    assert x.is_contiguous() and gamma.dtype == torch.float32
+    y = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    raw = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16) if want_raw_bf16 else None
+    yf = torch.empty((rows, dim), device=x.device, dtype=torch.float32) if want_f32 else None
+    _call("ctclip_layernorm_fwd", _ptr(x), _ll(rows), dim, _ptr(gamma), _ptr(beta), _f(eps), _ptr(y), _ptr(raw),
+          _ptr(yf), _stream())
+    return y, raw, yf
+
+
+def layernorm_bwd(dy, x, gamma, *, eps=1e-5, add_in=None, dgamma=None, dbeta=None, want_bf16=False, out=None):
+    """returns (dx fp32, dx_bf16 | None); dgamma / dbeta are accumulated in place"""
+    _req(dy, torch.float32, "layernorm_bwd.dy")
+    _req(x, torch.float32, "layernorm_bwd.x")
+    rows, dim = x.shape
+    assert dy.is_contiguous() and x.is_contiguous()
+    dx = out if out is not None else torch.empty_like(x)
+    dxb = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _call("ctclip_layernorm_bwd", _ptr(dy), _ptr(x), _ll(rows), dim, _ptr(gamma), _f(eps), _ptr(add_in), _ptr(dx),
+          _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _stream())
+    return dx, dxb
+
+
+def geglu_fwd(h):
+    _req(h, torch.bfloat16, "geglu_fwd.h")
+    rows, two = h.shape
+    assert h.is_contiguous() and two % 16 == 0
+    u = torch.empty((rows, two // 2), device=h.device, dtype=torch.bfloat16)
+    _call("ctclip_geglu_fwd", _ptr(h), _ptr(u), _ll(rows), two // 2, _stream())
+    return u
+
+
+def geglu_bwd(h, du):
+    _req(h, torch.bfloat16, "geglu_bwd.h")
+    _req(du, torch.bfloat16, "geglu_bwd.du")
+    rows, two = h.shape
+    assert h.is_contiguous() and du.is_contiguous() and du.shape == (rows, two // 2)
+    dh = torch.empty_like(h)
+    _call("ctclip_geglu_bwd", _ptr(h), _ptr(du), _ptr(dh), _ll(rows), two // 2, _stream())
+    return dh
+
+
+def cast_bf16(x):
+    _req(x, torch.float32, "cast_bf16.x")
+    assert x.is_contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _call("ctclip_cast_f32_bf16", _ptr(x), _ptr(y), _ll(x.numel()), _stream())
+    return y
+
+
+def peg_fwd(x, w27, bias, grid, temporal: bool):
+    """x fp32 [b*t*h*w, dim] canonical -> x + dwconv(x) + bias"""
+    _req(x, torch.float32, "peg_fwd.x")
+    b, t, h, w = grid
+    y = torch.empty_like(x)
+    _call("ctclip_peg_fwd", _ptr(x), _ptr(y), _ptr(w27), _ptr(bias), b, t, h, w, x.shape[-1], int(temporal), _stream())
+    return y
+
+
+def peg_bwd_data(dy, w27, grid, temporal: bool, want_bf16=False):
+    _req(dy, torch.float32, "peg_bwd_data.dy")
+    b, t, h, w = grid
+    dx = torch.empty_like(dy)
+    dxb = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16) if want_bf16 else None
+    _call("ctclip_peg_bwd_data", _ptr(dy), _ptr(dx), _ptr(dxb), _ptr(w27), b, t, h, w, dy.shape[-1], int(temporal),
+          _stream())
+    return dx, dxb
+
+
+def peg_bwd_weight(x, dy, dw27, dbias, grid, temporal: bool):
+    b, t, h, w = grid
+    _call("ctclip_peg_bwd_weight", _ptr(x), _ptr(dy), _ptr(dw27), _ptr(dbias), b, t, h, w, x.shape[-1], int(temporal),
+          _stream())
+
+
+def _attn_desc(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table, bias_rowmax):
+    b, t, h, w = grid
+    d = _lib.AttnDesc()
+    d.batch, d.t, d.h, d.w, d.heads, d.dim_head, d.temporal = b, t, h, w, heads, 32, int(temporal)
+    d.q, d.ldq = q.data_ptr(), q.stride(0)
+    d.kv, d.ldkv = kv.data_ptr(), kv.stride(0)
+    d.q_scale, d.k_scale = q_scale.data_ptr(), k_scale.data_ptr()
+    if bias_table is not None and not temporal:
+        d.bias_table, d.bias_rowmax = bias_table.data_ptr(), bias_rowmax.data_ptr()
+    return d
+
+
+def attn_fwd(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table=None, bias_rowmax=None):
+    """q bf16 [tokens, heads*32], kv bf16 [tokens, 2*heads*32] -> (o bf16 [tokens, heads*32], lse fp32 [tokens, heads])"""
+    _req(q, torch.bfloat16, "attn_fwd.q")
+    _req(kv, torch.bfloat16, "attn_fwd.kv")
+    tokens = q.shape[0]
+    o = torch.empty((tokens, heads * 32), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((tokens, heads), device=q.device, dtype=torch.float32)
+    d = _attn_desc(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table, bias_rowmax)
+    d.o, d.ldo, d.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
+    _call("ctclip_attn_fwd", C.byref(d), _stream())
+    return o, lse
+
+
+def attn_bwd(q, kv, o, lse, d_o, grid, heads, temporal, q_scale, k_scale, dq_scale, dk_scale, bias_table=None,
+             bias_rowmax=None, dbias_table=None):
+    """returns (dq bf16, dkv bf16); dq_scale / dk_scale / dbias_table accumulated in place"""
+    tokens = q.shape[0]
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    d = _attn_desc(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table, bias_rowmax)
+    d.o, d.ldo, d.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
+    d.d_o = d_o.data_ptr()
+    assert d_o.stride(0) == o.stride(0) and dq.stride(0) == q.stride(0) and dkv.stride(0) == kv.stride(0)
+    d.dq, d.dkv = dq.data_ptr(), dkv.data_ptr()
+    d.dq_scale, d.dk_scale = dq_scale.data_ptr(), dk_scale.data_ptr()
+    if dbias_table is not None and not temporal:
+        d.dbias_table = dbias_table.data_ptr()
+    _call("ctclip_attn_bwd", C.byref(d), _stream())
+    return dq, dkv

@@ -56,6 +56,55 @@ typedef struct ctclip_gemm_desc {
 } ctclip_gemm_desc;
 int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise memory-bound kernels (one warp per token row, 128-bit accesses, shuffle reductions).
+ * layernorm_fwd: attention.py:28-35 (gamma-only; beta=NULL), attention.py:47 / ctvit.py:173 (nn.LayerNorm, eps 1e-5).
+ *   y = (x-mean)*rstd*gamma (+beta); any of y_bf16 / raw_bf16 (bf16 copy of x) / y_f32 may be NULL.
+ * layernorm_bwd: dx_out = (add_in?) + dLN(dy); optional bf16 copy; dgamma/dbeta accumulated with fp32 atomics.
+ * geglu: attention.py:39-42 on a [rows][2*ld_half] bf16 buffer laid out [x | gate]. */
+int ctclip_layernorm_fwd(const float* x, long long rows, int dim, const float* gamma, const float* beta, float eps,
+                         void* y_bf16, void* raw_bf16, float* y_f32, void* stream);
+int ctclip_layernorm_bwd(const float* dy, const float* x, long long rows, int dim, const float* gamma, float eps,
+                         const float* add_in, float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_half, void* stream);
+int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, int ld_half, void* stream);
+int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PEG (attention.py:56-84): y = x + dwconv3x3x3_causal(x) + bias on tokens kept in the canonical (b,t,h,w,d) layout.
+ * w27 is the depth-wise weight re-laid as [27][dim] (tap = (kt*3+kh)*3+kw). temporal=1 reproduces the reference's
+ * reshape of the '(b h w) t d' tensor to (b,t,h,w,d) (ctvit.py:325-327) by index arithmetic. */
+int ctclip_peg_fwd(const float* x, float* y, const float* w27, const float* bias, int batch, int t, int h, int w,
+                   int dim, int temporal, void* stream);
+int ctclip_peg_bwd_data(const float* dy, float* dx, void* dx_bf16, const float* w27, int batch, int t, int h, int w,
+                        int dim, int temporal, void* stream);
+int ctclip_peg_bwd_weight(const float* x, const float* dy, float* dw27, float* dbias, int batch, int t, int h, int w,
+                          int dim, int temporal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cosine-sim attention (attention.py:127-181), dim_head 32, tcgen05/TMEM. Tokens in canonical (b,t,h,w) order.
+ *   q  [tokens][ldq]  bf16 (heads*32 used columns), kv [tokens][ldkv] bf16 (k | v), o [tokens][ldo] bf16,
+ *   lse [tokens][heads] fp32 (log2 domain). temporal=0: sequences are frames of h*w tokens, additive bias from
+ *   bias_table [heads][(2h-1)(2w-1)] (entry (dy+h-1)*(2w-1)+(dx+w-1), d = query - key) with bias_rowmax [heads][h*w]
+ *   = max over keys; temporal=1: sequences are the t tokens of one (b,h,w) column, no bias.
+ * Backward: dq [tokens][ldq], dkv [tokens][ldkv] bf16 (gradients w.r.t. the un-normalised projections),
+ *   dq_scale/dk_scale [32] and dbias_table [heads][(2h-1)(2w-1)] accumulated with fp32 atomics. */
+typedef struct ctclip_attn_desc {
+  int batch, t, h, w, heads, dim_head, temporal;
+  const void* q; int ldq;
+  const void* kv; int ldkv;
+  void* o; int ldo;
+  float* lse;
+  const float* q_scale; const float* k_scale;
+  const float* bias_table; const float* bias_rowmax;
+  /* backward only */
+  const void* d_o;
+  void* dq; void* dkv;
+  float* dq_scale; float* dk_scale; float* dbias_table;
+} ctclip_attn_desc;
+int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream);
+int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
