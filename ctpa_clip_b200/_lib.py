@@ -27,6 +27,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("atomic", C.c_int),
         ("splits", C.c_int),
+        ("top2_out", C.c_void_p),
     ]
 
 
@@ -72,4 +73,18 @@ class AttnDesc(C.Structure):
         ("d_o", C.c_void_p),
         ("dq", C.c_void_p), ("dkv", C.c_void_p),
         ("dq_scale", C.c_void_p), ("dk_scale", C.c_void_p), ("dbias_table", C.c_void_p),
+    ]
+
+
+class PrepDesc(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p), ("out", C.c_void_p),
+        ("batch", C.c_int), ("in_is_i16", C.c_int),
+        ("slope", C.c_double), ("intercept", C.c_double),
+        ("D", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("stride_d", C.c_longlong), ("stride_h", C.c_longlong), ("stride_w", C.c_longlong),
+        ("stride_batch", C.c_longlong),
+        ("oD", C.c_int), ("oH", C.c_int), ("oW", C.c_int),
+        ("tD", C.c_int), ("tH", C.c_int), ("tW", C.c_int),
+        ("pad_value", C.c_float),
     ]

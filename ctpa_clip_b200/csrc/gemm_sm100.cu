@@ -46,7 +46,7 @@ struct GemmKernelParams {
   const float* resid;
   long long ldr;
   float alpha;
-  int gelu_glu;  // reserved
+  float4* top2;  // non-null: per (row, n-tile) best two (value, column) instead of storing C
 };
 
 // ---------------------------------------------------------------- epilogue helpers
@@ -239,6 +239,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m_t * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      if (p.top2 != nullptr) {
+        // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column)
+        float v1 = -INFINITY, v2 = -INFINITY;
+        int i1 = -1, i2 = -1;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n_t * BN + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n_t * BN + c + j;
+            const float x = __uint_as_float(r[j]);
+            if (col < p.N) {
+              if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = col; }
+              else if (x > v2) { v2 = x; i2 = col; }
+            }
+          }
+        }
+        if (row < p.M)
+          p.top2[(long long)row * p.n_tiles + n_t] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         if (n_t * BN + c >= p.N) break;  // warp-uniform
@@ -308,7 +331,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   if ((d->lda % 8) || (d->ldb % 8)) return ctclip::fail(CTCLIP_E_ALIGN, "gemm: lda/ldb must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(d->A) & 15) || (reinterpret_cast<uintptr_t>(d->B) & 15))
     return ctclip::fail(CTCLIP_E_ALIGN, "gemm: A/B must be 16-byte aligned");
-  if (d->A == nullptr || d->B == nullptr || d->C == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: null pointer");
+  if (d->A == nullptr || d->B == nullptr || (d->C == nullptr && d->top2_out == nullptr)) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: null pointer");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
 
@@ -337,6 +360,8 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   kp.C = d->C; kp.ldc = d->ldc; kp.c_is_f32 = d->c_is_f32; kp.atomic = d->atomic;
   kp.bias = d->bias; kp.resid = d->resid; kp.ldr = d->ldr;
   kp.alpha = d->alpha;
+  kp.top2 = reinterpret_cast<float4*>(d->top2_out);
+  if (kp.top2 != nullptr && kp.splits > 1) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: top2 epilogue cannot be split-K");
   if (kp.splits > 1 && (d->bias || d->resid))
     return ctclip::fail(CTCLIP_E_SHAPE, "gemm: bias/resid not supported with split-K");
 
@@ -360,3 +385,5 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
     default: return launch<256, true, true>(d, kp, ta, tb, grid, stream);
   }
 }
+
+extern "C" int ctclip_gemm_tile_n(int N) { return (N <= 128) ? 128 : 256; }

@@ -315,3 +315,32 @@ extern "C" int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* 
   cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y, n / 4);
   return ctclip::check_launch("cast_f32_bf16");
 }
+
+namespace {
+// out[c] += sum_rows x[row][c]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int dim, float* __restrict__ out, int rows_per_block) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += x[r * dim + c];
+    atomicAdd(out + c, s);
+  }
+}
+}  // namespace
+
+extern "C" int ctclip_colsum(const float* x, long long rows, int dim, float* out, void* stream) {
+  if (rows <= 0 || dim <= 0) return CTCLIP_OK;
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  int rpb = 64;
+  long long blocks = (rows + rpb - 1) / rpb;
+  const long long cap = (long long)ctclip::sm_count() * 8;
+  if (blocks > cap) {
+    rpb = (int)((rows + cap - 1) / cap);
+    blocks = (rows + rpb - 1) / rpb;
+  }
+  colsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, out, rpb);
+  return ctclip::check_launch("colsum");
+}

@@ -1,0 +1,42 @@
+"""GPU mirror of the numeric core of CTPA_CLIP/data_prep/preprocess_train.py (== preprocess_test.py) and of the
+resampling / crop / pad in ct_clip/data.py. File I/O (NIfTI, npz, CSV) stays with the caller.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+
+TARGET_SPACING = (1.5, 0.75, 0.75)          # (z, x, y) — preprocess_train.py:92-97
+TARGET_SHAPE = (240, 480, 480)              # (d, h, w) — data.py:153 target_shape (480,480,240) permuted
+
+
+def resize_shape(shape, current_spacing, target_spacing):
+    """new_shape[i] = int(shape[i] * current[i] / target[i]) in python float64 (preprocess_train.py:33-39)"""
+    return [int(shape[i] * (current_spacing[i] / target_spacing[i])) for i in range(len(shape))]
+
+
+def resize_array(array, current_spacing, target_spacing):
+    """Same signature / return type as the reference resize_array (preprocess_train.py:31-42, ct_clip/data.py:15-40):
+    (1, 1, D, H, W) float tensor -> (1, 1, D', H', W') np.ndarray, trilinear, align_corners=False — computed on the GPU."""
+    assert array.dim() == 5 and array.shape[0] == 1 and array.shape[1] == 1
+    new_shape = resize_shape(array.shape[2:], current_spacing, target_spacing)
+    vol = array[0].to(device="cuda", dtype=torch.float32).contiguous()
+    out = ops.prep_resample(vol, new_shape, layout="dhw")
+    return out[None].cpu().numpy()
+
+
+def preprocess_volumes(raw, slope, intercept, xy_spacing, z_spacing, target_spacing=TARGET_SPACING, target_shape=None):
+    """process_file arithmetic for a batch of same-shape raw scans (preprocess_train.py:99-109).
+    raw: int16 CUDA tensor [b, H, W, N] in NIfTI array order. Returns fp32 [b, D', H', W'] (or target_shape with the
+    data.py:155-190 centre-crop / pad(-1) applied)."""
+    b, H, W, N = raw.shape
+    new_shape = resize_shape((N, H, W), (z_spacing, xy_spacing, xy_spacing), target_spacing)
+    return ops.prep_resample(raw, new_shape, hu=(slope, intercept), layout="hwn", target=target_shape)
+
+
+def to_training_volume(vol_dhw, target_shape=TARGET_SHAPE, pad_value=-1.0):
+    """centre crop / pad(-1) of an already normalised (b, D, H, W) fp32 volume to (b, 1, 240, 480, 480) (data.py:155-190)"""
+    out = ops.prep_resample(vol_dhw.contiguous(), vol_dhw.shape[1:], layout="dhw", target=target_shape, pad_value=pad_value)
+    return out[:, None]

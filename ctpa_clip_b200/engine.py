@@ -1,0 +1,270 @@
+"""Functional forward / backward of the CTViT encoder on the sm_100a kernels (libctclip_sm100.so).
+
+Tokens stay in one canonical HBM layout [(b t h w), d] for the whole encoder: fp32 residual stream, bf16 tensor-core
+operands. The spatial / temporal re-arrangements of the reference (ctvit.py:315,321,325,329) never materialise — the
+PEG and attention kernels do the index arithmetic. Every function cites the reference lines it replaces.
+
+`encoder_forward` returns the output plus a `ctx` object with the saved activations; `encoder_backward` consumes it
+and returns gradients keyed by the reference's parameter names. `EncodeFunction` wraps both for torch.autograd.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def ff_pad(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class LayerWeights:
+    """bf16 / re-laid-out operand copies of one transformer layer (derived caches, never saved)."""
+
+    def __init__(self, peg, attn, ff, dim):
+        inner2, _ = ff[1].weight.shape
+        self.ffi = inner2 // 2
+        self.ffp = ff_pad(self.ffi)
+        dev = ff[1].weight.device
+        self.w27 = peg.dsconv.weight.detach().reshape(dim, 27).t().contiguous()           # [27, dim] fp32
+        self.peg_bias = peg.dsconv.bias.detach()
+        self.gamma = attn.norm.gamma.detach()
+        self.wq = attn.to_q.weight.detach().to(torch.bfloat16).contiguous()              # [inner, dim]
+        self.wkv = attn.to_kv.weight.detach().to(torch.bfloat16).contiguous()            # [2 inner, dim]
+        self.wout = attn.to_out.weight.detach().to(torch.bfloat16).contiguous()          # [dim, inner]
+        self.q_scale = attn.q_scale.detach()
+        self.k_scale = attn.k_scale.detach()
+        self.ff_g = ff[0].weight.detach()
+        self.ff_b = ff[0].bias.detach()
+        w1 = ff[1].weight.detach()
+        w1p = torch.zeros(2 * self.ffp, dim, device=dev, dtype=torch.bfloat16)           # [x rows | gate rows], zero padded
+        w1p[: self.ffi] = w1[: self.ffi]
+        w1p[self.ffp: self.ffp + self.ffi] = w1[self.ffi:]
+        self.w1p = w1p
+        w2p = torch.zeros(dim, self.ffp, device=dev, dtype=torch.bfloat16)
+        w2p[:, : self.ffi] = ff[4].weight.detach()
+        self.w2p = w2p
+
+
+class EncoderWeights:
+    def __init__(self, vit):
+        dim = vit.dim
+        pe = vit.to_patch_emb
+        self.dim = dim
+        self.heads = vit.heads
+        self.pt, self.ps = vit.temporal_patch_size, vit.patch_size[0]
+        self.pdim = pe[1].weight.numel()
+        self.pe_g, self.pe_b = pe[1].weight.detach(), pe[1].bias.detach()
+        kp = ff_pad(self.pdim)
+        w = torch.zeros(dim, kp, device=pe[2].weight.device, dtype=torch.bfloat16)
+        w[:, : self.pdim] = pe[2].weight.detach()
+        self.pe_w = w
+        self.pe_bias = pe[2].bias.detach()
+        self.pe_g2, self.pe_b2 = pe[3].weight.detach(), pe[3].bias.detach()
+        self.spatial = [LayerWeights(l[0], l[1], l[3], dim) for l in vit.enc_spatial_transformer.layers]
+        self.temporal = [LayerWeights(l[0], l[1], l[3], dim) for l in vit.enc_temporal_transformer.layers]
+        self.s_out = vit.enc_spatial_transformer.norm_out.gamma.detach()
+        self.t_out = vit.enc_temporal_transformer.norm_out.gamma.detach()
+        embed = vit.vq._codebook.embed.detach()[0]
+        self.embed = embed
+        self.embed_n, self.embed_nb, _ = ops.l2norm_rows(embed.contiguous(), want_f32=True, want_bf16=True)
+
+
+class LayerCtx:
+    __slots__ = ("x", "x1", "x2", "xn", "xr", "q", "kv", "o", "lse", "xf", "h1", "u")
+
+
+class EncoderCtx:
+    pass
+
+
+# ------------------------------------------------------------------------------------------------ forward
+def layer_forward(x, L: LayerWeights, grid, heads, temporal, tab, rowmax, save: bool):
+    """x = peg(x)+x ; x = attn(x)+x ; x = ff(x)+x   (attention.py:322-331) on canonical fp32 tokens [T, dim]"""
+    x1 = ops.peg_fwd(x, L.w27, L.peg_bias, grid, temporal)                                   # attention.py:324
+    xn, xr, _ = ops.layernorm_fwd(x1, L.gamma, None, want_bf16=True, want_raw_bf16=True)     # :141 (q side), :139 (raw kv)
+    q = ops.gemm(xn, L.wq)                                                                   # :143 to_q
+    kv = ops.gemm(xr, L.wkv)                                                                 # :143 to_kv
+    o, lse = ops.attn_fwd(q, kv, grid, heads, temporal, L.q_scale, L.k_scale, tab, rowmax)   # :145-180
+    x2 = ops.gemm(o, L.wout, out_dtype=torch.float32, resid=x1)                              # :181 + residual :326
+    xf, _, _ = ops.layernorm_fwd(x2, L.ff_g, L.ff_b)                                         # :47
+    h1 = ops.gemm(xf, L.w1p)                                                                 # :48
+    u = ops.geglu_fwd(h1)                                                                    # :39-42
+    x3 = ops.gemm(u, L.w2p, out_dtype=torch.float32, resid=x2)                               # :51 + residual :331
+    c = None
+    if save:
+        c = LayerCtx()
+        c.x, c.x1, c.x2, c.xn, c.xr, c.q, c.kv, c.o, c.lse, c.xf, c.h1, c.u = x, x1, x2, xn, xr, q, kv, o, lse, xf, h1, u
+    return x3, c
+
+
+def bias_tables(vit, h, w, device):
+    """(2h-1)(2w-1) relative-position bias table per head and its per-query-position maximum over keys"""
+    tab = vit.spatial_rel_pos_bias.table(h, w, device)                    # attention.py:257-276 on distinct offsets
+    from .ct_clip.attention import pair_index
+    idx = pair_index(h, w, device)
+    rowmax = tab[:, idx].amax(dim=-1).contiguous()
+    return tab, rowmax
+
+
+def patch_embed_forward(W: EncoderWeights, video, save: bool):
+    """to_patch_emb: patchify + LN + Linear + LN (ctvit.py:169-174) -> fp32 tokens [T, dim]"""
+    a = ops.patch_ln_fwd(video, W.pe_g, W.pe_b, W.pt, W.ps)
+    y0 = ops.gemm(a, W.pe_w, out_dtype=torch.float32, bias=W.pe_bias)
+    _, _, x = ops.layernorm_fwd(y0, W.pe_g2, W.pe_b2, want_bf16=False, want_f32=True)
+    return x, (a, y0) if save else None
+
+
+def encoder_forward(vit, W: EncoderWeights, video, save: bool, tab=None, rowmax=None):
+    """CTViT.to_patch_emb + CTViT.encode (ctvit.py:409,417 / 306-331). Returns (tokens fp32 [T, dim], ctx)."""
+    b, _, f, hh, ww = video.shape
+    t, h, w = f // W.pt, hh // W.ps, ww // W.ps
+    grid = (b, t, h, w)
+    ctx = EncoderCtx()
+    ctx.grid, ctx.video = grid, video
+    x, ctx.pe = patch_embed_forward(W, video, save)
+    if tab is None:
+        with torch.no_grad():
+            tab, rowmax = bias_tables(vit, h, w, video.device)
+    ctx.tab, ctx.rowmax = tab, rowmax
+    ctx.spatial, ctx.temporal = [], []
+    for L in W.spatial:
+        x, c = layer_forward(x, L, grid, W.heads, False, tab, rowmax, save)
+        ctx.spatial.append(c)
+    ctx.s_pre = x if save else None
+    _, _, x = ops.layernorm_fwd(x, W.s_out, None, want_bf16=False, want_f32=True)          # norm_out, attention.py:333
+    for L in W.temporal:
+        x, c = layer_forward(x, L, grid, W.heads, True, None, None, save)
+        ctx.temporal.append(c)
+    ctx.t_pre = x if save else None
+    _, _, x = ops.layernorm_fwd(x, W.t_out, None, want_bf16=False, want_f32=True)
+    return x, ctx
+
+
+def vq_forward(W: EncoderWeights, tokens, stats=None):
+    """cosine-sim nearest code (ctvit.py:427): returns (indices int32 [T], inv_norm [T])"""
+    _, xb, inv = ops.l2norm_rows(tokens, want_bf16=True)
+    top2, tile_n = ops.gemm_top2(xb, W.embed_nb)
+    idx = ops.vq_finalize(top2, tile_n, tokens, W.embed_n, stats=stats)
+    return idx, inv
+
+
+# ------------------------------------------------------------------------------------------------ backward
+class GradStore:
+    """fp32 accumulators in kernel layout, converted to reference parameter shapes at the end"""
+
+    def __init__(self, device):
+        self.device = device
+        self.g = {}
+
+    def zeros(self, name, shape):
+        t = torch.zeros(shape, device=self.device, dtype=torch.float32)
+        self.g[name] = t
+        return t
+
+
+def layer_backward(g, c: LayerCtx, L: LayerWeights, grid, heads, temporal, tab, rowmax, dtab, gs: GradStore, prefix, dim):
+    """gradient of one [PEG, attention, feed-forward] layer; g = dL/dx3 fp32 [T, dim]; returns dL/dx"""
+    inner = L.wq.shape[0]
+    g_bf = ops.cast_bf16(g)
+    # ---- feed-forward (attention.py:44-52)
+    du = ops.gemm(g_bf, L.w2p, b_t=True)                                                     # [T, ffp]
+    dw2 = gs.zeros(prefix + "3.4.weight", (dim, L.ffp))
+    ops.gemm(g_bf, c.u, a_t=True, b_t=True, out=dw2, accumulate=True, splits=0)
+    dh1 = ops.geglu_bwd(c.h1, du)
+    dxf = ops.gemm(dh1, L.w1p, b_t=True, out_dtype=torch.float32)                           # [T, dim]
+    dw1 = gs.zeros(prefix + "3.1.weight", (2 * L.ffp, dim))
+    ops.gemm(dh1, c.xf, a_t=True, b_t=True, out=dw1, accumulate=True, splits=0)
+    dg = gs.zeros(prefix + "3.0.weight", (dim,))
+    db = gs.zeros(prefix + "3.0.bias", (dim,))
+    g2, g2_bf = ops.layernorm_bwd(dxf, c.x2, L.ff_g, add_in=g, dgamma=dg, dbeta=db, want_bf16=True)
+    del dxf, dh1, du
+    # ---- attention (attention.py:127-181)
+    d_o = ops.gemm(g2_bf, L.wout, b_t=True)                                                  # [T, inner]
+    dwo = gs.zeros(prefix + "1.to_out.weight", (dim, inner))
+    ops.gemm(g2_bf, c.o, a_t=True, b_t=True, out=dwo, accumulate=True, splits=0)
+    dqs = gs.zeros(prefix + "1.q_scale", (32,))
+    dks = gs.zeros(prefix + "1.k_scale", (32,))
+    dq, dkv = ops.attn_bwd(c.q, c.kv, c.o, c.lse, d_o, grid, heads, temporal, L.q_scale, L.k_scale, dqs, dks, tab, rowmax,
+                           dtab)
+    dxn = ops.gemm(dq, L.wq, b_t=True, out_dtype=torch.float32)
+    dwq = gs.zeros(prefix + "1.to_q.weight", (inner, dim))
+    ops.gemm(dq, c.xn, a_t=True, b_t=True, out=dwq, accumulate=True, splits=0)
+    dwkv = gs.zeros(prefix + "1.to_kv.weight", (2 * inner, dim))
+    ops.gemm(dkv, c.xr, a_t=True, b_t=True, out=dwkv, accumulate=True, splits=0)
+    dgam = gs.zeros(prefix + "1.norm.gamma", (dim,))
+    g1, _ = ops.layernorm_bwd(dxn, c.x1, L.gamma, add_in=g2, dgamma=dgam)
+    ops.gemm(dkv, L.wkv, b_t=True, out=g1, resid=g1)                                        # += d(raw kv input)
+    del dxn, dq, dkv, d_o, g2, g2_bf
+    # ---- PEG (attention.py:63-84)
+    dw27 = gs.zeros(prefix + "0.dsconv.weight", (27, dim))
+    dpb = gs.zeros(prefix + "0.dsconv.bias", (dim,))
+    ops.peg_bwd_weight(c.x, g1, dw27, dpb, grid, temporal)
+    g0, _ = ops.peg_bwd_data(g1, L.w27, grid, temporal)
+    return g0
+
+
+def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
+    """backward of encoder_forward; g_tokens = dL/d(tokens) fp32 [T, dim]. Returns {reference param name: grad}."""
+    dim = W.dim
+    dev = g_tokens.device
+    gs = GradStore(dev)
+    grid = ctx.grid
+    v = ""
+    # temporal transformer
+    dgo = gs.zeros("enc_temporal_transformer.norm_out.gamma", (dim,))
+    g, _ = ops.layernorm_bwd(g_tokens, ctx.t_pre, W.t_out, dgamma=dgo)
+    for i in reversed(range(len(W.temporal))):
+        g = layer_backward(g, ctx.temporal[i], W.temporal[i], grid, W.heads, True, None, None, None, gs,
+                           f"enc_temporal_transformer.layers.{i}.", dim)
+        ctx.temporal[i] = None
+    dgo = gs.zeros("enc_spatial_transformer.norm_out.gamma", (dim,))
+    g, _ = ops.layernorm_bwd(g, ctx.s_pre, W.s_out, dgamma=dgo)
+    dtab = torch.zeros_like(ctx.tab)
+    for i in reversed(range(len(W.spatial))):
+        g = layer_backward(g, ctx.spatial[i], W.spatial[i], grid, W.heads, False, ctx.tab, ctx.rowmax, dtab, gs,
+                           f"enc_spatial_transformer.layers.{i}.", dim)
+        ctx.spatial[i] = None
+    # patch embedding (ctvit.py:169-174)
+    a, y0 = ctx.pe
+    dg2 = gs.zeros("to_patch_emb.3.weight", (dim,))
+    db2 = gs.zeros("to_patch_emb.3.bias", (dim,))
+    dy0, dy0_bf = ops.layernorm_bwd(g, y0, W.pe_g2, dgamma=dg2, dbeta=db2, want_bf16=True)
+    dbias = gs.zeros("to_patch_emb.2.bias", (dim,))
+    ops.colsum(dy0, dbias)
+    dwp = gs.zeros("to_patch_emb.2.weight", (dim, a.shape[1]))
+    ops.gemm(dy0_bf, a, a_t=True, b_t=True, out=dwp, accumulate=True, splits=0)
+    dg1 = gs.zeros("to_patch_emb.1.weight", (W.pdim,))
+    db1 = gs.zeros("to_patch_emb.1.bias", (W.pdim,))
+    dwp_c = dwp[:, : W.pdim].contiguous() if a.shape[1] != W.pdim else dwp
+    ops.patch_ln_param_grad(vit.to_patch_emb[2].weight.detach().contiguous(), dwp_c, dbias, W.pe_g, W.pe_b, dg1, db1)
+    # continuous position bias MLP: tiny (2h-1)(2w-1)-row parameter-only graph, differentiated by autograd
+    _, _, h, w = grid
+    with torch.enable_grad():
+        tab = vit.spatial_rel_pos_bias.table(h, w, dev)
+        cpb_params = list(vit.spatial_rel_pos_bias.parameters())
+        cpb_grads = torch.autograd.grad(tab, cpb_params, dtab)
+    out = {}
+    for (name, _), gr in zip(vit.spatial_rel_pos_bias.named_parameters(), cpb_grads):
+        out["spatial_rel_pos_bias." + name] = gr
+    # kernel layouts -> reference parameter shapes
+    for name, t in gs.g.items():
+        if name.endswith("0.dsconv.weight"):
+            out[name] = t.t().reshape(dim, 1, 3, 3, 3)
+        elif name.endswith("3.1.weight"):
+            ffp = t.shape[0] // 2
+            L = W.spatial[0]
+            out[name] = torch.cat((t[: L.ffi], t[ffp: ffp + L.ffi]), dim=0)
+        elif name.endswith("3.4.weight"):
+            out[name] = t[:, : W.spatial[0].ffi]
+        elif name == "to_patch_emb.2.weight":
+            out[name] = t[:, : W.pdim]
+        else:
+            out[name] = t
+    return out
+
+
+def layernorm_module_forward(x, gamma, beta):
+    shape = x.shape
+    _, _, y = ops.layernorm_fwd(x.reshape(-1, shape[-1]).contiguous().float(), gamma, beta, want_bf16=False, want_f32=True)
+    return y.reshape(shape)

@@ -210,3 +210,174 @@ def attn_bwd(q, kv, o, lse, d_o, grid, heads, temporal, q_scale, k_scale, dq_sca
         d.dbias_table = dbias_table.data_ptr()
     _call("ctclip_attn_bwd", C.byref(d), _stream())
     return dq, dkv
+
+
+def colsum(x, out):
+    _req(x, torch.float32, "colsum.x")
+    assert x.is_contiguous()
+    _call("ctclip_colsum", _ptr(x), _ll(x.shape[0]), x.shape[1], _ptr(out), _stream())
+
+
+def gemm_top2(a, b):
+    """VQ assignment GEMM: returns (top2 float32 [M, n_tiles, 4], tile_n) without materialising the score matrix"""
+    _req(a, torch.bfloat16, "gemm_top2.a")
+    _req(b, torch.bfloat16, "gemm_top2.b")
+    M, K = a.shape
+    N = b.shape[0]
+    tile_n = int(_lib.lib().ctclip_gemm_tile_n(N))
+    n_tiles = (N + tile_n - 1) // tile_n
+    top2 = torch.empty((M, n_tiles, 4), device=a.device, dtype=torch.float32)
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn_major = a.data_ptr(), a.stride(0), 0
+    d.B, d.ldb, d.b_mn_major = b.data_ptr(), b.stride(0), 0
+    d.C, d.ldc, d.c_is_f32 = 0, N, 1
+    d.alpha, d.atomic, d.splits = 1.0, 0, 1
+    d.top2_out = top2.data_ptr()
+    _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16(top2)")
+    return top2, tile_n
+
+
+def patch_ln_fwd(video, gamma, beta, pt, ps, eps=1e-5):
+    """video fp32 [b,1,f,h,w] -> bf16 [tokens, pdim_padded] LayerNorm'd patches in (pt p1 p2) order"""
+    _req(video, torch.float32, "patch_ln_fwd.video")
+    assert video.is_contiguous() and video.dim() == 5 and video.shape[1] == 1
+    b, _, f, hh, ww = video.shape
+    pdim = pt * ps * ps
+    ld = (pdim + 7) // 8 * 8
+    tokens = b * (f // pt) * (hh // ps) * (ww // ps)
+    alloc = torch.zeros if ld != pdim else torch.empty
+    out = alloc((tokens, ld), device=video.device, dtype=torch.bfloat16)
+    _call("ctclip_patch_ln_fwd", _ptr(video), b, f, hh, ww, pt, ps, _ptr(gamma), _ptr(beta), _f(eps), _ptr(out), _ll(ld),
+          _stream())
+    return out
+
+
+def patch_ln_param_grad(W, dW, s, gamma, beta, dgamma, dbeta):
+    n_out, pdim = W.shape
+    assert W.is_contiguous() and dW.is_contiguous() and dW.shape == W.shape
+    _call("ctclip_patch_ln_param_grad", _ptr(W), _ptr(dW), _ptr(s), _ptr(gamma), _ptr(beta), _ptr(dgamma), _ptr(dbeta),
+          n_out, pdim, _stream())
+
+
+def l2norm_rows(x, want_f32=False, want_bf16=False):
+    """returns (y_f32 | None, y_bf16 | None, inv_norm)"""
+    _req(x, torch.float32, "l2norm_rows.x")
+    assert x.is_contiguous() and x.dim() == 2
+    rows, dim = x.shape
+    yf = torch.empty_like(x) if want_f32 else None
+    yb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    inv = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("ctclip_l2norm_rows", _ptr(x), _ll(rows), dim, _ptr(yf), _ptr(yb), _ptr(inv), _stream())
+    return yf, yb, inv
+
+
+def l2norm_bwd(y, inv_norm, g):
+    dx = torch.empty_like(y)
+    _call("ctclip_l2norm_bwd", _ptr(y), _ptr(inv_norm), _ptr(g), _ll(y.shape[0]), y.shape[1], _ptr(dx), _stream())
+    return dx
+
+
+VQ_MARGIN = 8e-3  # >= 2 * 2^-8: twice the worst-case error of a unit-vector dot product with bf16-rounded operands
+
+
+def vq_finalize(top2, tile_n, x, embed_n, margin=VQ_MARGIN, stats=None):
+    rows, dim = x.shape
+    codes = embed_n.shape[0]
+    idx = torch.empty(rows, device=x.device, dtype=torch.int32)
+    _call("ctclip_vq_finalize", _ptr(top2), top2.shape[1], tile_n, _ptr(x), _ptr(embed_n), _ll(rows), dim, codes,
+          _f(margin), _ptr(idx), _ptr(stats), _stream())
+    return idx
+
+
+def vq_gather_mean(embed, idx, batch, t, hw, want_bf16=True):
+    dim = embed.shape[-1]
+    out = torch.empty((batch, hw * dim), device=embed.device, dtype=torch.float32)
+    outb = torch.empty((batch, hw * dim), device=embed.device, dtype=torch.bfloat16) if want_bf16 else None
+    _call("ctclip_vq_gather_mean", _ptr(embed), _ptr(idx), _ptr(out), _ptr(outb), batch, t, hw, dim, _stream())
+    return out, outb
+
+
+def vq_gather(embed, idx):
+    dim = embed.shape[-1]
+    out = torch.empty((idx.numel(), dim), device=embed.device, dtype=torch.float32)
+    _call("ctclip_vq_gather", _ptr(embed), _ptr(idx), _ptr(out), _ll(idx.numel()), dim, _stream())
+    return out
+
+
+def pool_bwd(dpool, batch, t, hw, dim):
+    dx = torch.empty((batch * t * hw, dim), device=dpool.device, dtype=torch.float32)
+    _call("ctclip_pool_bwd", _ptr(dpool), _ptr(dx), batch, t, hw, dim, _stream())
+    return dx
+
+
+def vq_ema(embed, cluster_size, x, inv_norm, idx, decay=0.8):
+    """in-place train-mode EMA update of (embed [C,D], cluster_size [C]); returns (bins, embed_sum) for cross-rank reduction"""
+    codes, dim = embed.shape
+    bins = torch.zeros(codes, device=embed.device, dtype=torch.float32)
+    esum = torch.zeros((codes, dim), device=embed.device, dtype=torch.float32)
+    _call("ctclip_vq_ema_accum", _ptr(x), _ptr(inv_norm), _ptr(idx), _ll(x.shape[0]), dim, _ptr(bins), _ptr(esum), _stream())
+    return bins, esum
+
+
+def vq_ema_update(embed, cluster_size, bins, esum, decay=0.8):
+    codes, dim = embed.shape
+    _call("ctclip_vq_ema_update", _ptr(embed), _ptr(cluster_size), _ptr(bins), _ptr(esum), codes, dim, _f(decay), _stream())
+
+
+def clip_loss(T, I, tau, row0, rows_local, want_grad=True):
+    """T, I fp32 [B, d] normalised global latents; returns (loss scalar tensor, dT, dI, dtau) for the local rows"""
+    B, d = T.shape
+    work = torch.empty(B * B + 2 * B + d, device=T.device, dtype=torch.float32)
+    loss = torch.zeros((), device=T.device, dtype=torch.float32)
+    dT = torch.empty((rows_local, d), device=T.device, dtype=torch.float32) if want_grad else None
+    dI = torch.empty((rows_local, d), device=T.device, dtype=torch.float32) if want_grad else None
+    dtau = torch.zeros((), device=T.device, dtype=torch.float32) if want_grad else None
+    _call("ctclip_clip_loss", _ptr(T), _ptr(I), _ptr(tau), B, d, row0, rows_local, _ptr(work), _ptr(loss), _ptr(dT),
+          _ptr(dI), _ptr(dtau), _stream())
+    return loss, dT, dI, dtau
+
+
+def sumsq(g, out):
+    _call("ctclip_sumsq", _ptr(g), _ll(g.numel()), _ptr(out), _stream())
+
+
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max_norm=0.0, zero_grad=True):
+    _call("ctclip_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), _ll(p.numel()), _f(lr), _f(beta1),
+          _f(beta2), _f(eps), step, _ptr(norm_sq), _f(max_norm), int(zero_grad), _stream())
+
+
+def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0):
+    """Trilinear resample (align_corners=False) of a batch of volumes on the GPU.
+    layout "dhw": inp is [b, D, H, W] (fp32, or int16 with hu=(slope, intercept));
+    layout "hwn": inp is [b, H, W, N] as stored in a NIfTI array (depth contiguous).
+    out_grid = (oD, oH, oW) resampled size; target = (tD, tH, tW) -> centre crop / pad(pad_value) window."""
+    assert inp.is_cuda and inp.is_contiguous() and inp.dim() == 4
+    d = _lib.PrepDesc()
+    b = inp.shape[0]
+    if layout == "dhw":
+        D, H, W = inp.shape[1:]
+        sd, sh, sw = H * W, W, 1
+    elif layout == "hwn":
+        H, W, D = inp.shape[1:]
+        sd, sh, sw = 1, W * D, D
+    else:
+        raise _lib.CtclipError("prep_resample: unknown layout")
+    if inp.dtype == torch.int16:
+        if hu is None:
+            raise _lib.CtclipError("prep_resample: int16 input needs hu=(slope, intercept)")
+        d.in_is_i16, d.slope, d.intercept = 1, float(hu[0]), float(hu[1])
+    elif inp.dtype == torch.float32:
+        d.in_is_i16 = 0
+    else:
+        raise _lib.CtclipError("prep_resample: input must be int16 or float32")
+    tgt = tuple(target) if target is not None else tuple(out_grid)
+    out = torch.empty((b, *tgt), device=inp.device, dtype=torch.float32)
+    d.in_, d.out, d.batch = inp.data_ptr(), out.data_ptr(), b
+    d.D, d.H, d.W = D, H, W
+    d.stride_d, d.stride_h, d.stride_w, d.stride_batch = sd, sh, sw, D * H * W
+    d.oD, d.oH, d.oW = (int(v) for v in out_grid)
+    d.tD, d.tH, d.tW = (int(v) for v in tgt)
+    d.pad_value = pad_value
+    _call("ctclip_prep_resample", C.byref(d), _stream())
+    return out

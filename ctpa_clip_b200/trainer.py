@@ -1,0 +1,87 @@
+"""Training step of the reference trainer (CTPA_CLIP/ct_clip/CTCLIPTrainer.py:316-353) on one process per GPU:
+forward(loss) -> backward -> gradient all-reduce (NCCL over NVLink) -> clip_grad_norm_(0.5) -> Adam(lr, betas (0.9, 0.99)).
+
+All trainable parameters live in ONE flat fp32 arena (parameters are views into it), with matching flat gradient /
+Adam-moment arenas, so clipping and the optimiser are two HBM passes and the all-reduce is a handful of large buckets.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class ParamArena:
+    def __init__(self, module: torch.nn.Module):
+        params = [p for p in module.parameters() if p.requires_grad and p.numel() > 0]
+        self.params = params
+        dev = params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        total = sum(sizes)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p, s in zip(params, sizes):
+                view = self.flat[off: off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[off: off + p.numel()].view(p.shape)
+                off += s
+        self.norm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.total = total
+
+
+class CTClipTrainStep:
+    """One optimisation step with the reference's hyper-parameters (CTCLIPTrainer.py:203-205: lr 1.25e-6, wd 0,
+    max_grad_norm 0.5; optimizer.py:13-14: betas (0.9, 0.99), eps 1e-8)."""
+
+    def __init__(self, model, lr=1.25e-6, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=0.5, bucket_elems=64 * 1024 * 1024):
+        self.model = model
+        self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
+        self.arena = ParamArena(model)
+        self.step_count = 0
+        self.bucket = bucket_elems
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            vit = model.visual_transformer
+
+            def ema_reduce(bins, esum):
+                dist.all_reduce(bins)
+                dist.all_reduce(esum)
+            vit.ema_reduce = ema_reduce
+
+    def forward_backward(self, text, video):
+        self.model.train()
+        loss = self.model(text, video, return_loss=True)
+        loss.backward()
+        return loss
+
+    def reduce_gradients(self):
+        """sum over ranks: every rank back-propagated its own rows of the global-batch loss"""
+        if not self.distributed:
+            return
+        g = self.arena.grad
+        for off in range(0, g.numel(), self.bucket):
+            dist.all_reduce(g[off: off + self.bucket])
+
+    def optimizer_step(self):
+        a = self.arena
+        self.step_count += 1
+        a.norm_sq.zero_()
+        ops.sumsq(a.grad, a.norm_sq)
+        ops.adam_step(a.flat, a.grad, a.m, a.v, None, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+                      norm_sq=a.norm_sq, max_norm=self.max_grad_norm, zero_grad=True)
+        # parameters changed in place behind autograd's back: drop the derived operand caches
+        self.model.visual_transformer.invalidate_weights()
+        self.model._sh_text.key = None
+        self.model._sh_vis.key = None
+
+    def step(self, text, video):
+        loss = self.forward_backward(text, video)
+        self.reduce_gradients()
+        self.optimizer_step()
+        return loss

@@ -42,7 +42,9 @@ long long ctclip_launch_count(void);
  *   a_mn_major = 0: A is [M][lda] with K contiguous;   1: A is [K][lda] with M contiguous (i.e. A^T stored)
  *   b_mn_major = 0: B is [N][ldb] with K contiguous;   1: B is [K][ldb] with N contiguous
  *   C is row-major [M][ldc], bf16 (c_is_f32=0) or fp32 (c_is_f32=1); resid is fp32 [M][ldr] (may alias C)
- *   atomic=1: C += result with fp32 atomics (required for splits>1); splits<=0 picks a split-K factor. */
+ *   atomic=1: C += result with fp32 atomics (required for splits>1); splits<=0 picks a split-K factor.
+ *   top2_out: VQ-assignment epilogue (ctvit.py:427): instead of C, the two largest accumulators of every row within
+ *   each N-tile and their column indices. */
 typedef struct ctclip_gemm_desc {
   int M, N, K;
   const void* A; long long lda; int a_mn_major;
@@ -53,7 +55,10 @@ typedef struct ctclip_gemm_desc {
   float alpha;
   int atomic;
   int splits;
+  void* top2_out; /* non-NULL: float4 [M][ceil(N/BN)] = per n-tile best two (value, column-as-int-bits); C unused */
 } ctclip_gemm_desc;
+/* N-tile width the kernel will use for a given N (128 or 256): sizes the top2_out buffer */
+int ctclip_gemm_tile_n(int N);
 int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -69,6 +74,8 @@ int ctclip_layernorm_bwd(const float* dy, const float* x, long long rows, int di
 int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_half, void* stream);
 int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, int ld_half, void* stream);
 int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+/* out[c] += sum_rows x[row][c]  (bias gradients) */
+int ctclip_colsum(const float* x, long long rows, int dim, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PEG (attention.py:56-84): y = x + dwconv3x3x3_causal(x) + bias on tokens kept in the canonical (b,t,h,w,d) layout.
@@ -104,6 +111,69 @@ typedef struct ctclip_attn_desc {
 } ctclip_attn_desc;
 int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream);
 int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch embedding front end (ctvit.py:170-171): 'b c (t pt)(h p1)(w p2) -> b t h w (c pt p1 p2)' + LayerNorm(pt*p1*p2),
+ * written as the bf16 A operand [tokens][ld_out] of the patch-embed GEMM. video is fp32 [batch][1][frames][height][width].
+ * patch_ln_param_grad: dgamma/dbeta (+=) of that LayerNorm derived algebraically from the Linear's W, dW and bias grad. */
+int ctclip_patch_ln_fwd(const float* video, int batch, int frames, int height, int width, int pt, int ps,
+                        const float* gamma, const float* beta, float eps, void* out, long long ld_out, void* stream);
+int ctclip_patch_ln_param_grad(const float* W, const float* dW, const float* s, const float* gamma, const float* beta,
+                               float* dgamma, float* dbeta, int n_out, int pdim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cosine-sim vector quantiser (vector_quantize_pytorch 1.1.2; ctvit.py:187,427).
+ * l2norm_rows: y = x / max(|x|,1e-12) (fp32 and/or bf16) + inverse norms.
+ * vq_finalize: exact fp32 arg-max from the GEMM's top2_out (n_tiles x float4 per token), embed_n = l2norm(embed) fp32.
+ *   stats (may be NULL): [0] += exact dot products evaluated, [1] += whole-tile rescans.
+ * vq_gather(_mean): embed[idx] rows / their mean over t (ct_clip.py:724) as fp32 and/or bf16 [batch][hw][dim].
+ * pool_bwd: dx[b][t][p][:] = dpool[b][p][:] / t  (mean-over-t backward through the straight-through estimator).
+ * vq_ema_*: train-mode EMA statistics (atomics) and the (cluster_size, embed) lerp update with decay 0.8. */
+int ctclip_l2norm_rows(const float* x, long long rows, int dim, float* y_f32, void* y_bf16, float* inv_norm, void* stream);
+int ctclip_l2norm_bwd(const float* y, const float* inv_norm, const float* g, long long rows, int dim, float* dx, void* stream);
+int ctclip_vq_finalize(const void* top2, int n_tiles, int tile_n, const float* x, const float* embed_n, long long rows,
+                       int dim, int codes, float margin, int* idx_out, unsigned long long* stats, void* stream);
+int ctclip_vq_gather_mean(const float* embed, const int* idx, float* out_f32, void* out_bf16, int batch, int t, int hw,
+                          int dim, void* stream);
+int ctclip_vq_gather(const float* embed, const int* idx, float* out, long long rows, int dim, void* stream);
+int ctclip_pool_bwd(const float* dpool, float* dx, int batch, int t, int hw, int dim, void* stream);
+int ctclip_vq_ema_accum(const float* x, const float* inv_norm, const int* idx, long long rows, int dim, float* bins,
+                        float* embed_sum, void* stream);
+int ctclip_vq_ema_update(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int codes, int dim,
+                         float decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Symmetric InfoNCE (ct_clip.py:796,845-878) over the global batch of l2-normalised latents T, I fp32 [B][d].
+ * work: fp32 [B*B + 2*B + d]. loss: device scalar. dT/dI: fp32 [rows_local][d], gradients w.r.t. the normalised latents of
+ * rows [row0,row0+rows_local) (NULL -> loss only). dtau += this rank's share of dloss/dtemperature. */
+int ctclip_clip_loss(const float* T, const float* I, const float* tau, int B, int d, int row0, int rows_local, float* work,
+                     float* loss, float* dT, float* dI, float* dtau, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Trainer step (CTCLIPTrainer.py:347-353, optimizer.py:10-24) on flat fp32 arenas: sum of squares for the global-norm
+ * clip, then fused clip + Adam + bf16 shadow refresh + gradient zeroing. */
+int ctclip_sumsq(const float* g, long long n, float* out, void* stream);
+int ctclip_adam_step(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, float lr, float beta1,
+                     float beta2, float eps, int step, const float* norm_sq, float max_norm, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * data_prep volume normalisation (preprocess_train.py:99-109, resize_array :31-42, data.py:155-190).
+ *   in_is_i16=1: raw scan, int16, logical (D,H,W) addressed through element strides (a NIfTI (H,W,N) array has
+ *   stride_d=1, stride_w=N, stride_h=W*N); HU = slope*x+intercept in float64, clip [-1000,1000], /1000, float32.
+ *   in_is_i16=0: float32 volume, resample only (ctpa_report/vqa_meditron.py:170-175 direct-to-target variant).
+ *   (oD,oH,oW): trilinear target grid (align_corners=False). (tD,tH,tW) > 0: destination volume receiving the
+ *   centre-cropped / pad_value-padded result (data.py:155-189); 0 -> destination == target grid. */
+typedef struct ctclip_prep_desc {
+  const void* in; float* out;
+  int batch; int in_is_i16;
+  double slope, intercept;
+  int D, H, W;
+  long long stride_d, stride_h, stride_w, stride_batch;
+  int oD, oH, oW;
+  int tD, tH, tW;
+  float pad_value;
+} ctclip_prep_desc;
+int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream);
 
 #ifdef __cplusplus
 }
