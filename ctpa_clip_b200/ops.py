@@ -11,6 +11,43 @@ import torch
 from . import _lib
 
 
+_PROF = None  # {name: [(start_event, end_event, flops), ...]} while bench.py's instrumented step runs
+
+
+def profile_begin():
+    global _PROF
+    _PROF = {}
+
+
+def profile_end():
+    """returns {op name: {"ms": summed device time, "n": launches, "flops": algorithmic flops}}"""
+    global _PROF
+    prof, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, recs in prof.items():
+        out[name] = {"ms": sum(a.elapsed_time(b) for a, b, _ in recs), "n": len(recs), "flops": sum(f for _, _, f in recs)}
+    return out
+
+
+class _Span:
+    def __init__(self, name, flops=0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _PROF.setdefault(self.name, []).append((self.a, b, self.flops))
+        return False
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -28,7 +65,7 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_t: bool = False, b_t: bool = False, out: torch.Tensor | None = None,
          out_dtype=torch.bfloat16, bias: torch.Tensor | None = None, resid: torch.Tensor | None = None,
-         alpha: float = 1.0, accumulate: bool = False, splits: int = 1) -> torch.Tensor:
+         alpha: float = 1.0, accumulate: bool = False, splits: int = 1, tag: str = "", flops: float | None = None) -> torch.Tensor:
     """C[M,N] = alpha * op(A) op(B)^T (+bias) (+resid)   bf16 operands, fp32 accumulation (tcgen05).
 
     a_t=False: `a` is [M,K] row-major;  a_t=True: `a` is [K,M] row-major (A^T stored).
@@ -74,13 +111,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_t: bool = False, b_t: bool = Fal
     d.alpha = alpha
     d.atomic = int(accumulate)
     d.splits = splits
-    _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16")
+    with _Span("gemm:" + (tag or f"{M}x{N}x{K}"), 2.0 * M * N * K if flops is None else flops):
+        _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16")
     return out
 
 
 def _call(name: str, *args):
     fn = getattr(_lib.lib(), name)
-    _lib.check(fn(*args), name)
+    with _Span(name.replace("ctclip_", "")):
+        _lib.check(fn(*args), name)
 
 
 def _f(x: float):
@@ -234,7 +273,8 @@ def gemm_top2(a, b):
     d.C, d.ldc, d.c_is_f32 = 0, N, 1
     d.alpha, d.atomic, d.splits = 1.0, 0, 1
     d.top2_out = top2.data_ptr()
-    _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16(top2)")
+    with _Span("gemm:vq_top2", 2.0 * M * N * K):
+        _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16(top2)")
     return top2, tile_n
 
 

@@ -12,9 +12,20 @@ import torch.distributed as dist
 from . import ops
 
 
+# parameters that exist in the reference's state_dict but never receive a gradient on the CLIP path (SURVEY.md a16;
+# the reference needs DDP(find_unused_parameters=True) for them, CTCLIPTrainer.py:213): static, so excluded up front
+UNUSED_PARAM_MARKERS = ("_latent_extra", "to_pixels", "to_patch_emb_first_frame", "context_norm", "null_kv",
+                        "text_transformer.pooler")
+
+
+def trainable_parameters(module):
+    return [(n, p) for n, p in module.named_parameters()
+            if p.requires_grad and p.numel() > 0 and not any(m in n for m in UNUSED_PARAM_MARKERS)]
+
+
 class ParamArena:
     def __init__(self, module: torch.nn.Module):
-        params = [p for p in module.parameters() if p.requires_grad and p.numel() > 0]
+        params = [p for _, p in trainable_parameters(module)]
         self.params = params
         dev = params[0].device
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]
