@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ctclip_b200.h declares; host-side logic."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "ctclip_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctclip_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ctpa_clip_b200 import _lib
+    lib = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ctclip_b200.h but not exported"
+    assert lib.ctclip_version() >= 100
+
+
+def test_no_cpu_fallback_ops_refuse_cpu_tensors():
+    from ctpa_clip_b200 import _lib, ops
+    with pytest.raises(_lib.CtclipError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    with pytest.raises(_lib.CtclipError):
+        ops.layernorm_fwd(torch.zeros(4, 8), torch.ones(8))
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors have the same size as the C structs (compiled probe)"""
+    import subprocess, tempfile
+    from ctpa_clip_b200 import _lib
+    src = '#include "ctclip_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(ctclip_gemm_desc), sizeof(ctclip_attn_desc), sizeof(ctclip_prep_desc));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        p = Path(d) / "p.c"
+        p.write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), str(p), "-o", str(Path(d) / "p")], check=True)
+        out = subprocess.run([str(Path(d) / "p")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [ctypes.sizeof(_lib.GemmDesc), ctypes.sizeof(_lib.AttnDesc), ctypes.sizeof(_lib.PrepDesc)]
+
+
+def test_state_dict_keys_match_reference_contract():
+    """key names and shapes of the drop-in modules (tiny config)"""
+    from ctpa_clip_b200.ct_clip import CTCLIP, CTViT
+    from oracle import ctclip_oracle as O
+    cfg = O.TINY
+    vit = CTViT(dim=cfg["dim"], codebook_size=cfg["codebook_size"], image_size=cfg["image_size"], patch_size=cfg["patch_size"],
+                temporal_patch_size=cfg["temporal_patch_size"], spatial_depth=cfg["spatial_depth"],
+                temporal_depth=cfg["temporal_depth"], dim_head=cfg["dim_head"], heads=cfg["heads"])
+    m = CTCLIP(image_encoder=vit, text_encoder=O.make_text_encoder(cfg), dim_text=cfg["dim_text"], dim_image=cfg["dim_image"],
+               dim_latent=cfg["dim_latent"])
+    sd = O.init_state_dict(cfg)
+    mine = m.state_dict()
+    for k, v in sd.items():
+        assert k in mine and tuple(mine[k].shape) == tuple(v.shape), k
+    for k in ("to_visual_latent_extra.weight", "to_text_latent_extra.weight", "visual_transformer.to_pixels.0.weight",
+              "visual_transformer.to_patch_emb_first_frame.2.weight",
+              "visual_transformer.enc_spatial_transformer.layers.0.1.null_kv",
+              "visual_transformer.enc_temporal_transformer.norm_out.beta"):
+        assert k in mine, k
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+
+
+def test_unsupported_configs_refuse_loudly():
+    from ctpa_clip_b200.ct_clip import CTCLIP, CTViT
+    with pytest.raises(NotImplementedError):
+        CTViT(dim=64, codebook_size=16, image_size=40, patch_size=20, temporal_patch_size=10, spatial_depth=1,
+              temporal_depth=1, dim_head=64, heads=2)
+    with pytest.raises(NotImplementedError):
+        CTCLIP(image_encoder=None, text_encoder=None)
+
+
+def test_unused_parameter_set_is_static():
+    from ctpa_clip_b200.trainer import trainable_parameters
+    from ctpa_clip_b200.ct_clip import CTCLIP, CTViT
+    from oracle import ctclip_oracle as O
+    cfg = O.TINY
+    vit = CTViT(dim=cfg["dim"], codebook_size=cfg["codebook_size"], image_size=cfg["image_size"], patch_size=cfg["patch_size"],
+                temporal_patch_size=cfg["temporal_patch_size"], spatial_depth=cfg["spatial_depth"],
+                temporal_depth=cfg["temporal_depth"], dim_head=cfg["dim_head"], heads=cfg["heads"])
+    m = CTCLIP(image_encoder=vit, text_encoder=O.make_text_encoder(cfg), dim_text=cfg["dim_text"], dim_image=cfg["dim_image"],
+               dim_latent=cfg["dim_latent"])
+    names = [n for n, _ in trainable_parameters(m)]
+    fx = torch.load("tests/golden/ctclip_tiny.pt", weights_only=False)
+    with_grad = set(fx["grads"].keys())            # parameters the REFERENCE's backward touches
+    assert set(names) == with_grad

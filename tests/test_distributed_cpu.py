@@ -1,0 +1,63 @@
+"""CPU, gloo, world_size 2: the global-batch InfoNCE partitioning — each rank differentiates its own rows
+of the all-gathered logits and the SUM of rank gradients equals the single-process gradient on the concatenated batch."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ctclip_oracle as O
+
+
+def _local_grads(T, I, tau, row0, rows):
+    """restates csrc/loss.cu clip_grad_kernel in torch: gradient w.r.t. rows [row0, row0+rows) and the dtau share"""
+    B = T.shape[0]
+    L = tau.exp() * T @ I.t()
+    row_lse, col_lse = torch.logsumexp(L, dim=1), torch.logsumexp(L, dim=0)
+    G = (torch.exp(L - row_lse[:, None]) + torch.exp(L - col_lse[None, :]) - 2 * torch.eye(B)) / (2 * B)
+    sl = slice(row0, row0 + rows)
+    dT = tau.exp() * G[sl] @ I
+    dI = tau.exp() * G[:, sl].t() @ T
+    dtau = (G[sl] * L[sl]).sum()
+    loss = (row_lse + col_lse - 2 * torch.diagonal(L)).sum() / (2 * B)
+    return loss, dT, dI, dtau
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    b, d = 3, 16
+    T_all = torch.nn.functional.normalize(torch.randn(world * b, d), dim=-1)
+    I_all = torch.nn.functional.normalize(torch.randn(world * b, d), dim=-1)
+    tau = torch.tensor(0.7)
+    local = torch.stack((T_all[rank * b:(rank + 1) * b], I_all[rank * b:(rank + 1) * b]))
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    g = torch.stack(gathered)
+    T, I = g[:, 0].reshape(world * b, d), g[:, 1].reshape(world * b, d)
+    loss, dT, dI, dtau = _local_grads(T, I, tau, rank * b, b)
+    # a parameter shared by all ranks (here: tau) receives the SUM of the rank shares
+    dist.all_reduce(dtau)
+    ret[rank] = (loss, dT, dI, dtau)
+    dist.destroy_process_group()
+
+
+def test_global_infonce_partition_two_ranks():
+    world, b, d = 2, 3, 16
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29617, ret), nprocs=world, join=True)
+    torch.manual_seed(0)
+    T = torch.nn.functional.normalize(torch.randn(world * b, d), dim=-1).requires_grad_()
+    I = torch.nn.functional.normalize(torch.randn(world * b, d), dim=-1).requires_grad_()
+    tau = torch.tensor(0.7, requires_grad=True)
+    loss = O.clip_loss(T, I, tau)           # single process on the concatenated batch (the parity oracle for W>1)
+    loss.backward()
+    for r in range(world):
+        l, dT, dI, dtau = ret[r]
+        assert torch.allclose(l, loss.detach(), atol=1e-6)
+        assert torch.allclose(dT, T.grad[r * b:(r + 1) * b], atol=1e-6)
+        assert torch.allclose(dI, I.grad[r * b:(r + 1) * b], atol=1e-6)
+        assert torch.allclose(dtau, tau.grad, atol=1e-6)

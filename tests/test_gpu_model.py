@@ -1,0 +1,150 @@
+"""GPU (-m gpu): the drop-in CTViT / CTCLIP modules (ctpa_clip_b200) against the CPU oracle and the committed
+reference fixtures. bf16 tensor-core operands + fp32 accumulation: tolerances stated per assertion."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ctclip_oracle as O  # noqa: E402
+
+
+def build(cfg, sd, txt):
+    from ctpa_clip_b200.ct_clip import CTCLIP, CTViT
+    vit = CTViT(dim=cfg["dim"], codebook_size=cfg["codebook_size"], image_size=cfg["image_size"], patch_size=cfg["patch_size"],
+                temporal_patch_size=cfg["temporal_patch_size"], spatial_depth=cfg["spatial_depth"],
+                temporal_depth=cfg["temporal_depth"], dim_head=cfg["dim_head"], heads=cfg["heads"])
+    m = CTCLIP(image_encoder=vit, text_encoder=txt, dim_text=cfg["dim_text"], dim_image=cfg["dim_image"],
+               dim_latent=cfg["dim_latent"])
+    m.load_state_dict(sd, strict=False)
+    m.text_autocast = False
+    return m.cuda()
+
+
+def text_of(ids, mask):
+    from transformers import BatchEncoding
+    return BatchEncoding({"input_ids": ids.cuda(), "attention_mask": mask.cuda()})
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_forward_matches_reference_fixture(name):
+    fx = torch.load(f"tests/golden/ctclip_{name}.pt", weights_only=False)
+    cfg = O.CONFIGS[name]
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, fx["batch"], 0)
+    m = build(cfg, sd, O.make_text_encoder(cfg, 0)).eval()
+    with torch.no_grad():
+        # pre-VQ tokens: bf16 operands through 4+ layers -> 2e-2 of the token scale (unit variance after norm_out)
+        vit = m.visual_transformer
+        pre = vit.encode(vit.to_patch_emb(video.cuda()))
+        err = (pre.reshape(fx["batch"], -1, cfg["dim"]).cpu() - fx["pre_vq_full"]).abs().max().item()
+        assert err < 6e-2 * fx["pre_vq_full"].abs().max().item()
+        # with the reference's code indices forced, everything downstream is tight
+        vit.force_indices = fx["indices"]
+        tl, il, enc = m(text_of(ids, mask), video.cuda(), return_latents=True)
+        assert F.cosine_similarity(tl.cpu(), fx["text_latents"]).min() > 0.9999
+        assert F.cosine_similarity(il.cpu(), fx["image_latents"]).min() > 0.9999
+        assert abs(enc.double().sum().item() - fx["enc_checksum"]) < 1e-3 * max(1.0, abs(fx["enc_checksum"]))
+        loss = m(text_of(ids, mask), video.cuda(), return_loss=True)
+        assert abs(float(loss) - float(fx["loss_eval"])) < 2e-3
+        sim = m(text_of(ids, mask), video.cuda())
+        assert torch.allclose(sim.cpu(), fx["sim_eval"], atol=2e-2)
+        # free-running arg-max: report-style bound on index agreement (near-ties flip under bf16 upstream noise)
+        vit.force_indices = None
+        idx = vit(video.cuda(), return_only_codebook_ids=True).reshape(fx["batch"], -1).cpu().to(torch.int32)
+        assert (idx == fx["indices"]).float().mean() > 0.97
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_gradients_match_reference_fixture(name):
+    """train-mode loss + every parameter gradient against the reference's autograd (indices forced, see above)"""
+    fx = torch.load(f"tests/golden/ctclip_{name}.pt", weights_only=False)
+    cfg = O.CONFIGS[name]
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, fx["batch"], 0)
+    m = build(cfg, sd, O.make_text_encoder(cfg, 0)).train()
+    m.text_transformer.eval()
+    m.visual_transformer.force_indices = fx["indices"]
+    loss = m(text_of(ids, mask), video.cuda(), return_loss=True)
+    loss.backward()
+    assert abs(float(loss) - float(fx["loss_train"])) < 2e-3
+    params = dict(m.named_parameters())
+    n = 0
+    for k, g in fx["grads"].items():
+        if g["norm"] < 1e-6:
+            continue                                                   # analytically-zero gradients (softmax shift invariance)
+        assert params[k].grad is not None, k
+        got = params[k].grad.float().cpu()
+        assert abs(got.norm().item() - g["norm"]) < 5e-2 * g["norm"], k          # bf16 path: 5% on the norm
+        if g["full"] is not None:
+            assert ((got - g["full"]).norm() / g["full"].norm()).item() < 4e-2, k
+        n += 1
+    assert n > 90
+    # parameters outside the path must not receive gradients (static unused set)
+    assert params["to_visual_latent_extra.weight"].grad is None
+    # EMA codebook update (train-mode forward side effect)
+    cb = m.visual_transformer.vq._codebook
+    assert torch.allclose(cb.cluster_size.cpu(), fx["ema_cluster_size"], atol=1e-5)
+    assert torch.allclose(cb.embed[0, :16].cpu(), fx["ema_embed_head"], atol=2e-3)
+
+
+def test_production_forward_vs_fixture_and_oracle():
+    """production config, B=2: free-running VQ agreement rate, latent cosine, loss; then tight with forced indices"""
+    fx = torch.load("tests/golden/ctclip_production.pt", weights_only=False)
+    cfg = O.PRODUCTION
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, 2, 0)
+    m = build(cfg, sd, O.make_text_encoder(cfg, 0)).eval()
+    vit = m.visual_transformer
+    with torch.no_grad():
+        stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+        vit.vq_stats = stats
+        tl, il, _ = m(text_of(ids, mask), video.cuda(), return_latents=True)
+        agree = (vit.last_indices.reshape(2, -1).cpu() == fx["indices"]).float().mean().item()
+        assert agree > 0.985                                           # ~0.4-1% of near-ties flip under bf16 noise
+        assert F.cosine_similarity(il.cpu(), fx["image_latents"]).min() > 0.985
+        assert F.cosine_similarity(tl.cpu(), fx["text_latents"]).min() > 0.9995
+        assert stats[0].item() >= 2 * 13824
+        loss = m(text_of(ids, mask), video.cuda(), return_loss=True)
+        assert abs(float(loss) - float(fx["loss_eval"])) < 3e-2
+        vit.force_indices = fx["indices"]
+        tl2, il2, _ = m(text_of(ids, mask), video.cuda(), return_latents=True)
+        assert F.cosine_similarity(il2.cpu(), fx["image_latents"]).min() > 0.9999
+        loss2 = m(text_of(ids, mask), video.cuda(), return_loss=True)
+        assert abs(float(loss2) - float(fx["loss_eval"])) < 2e-3
+
+
+def test_train_step_reduces_loss_and_matches_adam_semantics():
+    """a few optimisation steps through the flat-arena trainer on the tiny config: finite, decreasing loss"""
+    from ctpa_clip_b200.trainer import CTClipTrainStep
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, 4, 1)
+    m = build(cfg, sd, O.make_text_encoder(cfg, 0))
+    tr = CTClipTrainStep(m, lr=1e-3)
+    losses = [float(tr.step(text_of(ids, mask), video.cuda())) for _ in range(6)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    assert float(tr.arena.grad.abs().max()) == 0.0                     # gradients zeroed by the fused optimiser pass
+
+
+def test_zero_shot_scores_match_reference_calling_pattern():
+    """config 5 semantics: softmax over the (present, absent) prompt pair (ctclip_inference.py:305-315)"""
+    cfg = O.TINY
+    sd = O.init_state_dict(cfg, 0)
+    txt = O.make_text_encoder(cfg, 0)
+    m = build(cfg, sd, txt).eval()
+    video, ids, mask = O.make_inputs(cfg, 4, 2)
+    p_ids, p_mask = ids[:4].repeat(2, 1)[:6], mask[:4].repeat(2, 1)[:6]          # 3 pathologies x 2 prompts
+    p_ids[:, 1] = torch.arange(6) + 5
+    got = m.zero_shot_scores(text_of(p_ids, p_mask), video.cuda()).cpu()
+    sdc = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        enc_text = O.make_text_encoder(cfg, 0)(p_ids, attention_mask=p_mask)[0]
+        tl = O.text_latent(sdc, enc_text).reshape(3, 2, -1)
+        vit = m.visual_transformer
+        m(text_of(ids, mask), video.cuda(), return_latents=True)
+        q = O.ctvit_tokens(sdc, video, cfg)
+        il = O.image_latent(sdc, q)
+        want = O.zero_shot_scores(tl, il, sdc["temperature"])
+    assert got.shape == (4, 3)
+    assert torch.allclose(got, want, atol=3e-2)
