@@ -103,26 +103,33 @@ __device__ __forceinline__ void store_zero_row_cm(uint8_t* tile, int r) {
 }
 
 // =============================================================================================== forward
-// grid.x = num_blocks * heads (head fastest), 128 threads.
-__global__ void __launch_bounds__(128)
+// grid.x = num_blocks * heads (head fastest), 256 threads: thread t owns query row (t & 127) of the current tile and the
+// column half (t >> 7) of every 64-key chunk. Per element: one broadcast LDS (key offset), one table LDS, 2 FADD, 1 EX2.
+// The additive bias index is A_i - B_j with A_i = (qy+gh-1)(2gw-1) + qx+gw-1 per query row and B_j = ky(2gw-1)+kx per key.
+__global__ void __launch_bounds__(256)
 attn_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int head = blockIdx.x % p.heads;
   const int blk = blockIdx.x / p.heads;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowt = tid & 127, half = tid >> 7;
   const int R = p.ns * p.n;
   const int nchunks = (R + KC - 1) / KC;
   const int ntiles = (R + QT - 1) / QT;
+  const bool has_bias = p.bias_table != nullptr;
 
   uint8_t* sK = smem;                        // r_pad x 32 bf16
   uint8_t* sV = sK + p.r_pad * DH * 2;       // r_pad x 32
   uint8_t* sQ = sV + p.r_pad * DH * 2;       // 128 x 32
   uint8_t* sP = sQ + QT * DH * 2;            // 128 x 64
-  float* sTab = reinterpret_cast<float*>(sP + QT * KC * 2);
-  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
+  int* sB = reinterpret_cast<int*>(sP + QT * KC * 2);   // [r_pad] key offsets B_j (16-byte aligned)
+  float* sL = reinterpret_cast<float*>(sB + p.r_pad);   // [2][128] partial row sums of the two column halves
+  float* sScale = sL + 256;                             // [64]: q_scale*8*log2e , k_scale
+  float* sTab = sScale + 64;
+  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
   float* sRowMax = sTab + tab_n;
-  float* sScale = sRowMax + ((p.bias_table != nullptr) ? p.n : 0);  // [64]: q_scale*8*log2e , k_scale
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sScale + 64) + 15) & ~uintptr_t(15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(sRowMax + (has_bias ? p.n : 0)) + 15) & ~uintptr_t(15));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
   if (tid == 0) {
@@ -138,11 +145,14 @@ attn_fwd_kernel(const AttnParams p) {
     sScale[DH + tid] = p.k_scale[tid];
   }
   for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
-  if (p.bias_table != nullptr)
+  if (has_bias)
     for (int i = tid; i < p.n; i += blockDim.x) sRowMax[i] = p.bias_rowmax[(long long)head * p.n + i] * kLog2e;
+  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+    const int kp = r % p.n;
+    sB[r] = (kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw);
+  }
   __syncthreads();
-  // bound of |8 log2e q^.k^|
-  float cmax = 0.f;
+  float cmax = 0.f;  // bound of |8 log2e q^.k^|
 #pragma unroll
   for (int d = 0; d < DH; ++d) cmax = fmaxf(cmax, fabsf(sScale[d] * sScale[DH + d]));
 
@@ -170,33 +180,35 @@ attn_fwd_kernel(const AttnParams p) {
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tS = tmem;         // 2 x 64 columns
   const uint32_t tO = tmem + 128;   // 32 columns
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   constexpr uint32_t idesc_s = make_idesc_bf16(QT, KC, false, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
   uint32_t phase = 0;
 
   for (int tile = 0; tile < ntiles; ++tile) {
-    const int r = tile * QT + tid;
+    const int r = tile * QT + rowt;
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
-    if (valid) {
-      float v[DH];
-      const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
+    if (half == 0) {
+      if (valid) {
+        float v[DH];
+        const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
 #pragma unroll
-      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d];
-      store_row_cm(sQ, tid, v);
-    } else {
-      store_zero_row_cm(sQ, tid);
+        for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d];
+        store_row_cm(sQ, rowt, v);
+      } else {
+        store_zero_row_cm(sQ, rowt);
+      }
     }
     const int my_seq = r / p.n;
     const int my_pos = r - my_seq * p.n;
-    const int qy = my_pos / p.gw, qx = my_pos - qy * p.gw;
-    const float m_i = cmax + ((p.bias_table != nullptr && valid) ? sRowMax[my_pos] : 0.f);
+    const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);   // keys of this row's own sequence
+    const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
+    const float m_i = cmax + ((has_bias && valid) ? sRowMax[my_pos] : 0.f);
     float l = 0.f;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    // restrict key chunks to those that can hold keys of this tile's sequences (packed temporal blocks: all)
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -209,37 +221,37 @@ attn_fwd_kernel(const AttnParams p) {
       mbar_wait(bars, phase);
       phase ^= 1;
       tc_fence_after();
-      const uint32_t tSc = tS + (c & 1) * KC;
-      uint32_t pk[KC / 2];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t s[32];
-        tmem_ld_32x32(tSc + lane_off + half * 32, s);
-        tmem_wait_ld();
+      uint32_t s[32];
+      tmem_ld_32x32(tS + (c & 1) * KC + lane_off + half * 32, s);
+      tmem_wait_ld();
+      const int k0 = c * KC + half * 32;  // first key of this thread's 32 columns
+      uint32_t pk[16];
+      if (has_bias) {
+        const float* tabp = sTab + a_i;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float e[2];
+          const int2 b2 = *reinterpret_cast<const int2*>(sB + k0 + j);
+          float x0 = __uint_as_float(s[j]) - m_i + tabp[-b2.x];
+          float x1 = __uint_as_float(s[j + 1]) - m_i + tabp[-b2.y];
+          float e0 = (k0 + j < key_hi) ? exp2f(x0) : 0.f;
+          float e1 = (k0 + j + 1 < key_hi) ? exp2f(x1) : 0.f;
+          l += e0 + e1;
+          pk[j >> 1] = pack_bf16(e0, e1);
+        }
+      } else {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kr = c * KC + half * 32 + j + u;  // key row in block
-            float x = __uint_as_float(s[j + u]) - m_i;
-            bool ok = valid && kr < R;
-            if (p.ns > 1) ok = ok && (kr / p.n == my_seq);
-            if (p.bias_table != nullptr) {
-              const int kp = kr % p.n;
-              const int ky = kp / p.gw, kx = kp - ky * p.gw;
-              x += sTab[(qy - ky + p.gh - 1) * (2 * p.gw - 1) + (qx - kx + p.gw - 1)];
-            }
-            e[u] = ok ? exp2f(x) : 0.f;
-            l += e[u];
-          }
-          pk[(half * 32 + j) >> 1] = pack_bf16(e[0], e[1]);
+        for (int j = 0; j < 32; j += 2) {
+          const int ka = k0 + j;
+          float e0 = (ka >= key_lo && ka < key_hi) ? exp2f(__uint_as_float(s[j]) - m_i) : 0.f;
+          float e1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? exp2f(__uint_as_float(s[j + 1]) - m_i) : 0.f;
+          l += e0 + e1;
+          pk[j >> 1] = pack_bf16(e0, e1);
         }
       }
-      // P tile (128 x 64) as K-major core matrices
+      // this thread's 32 columns of the P tile (128 x 64, K-major core matrices)
 #pragma unroll
-      for (int c8 = 0; c8 < KC / 8; ++c8)
-        *reinterpret_cast<uint4*>(sP + cm_off(tid, c8, KC)) =
+      for (int c8 = 0; c8 < 4; ++c8)
+        *reinterpret_cast<uint4*>(sP + cm_off(rowt, half * 4 + c8, KC)) =
             make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
@@ -261,19 +273,22 @@ attn_fwd_kernel(const AttnParams p) {
         mma_commit(bars);
       }
     }
-    // ---- epilogue of this query tile
+    // ---- epilogue of this query tile: each column half stores 16 of the 32 output columns
+    sL[half * 128 + rowt] = l;
     mbar_wait(bars, phase);
     phase ^= 1;
     tc_fence_after();
+    __syncthreads();
     {
-      uint32_t o[32];
-      tmem_ld_32x32(tO + lane_off, o);
+      const float lt = sL[rowt] + sL[128 + rowt];
+      uint32_t o[16];
+      tmem_ld_32x16(tO + lane_off + half * 16, o);
       tmem_wait_ld();
       if (valid) {
-        const float inv_l = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(p.o + tok * p.ldo + head * DH);
+        const float inv_l = 1.f / lt;
+        uint4* dst = reinterpret_cast<uint4*>(p.o + tok * p.ldo + head * DH + half * 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           uint4 u;
           u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
           u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
@@ -281,7 +296,7 @@ attn_fwd_kernel(const AttnParams p) {
           u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
           dst[j] = u;
         }
-        if (p.lse != nullptr) p.lse[tok * p.heads + head] = m_i + log2f(l);
+        if (half == 0 && p.lse != nullptr) p.lse[tok * p.heads + head] = m_i + log2f(lt);
       }
     }
     tc_fence_before();
@@ -292,7 +307,6 @@ attn_fwd_kernel(const AttnParams p) {
     tmem_dealloc(tmem, 256);
   }
 }
-
 
 // =============================================================================================== backward
 // One CTA per (sequence block, head), 128 threads. Q~ (= 8 log2e q^), dO, lse and delta = rowsum(dO*O) stay in
@@ -332,13 +346,14 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   uint8_t* sV = sK + BKC * DH * 2;                 // 128 x 32
   uint8_t* sP = sV + BKC * DH * 2;                 // 128 x 128
   uint8_t* sdS = sP + QT * BKC * 2;                // 128 x 128
-  float* sLse = reinterpret_cast<float*>(sdS + QT * BKC * 2);
+  int* sB = reinterpret_cast<int*>(sdS + QT * BKC * 2);  // [r_pad] key offsets B_j
+  float* sLse = reinterpret_cast<float*>(sB + p.r_pad);
   float* sDelta = sLse + p.r_pad;
-  float* sTab = sDelta + p.r_pad;
-  float* sdTab = sTab + tab_n;
-  float* sScale = sdTab + tab_n;                   // [64]
+  float* sScale = sDelta + p.r_pad;                // [64]
   float* sRed = sScale + 64;                       // [64] dq_scale | dk_scale partial sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRed + 64) + 15) & ~uintptr_t(15));
+  float* sTab = sRed + 64;                         // [tab_n] bias * log2e
+  float* sdTab = sTab + tab_n;                     // [4][tab_n] per-warp private dbias accumulators
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sdTab + 4 * tab_n) + 15) & ~uintptr_t(15));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
   if (tid == 0) {
@@ -354,9 +369,11 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     sScale[DH + tid] = p.k_scale[tid];
   }
   if (tid < 64) sRed[tid] = 0.f;
-  for (int i = tid; i < tab_n; i += blockDim.x) {
-    sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
-    sdTab[i] = 0.f;
+  for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
+  for (int i = tid; i < 4 * tab_n; i += blockDim.x) sdTab[i] = 0.f;
+  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+    const int kp = r % p.n;
+    sB[r] = (kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw);
   }
   __syncthreads();
 
@@ -383,7 +400,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       store_zero_row_cm(sQ, r);
       store_zero_row_cm(sdO, r);
       sDelta[r] = 0.f;
-      sLse[r] = 0.f;
+      sLse[r] = INFINITY;  // exp2(x - inf) = 0: invalid query rows contribute nothing
     }
   }
   tc_fence_before();
@@ -396,6 +413,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
   constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
   constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
+  float* my_dtab = sdTab + warp * tab_n;
   uint32_t phase = 0;
 
   for (int c = 0; c < nchunks; ++c) {
@@ -436,41 +454,59 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       const int r = i * QT + tid;
       const int my_seq = r / p.n;
       const int my_pos = r - my_seq * p.n;
-      const bool valid = (r < R) && (my_seq < p.ns) && ((long long)blk * p.ns + my_seq < p.num_seqs);
-      const int qy = my_pos / p.gw, qx = my_pos - qy * p.gw;
+      const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);
+      const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
       const float lse_i = sLse[r], delta_i = sDelta[r];
       mbar_wait(bars, phase);
       phase ^= 1;
       tc_fence_after();
 #pragma unroll 1
       for (int piece = 0; piece < BKC / 32; ++piece) {
+        const int k0 = c * BKC + piece * 32;
+        if (k0 >= R) {  // warp-uniform: nothing but padding keys in this piece
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            *reinterpret_cast<uint4*>(sP + cm_off(tid, piece * 4 + c8, BKC)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sdS + cm_off(tid, piece * 4 + c8, BKC)) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
         uint32_t s[32], dp[32];
         tmem_ld_32x32(tS + lane_off + piece * 32, s);
         tmem_ld_32x32(tdP + lane_off + piece * 32, dp);
         tmem_wait_ld();
         uint32_t pk[16], dk[16];
+        if (has_bias) {
+          const float* tabp = sTab + a_i;
+          float* dtabp = my_dtab + a_i;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float pe[2], de[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kk = c * BKC + piece * 32 + j + u;
-            bool ok = valid && kk < R;
-            if (p.ns > 1) ok = ok && (kk / p.n == my_seq);
-            float x = __uint_as_float(s[j + u]) - lse_i;
-            int idx = 0;
-            if (has_bias) {
-              const int kp = kk % p.n;
-              const int ky = kp / p.gw, kx = kp - ky * p.gw;
-              idx = (qy - ky + p.gh - 1) * (2 * p.gw - 1) + (qx - kx + p.gw - 1);
-              x += sTab[idx];
-            }
-            pe[u] = ok ? exp2f(x) : 0.f;
-            de[u] = pe[u] * (__uint_as_float(dp[j + u]) - delta_i);
-            if (has_bias && ok) atomicAdd(&sdTab[idx], de[u]);
+          for (int j = 0; j < 32; j += 2) {
+            const int2 b2 = *reinterpret_cast<const int2*>(sB + k0 + j);
+            const float x0 = __uint_as_float(s[j]) - lse_i + tabp[-b2.x];
+            const float x1 = __uint_as_float(s[j + 1]) - lse_i + tabp[-b2.y];
+            const float p0 = (k0 + j < key_hi) ? exp2f(x0) : 0.f;
+            const float p1 = (k0 + j + 1 < key_hi) ? exp2f(x1) : 0.f;
+            const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
+            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
+            // lanes of a warp are consecutive query positions -> distinct A_i: plain read-modify-write is race free
+            if (r < R) dtabp[-b2.x] += d0;
+            __syncwarp();
+            if (r < R) dtabp[-b2.y] += d1;
+            __syncwarp();
+            pk[j >> 1] = pack_bf16(p0, p1);
+            dk[j >> 1] = pack_bf16(d0, d1);
           }
-          pk[j >> 1] = pack_bf16(pe[0], pe[1]);
-          dk[j >> 1] = pack_bf16(de[0], de[1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int ka = k0 + j;
+            const float p0 = (ka >= key_lo && ka < key_hi) ? exp2f(__uint_as_float(s[j]) - lse_i) : 0.f;
+            const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? exp2f(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
+            const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
+            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
+            pk[j >> 1] = pack_bf16(p0, p1);
+            dk[j >> 1] = pack_bf16(d0, d1);
+          }
         }
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
@@ -593,7 +629,9 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     if (bp.dk_scale != nullptr) atomicAdd(bp.dk_scale + tid, sRed[DH + tid]);
   }
   if (has_bias && bp.dbias_table != nullptr)
-    for (int i = tid; i < tab_n; i += blockDim.x) atomicAdd(bp.dbias_table + (long long)head * tab_n + i, sdTab[i]);
+    for (int i = tid; i < tab_n; i += blockDim.x)
+      atomicAdd(bp.dbias_table + (long long)head * tab_n + i,
+                (sdTab[i] + sdTab[tab_n + i]) + (sdTab[2 * tab_n + i] + sdTab[3 * tab_n + i]));
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -602,13 +640,14 @@ attn_bwd_kernel(const AttnBwdParams bp) {
 
 size_t bwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
-  return (size_t)p.r_pad * DH * 2 * 2 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 2 +
-         (size_t)tab_n * 4 * 2 + 128 * 4 + 64 + 16;
+  return (size_t)p.r_pad * DH * 2 * 2 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
+         (size_t)tab_n * 4 * 5 + 128 * 4 + 64 + 16;
 }
 
 size_t fwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) + p.n : 0;
-  return (size_t)p.r_pad * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 64 + 16;
+  return (size_t)p.r_pad * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 256 * 4 +
+         (size_t)p.r_pad * 4 + 64 + 16;
 }
 
 int fill_params(AttnParams& p, const ctclip_attn_desc* d, const char* what) {
@@ -655,7 +694,7 @@ extern "C" int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream) {
     configured = smem;
   }
   const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
-  attn_fwd_kernel<<<(unsigned)(blocks * p.heads), 128, smem, (cudaStream_t)stream>>>(p);
+  attn_fwd_kernel<<<(unsigned)(blocks * p.heads), 256, smem, (cudaStream_t)stream>>>(p);
   return ctclip::check_launch("attn_fwd");
 }
 

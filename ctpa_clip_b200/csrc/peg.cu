@@ -135,6 +135,138 @@ peg_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tiled kernels
+// A CTA owns a (TH x TW) patch of the virtual (vh, vw) plane for one 32-channel slice and walks the whole vt axis with a
+// rolling window of three input planes in shared memory: every input element is read ~1.5x from HBM/L2 instead of 27x.
+// lane = channel (its 27 taps stay in registers), warp = output position. MODE 0: y = x + conv(x) + bias;
+// MODE 1: dx = dy + conv^T(dy) (walks vt downwards, taps mirrored); MODE 2: dw27 / dbias accumulation.
+constexpr int TH = 8, TW = 8, PH = TH + 2, PW = TW + 2;
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out,
+                 __nv_bfloat16* __restrict__ out_bf16, const float* __restrict__ w27, const float* __restrict__ bias,
+                 float* __restrict__ dw27, float* __restrict__ dbias, PegGrid g, int dim) {
+  __shared__ float planes[3][PH * PW][32];
+  __shared__ float dyp[MODE == 2 ? TH * TW : 1][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ch = blockIdx.y * 32 + lane;
+  const int tiles_w = (g.w + TW - 1) / TW;
+  const int h0 = (blockIdx.x / tiles_w) * TH, w0 = (blockIdx.x % tiles_w) * TW;
+  const int b = blockIdx.z;
+  const long long per_b = (long long)g.t * g.h * g.w;
+  const float* base = in + b * per_b * dim;
+  const bool flip = (MODE == 1);
+
+  float wt[27];
+  if (MODE != 2) {
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          // age a = 2 - kt planes behind the cursor; spatial taps mirrored for the transposed stencil
+          const int src = flip ? ((kt * 3 + (2 - kh)) * 3 + (2 - kw)) : ((kt * 3 + kh) * 3 + kw);
+          wt[(kt * 3 + kh) * 3 + kw] = w27[src * dim + ch];
+        }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 27; ++i) wt[i] = 0.f;
+  }
+  float bsum = 0.f;
+  const float bval = (MODE == 0 && bias != nullptr) ? bias[ch] : 0.f;
+
+  for (int step = 0; step < g.t; ++step) {
+    const int vt = flip ? g.t - 1 - step : step;
+    // ---- load plane vt into slot step % 3 (zero outside the grid)
+    float (*slot)[32] = planes[step % 3];
+    for (int pos = warp; pos < PH * PW; pos += 8) {
+      const int vh = h0 - 1 + pos / PW, vw = w0 - 1 + pos % PW;
+      float v = 0.f;
+      if (vh >= 0 && vh < g.h && vw >= 0 && vw < g.w) v = base[(long long)virtual_to_canon(vt, vh, vw, g) * dim + ch];
+      slot[pos][lane] = v;
+    }
+    if (MODE == 2) {
+      const float* base2 = in2 + b * per_b * dim;
+      for (int pos = warp; pos < TH * TW; pos += 8) {
+        const int vh = h0 + pos / TW, vw = w0 + pos % TW;
+        float v = 0.f;
+        if (vh < g.h && vw < g.w) v = base2[(long long)virtual_to_canon(vt, vh, vw, g) * dim + ch];
+        dyp[pos][lane] = v;
+      }
+    }
+    __syncthreads();
+    // ---- outputs of plane vt
+    for (int pos = warp; pos < TH * TW; pos += 8) {
+      const int oh = pos / TW, ow = pos % TW;
+      const int vh = h0 + oh, vw = w0 + ow;
+      if (vh >= g.h || vw >= g.w) continue;
+      if (MODE != 2) {
+        float acc = planes[step % 3][(oh + 1) * PW + ow + 1][lane] + bval;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (step - a < 0) continue;
+          float (*pl)[32] = planes[(step - a) % 3];
+          const int kt = 2 - a;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              acc = fmaf(wt[(kt * 3 + kh) * 3 + kw], pl[(oh + kh) * PW + ow + kw][lane], acc);
+        }
+        const long long o = (b * per_b + virtual_to_canon(vt, vh, vw, g)) * dim + ch;
+        out[o] = acc;
+        if (MODE == 1 && out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(acc);
+      } else {
+        const float d = dyp[pos][lane];
+        bsum += d;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (step - a < 0) continue;
+          float (*pl)[32] = planes[(step - a) % 3];
+          const int kt = 2 - a;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              wt[(kt * 3 + kh) * 3 + kw] = fmaf(d, pl[(oh + kh) * PW + ow + kw][lane], wt[(kt * 3 + kh) * 3 + kw]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (MODE == 2) {
+    // reduce the 8 warps through shared memory (reuse the plane buffers), one atomic per (tap, channel) per CTA
+    float (*red)[32] = planes[0];  // [8*28][32] fits in 3*100 rows
+#pragma unroll
+    for (int i = 0; i < 27; ++i) red[warp * 28 + i][lane] = wt[i];
+    red[warp * 28 + 27][lane] = bsum;
+    __syncthreads();
+    for (int i = warp; i < 28; i += 8) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * 28 + i][lane];
+      if (i < 27) atomicAdd(dw27 + i * dim + ch, s);
+      else if (dbias != nullptr) atomicAdd(dbias + ch, s);
+    }
+  }
+}
+
+template <int MODE>
+int launch_tiled(const float* in, const float* in2, float* out, void* out_bf16, const float* w27, const float* bias,
+                 float* dw27, float* dbias, int batch, int t, int h, int w, int dim, int temporal, void* stream,
+                 const char* what) {
+  PegGrid g{t, h, w, temporal};
+  int vt = t, vh = h, vw = w;  // the virtual grid has the same extents (reshape, not permute)
+  (void)vt;
+  dim3 grid((unsigned)(((vh + TH - 1) / TH) * ((vw + TW - 1) / TW)), (unsigned)(dim / 32), (unsigned)batch);
+  peg_tiled_kernel<MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(in, in2, out, (__nv_bfloat16*)out_bf16, w27, bias, dw27,
+                                                                dbias, g, dim);
+  return ctclip::check_launch(what);
+}
+
 int check(int batch, int t, int h, int w, int dim, const char* what) {
   if (batch <= 0 || t <= 0 || h <= 0 || w <= 0) return ctclip::fail(CTCLIP_E_SHAPE, "%s: empty grid", what);
   if (dim % 4 || dim <= 0) return ctclip::fail(CTCLIP_E_SHAPE, "%s: dim must be a multiple of 4", what);
@@ -147,6 +279,8 @@ extern "C" int ctclip_peg_fwd(const float* x, float* y, const float* w27, const 
                               int w, int dim, int temporal, void* stream) {
   int rc = check(batch, t, h, w, dim, "peg_fwd");
   if (rc) return rc;
+  if (dim % 32 == 0 && batch <= 65535)
+    return launch_tiled<0>(x, nullptr, y, nullptr, w27, bias, nullptr, nullptr, batch, t, h, w, dim, temporal, stream, "peg_fwd");
   const long long tokens = (long long)batch * t * h * w;
   dim3 grid((unsigned)((tokens + 7) / 8), (unsigned)((dim / 4 + 31) / 32));
   peg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, w27, bias, batch, PegGrid{t, h, w, temporal}, dim, 0,
@@ -159,6 +293,9 @@ extern "C" int ctclip_peg_bwd_data(const float* dy, float* dx, void* dx_bf16, co
                                    int w, int dim, int temporal, void* stream) {
   int rc = check(batch, t, h, w, dim, "peg_bwd_data");
   if (rc) return rc;
+  if (dim % 32 == 0 && batch <= 65535)
+    return launch_tiled<1>(dy, nullptr, dx, dx_bf16, w27, nullptr, nullptr, nullptr, batch, t, h, w, dim, temporal, stream,
+                           "peg_bwd_data");
   const long long tokens = (long long)batch * t * h * w;
   dim3 grid((unsigned)((tokens + 7) / 8), (unsigned)((dim / 4 + 31) / 32));
   peg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, w27, nullptr, batch, PegGrid{t, h, w, temporal}, dim, 1,
@@ -171,6 +308,9 @@ extern "C" int ctclip_peg_bwd_weight(const float* x, const float* dy, float* dw2
                                      int w, int dim, int temporal, void* stream) {
   int rc = check(batch, t, h, w, dim, "peg_bwd_weight");
   if (rc) return rc;
+  if (dim % 32 == 0 && batch <= 65535)
+    return launch_tiled<2>(x, dy, nullptr, nullptr, nullptr, nullptr, dw27, dbias, batch, t, h, w, dim, temporal, stream,
+                           "peg_bwd_weight");
   const long long tokens = (long long)batch * t * h * w;
   int tokens_per_block = 128;
   long long blocks = (tokens + tokens_per_block - 1) / tokens_per_block;

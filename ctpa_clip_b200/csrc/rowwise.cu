@@ -6,7 +6,7 @@
 
 namespace {
 
-constexpr int kMaxVec = 8;  // float4 per lane -> dim <= 1024
+constexpr int kMaxVecAll = 8;  // float4 per lane -> dim <= 1024
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -16,6 +16,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------------------------------ LayerNorm fwd
 // y = (x - mean) * rstd * gamma (+ beta). Optional outputs: bf16 normalised, bf16 raw copy of x, fp32 normalised.
+template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int dim, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y_bf16,
@@ -82,6 +83,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int dim, const
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx_out = (add_in ? add_in : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy  (fp32 atomics, one per column per block)
+template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long rows, int dim,
                      const float* __restrict__ gamma, float eps, const float* __restrict__ add_in,
@@ -260,13 +262,19 @@ int grid_for(long long work_items, int per_block) {
 extern "C" int ctclip_layernorm_fwd(const float* x, long long rows, int dim, const float* gamma, const float* beta,
                                     float eps, void* y_bf16, void* raw_bf16, float* y_f32, void* stream) {
   if (rows <= 0) return CTCLIP_OK;
-  if (dim % 4 || dim > kMaxVec * 128 || dim <= 0)
-    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_fwd: dim must be a multiple of 4 and <= %d", kMaxVec * 128);
+  if (dim % 4 || dim > kMaxVecAll * 128 || dim <= 0)
+    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_fwd: dim must be a multiple of 4 and <= %d", kMaxVecAll * 128);
   if (x == nullptr || gamma == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_fwd: null pointer");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
-  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, rows, dim, gamma, beta, eps, (__nv_bfloat16*)y_bf16, (__nv_bfloat16*)raw_bf16, y_f32);
+  const int nv = (dim + 127) / 128;
+  const int g = grid_for(rows, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16 *yb = (__nv_bfloat16*)y_bf16, *rb = (__nv_bfloat16*)raw_bf16;
+  if (nv <= 1) layernorm_fwd_kernel<1><<<g, 256, 0, s>>>(x, rows, dim, gamma, beta, eps, yb, rb, y_f32);
+  else if (nv <= 2) layernorm_fwd_kernel<2><<<g, 256, 0, s>>>(x, rows, dim, gamma, beta, eps, yb, rb, y_f32);
+  else if (nv <= 4) layernorm_fwd_kernel<4><<<g, 256, 0, s>>>(x, rows, dim, gamma, beta, eps, yb, rb, y_f32);
+  else layernorm_fwd_kernel<8><<<g, 256, 0, s>>>(x, rows, dim, gamma, beta, eps, yb, rb, y_f32);
   return ctclip::check_launch("layernorm_fwd");
 }
 
@@ -274,16 +282,22 @@ extern "C" int ctclip_layernorm_bwd(const float* dy, const float* x, long long r
                                     float eps, const float* add_in, float* dx_out, void* dx_bf16, float* dgamma,
                                     float* dbeta, void* stream) {
   if (rows <= 0) return CTCLIP_OK;
-  if (dim % 4 || dim > kMaxVec * 128 || dim <= 0)
-    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: dim must be a multiple of 4 and <= %d", kMaxVec * 128);
+  if (dim % 4 || dim > kMaxVecAll * 128 || dim <= 0)
+    return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: dim must be a multiple of 4 and <= %d", kMaxVecAll * 128);
   if (dy == nullptr || x == nullptr || gamma == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: null pointer");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
   long long blocks = (rows + 63) / 64;  // each warp walks >= 8 rows so the column reductions amortise
   const long long cap = (long long)ctclip::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  layernorm_bwd_kernel<<<(int)blocks, 256, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
-      dy, x, rows, dim, gamma, eps, add_in, dx_out, (__nv_bfloat16*)dx_bf16, dgamma, dbeta);
+  const int nv = (dim + 127) / 128;
+  const size_t sm = 2 * dim * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
+  if (nv <= 1) layernorm_bwd_kernel<1><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
+  else if (nv <= 2) layernorm_bwd_kernel<2><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
+  else if (nv <= 4) layernorm_bwd_kernel<4><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
+  else layernorm_bwd_kernel<8><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
   return ctclip::check_launch("layernorm_bwd");
 }
 
