@@ -118,9 +118,10 @@ attn_fwd_kernel(const AttnParams p) {
   const int ntiles = (R + QT - 1) / QT;
   const bool has_bias = p.bias_table != nullptr;
 
-  uint8_t* sK = smem;                        // r_pad x 32 bf16
-  uint8_t* sV = sK + p.r_pad * DH * 2;       // r_pad x 32
-  uint8_t* sQ = sV + p.r_pad * DH * 2;       // 128 x 32
+  const int kv_rows = nchunks * KC;          // keys padded to whole chunks
+  uint8_t* sK = smem;                        // kv_rows x 32 bf16
+  uint8_t* sV = sK + kv_rows * DH * 2;       // kv_rows x 32
+  uint8_t* sQ = sV + kv_rows * DH * 2;       // 128 x 32
   uint8_t* sP = sQ + QT * DH * 2;            // 128 x 64
   int* sB = reinterpret_cast<int*>(sP + QT * KC * 2);   // [r_pad] key offsets B_j (16-byte aligned)
   float* sL = reinterpret_cast<float*>(sB + p.r_pad);   // [2][128] partial row sums of the two column halves
@@ -130,10 +131,12 @@ attn_fwd_kernel(const AttnParams p) {
   float* sRowMax = sTab + tab_n;
   uint64_t* bars = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(sRowMax + (has_bias ? p.n : 0)) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   if (tid == 0) {
-    mbar_init(bars, 1);
+    mbar_init(bars + 0, 1);  // S buffer 0 ready
+    mbar_init(bars + 1, 1);  // S buffer 1 ready
+    mbar_init(bars + 2, 1);  // P V of the previous chunk retired (P tile free, O updated)
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -157,7 +160,7 @@ attn_fwd_kernel(const AttnParams p) {
   for (int d = 0; d < DH; ++d) cmax = fmaxf(cmax, fabsf(sScale[d] * sScale[DH + d]));
 
   // ---- K^ and V for the whole block
-  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+  for (int r = tid; r < kv_rows; r += blockDim.x) {
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
     if (valid) {
@@ -183,7 +186,7 @@ attn_fwd_kernel(const AttnParams p) {
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   constexpr uint32_t idesc_s = make_idesc_bf16(QT, KC, false, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
-  uint32_t phase = 0;
+  uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int r = tile * QT + rowt;
@@ -215,11 +218,19 @@ attn_fwd_kernel(const AttnParams p) {
       for (int k = 0; k < DH / 16; ++k)
         mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512),
                    idesc_s, k > 0);
-      mma_commit(bars);
+      mma_commit(bars + 0);
     }
     for (int c = 0; c < nchunks; ++c) {
-      mbar_wait(bars, phase);
-      phase ^= 1;
+      // S of the NEXT chunk is issued before this chunk is processed (its TMEM buffer was drained one chunk ago)
+      if (tid == 0 && c + 1 < nchunks) {
+        const uint32_t tSn = tS + ((c + 1) & 1) * KC;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          mma_f16_ss(tSn, desc_nosw(smem_u32(sQ) + k * 256, 128, 512),
+                     desc_nosw(smem_u32(sK) + (c + 1) * KC * (DH * 2) + k * 256, 128, 512), idesc_s, k > 0);
+        mma_commit(bars + ((c + 1) & 1));
+      }
+      if (c & 1) { mbar_wait(bars + 1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bars + 0, ph_s0); ph_s0 ^= 1; }
       tc_fence_after();
       uint32_t s[32];
       tmem_ld_32x32(tS + (c & 1) * KC + lane_off + half * 32, s);
@@ -248,6 +259,10 @@ attn_fwd_kernel(const AttnParams p) {
           pk[j >> 1] = pack_bf16(e0, e1);
         }
       }
+      if (c > 0) {  // the previous P V must have finished reading the P tile
+        mbar_wait(bars + 2, ph_o);
+        ph_o ^= 1;
+      }
       // this thread's 32 columns of the P tile (128 x 64, K-major core matrices)
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8)
@@ -263,20 +278,13 @@ attn_fwd_kernel(const AttnParams p) {
         for (int k = 0; k < KC / 16; ++k)
           mma_f16_ss(tO, desc_nosw(smem_u32(sP) + k * 256, 128, (KC / 8) * 128),
                      desc_nosw(smem_u32(sV) + (c * KC + k * 16) * (DH * 2), 512, 128), idesc_o, (c > 0 || k > 0));
-        if (c + 1 < nchunks) {
-          const uint32_t tSn = tS + ((c + 1) & 1) * KC;
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            mma_f16_ss(tSn, desc_nosw(smem_u32(sQ) + k * 256, 128, 512),
-                       desc_nosw(smem_u32(sK) + (c + 1) * KC * (DH * 2) + k * 256, 128, 512), idesc_s, k > 0);
-        }
-        mma_commit(bars);
+        mma_commit(bars + 2);
       }
     }
     // ---- epilogue of this query tile: each column half stores 16 of the 32 output columns
     sL[half * 128 + rowt] = l;
-    mbar_wait(bars, phase);
-    phase ^= 1;
+    mbar_wait(bars + 2, ph_o);
+    ph_o ^= 1;
     tc_fence_after();
     __syncthreads();
     {
@@ -327,22 +335,26 @@ struct AttnBwdParams {
 
 constexpr int BKC = 128;  // keys per chunk (backward)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const AttnBwdParams bp) {
+  // 256 threads: thread t owns row (t & 127) of the current 128-row tile and the 64-column half (t >> 7) of the
+  // 128-key chunk. Q~_i / dO_i tiles are (re)built per step into double-buffered shared tiles (global rows are
+  // prefetched into registers one step ahead), so that 8 private dbias tables fit next to the P / dS tiles.
   const AttnParams& p = bp.f;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int head = blockIdx.x % p.heads;
   const int blk = blockIdx.x / p.heads;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowt = tid & 127, half = tid >> 7;
   const int R = p.ns * p.n;
   const int nchunks = (R + BKC - 1) / BKC;
   const int ntiles = (R + QT - 1) / QT;
   const bool has_bias = p.bias_table != nullptr;
   const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
 
-  uint8_t* sQ = smem;                              // r_pad x 32
-  uint8_t* sdO = sQ + p.r_pad * DH * 2;            // r_pad x 32
-  uint8_t* sK = sdO + p.r_pad * DH * 2;            // 128 x 32
+  uint8_t* sQt = smem;                             // 2 x (128 x 32)  Q~ tile, double buffered
+  uint8_t* sdOt = sQt + 2 * QT * DH * 2;           // 2 x (128 x 32)  dO tile
+  uint8_t* sK = sdOt + 2 * QT * DH * 2;            // 128 x 32
   uint8_t* sV = sK + BKC * DH * 2;                 // 128 x 32
   uint8_t* sP = sV + BKC * DH * 2;                 // 128 x 128
   uint8_t* sdS = sP + QT * BKC * 2;                // 128 x 128
@@ -350,14 +362,15 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   float* sLse = reinterpret_cast<float*>(sB + p.r_pad);
   float* sDelta = sLse + p.r_pad;
   float* sScale = sDelta + p.r_pad;                // [64]
-  float* sRed = sScale + 64;                       // [64] dq_scale | dk_scale partial sums
+  float* sRed = sScale + 64;                       // [64]
   float* sTab = sRed + 64;                         // [tab_n] bias * log2e
-  float* sdTab = sTab + tab_n;                     // [4][tab_n] per-warp private dbias accumulators
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sdTab + 4 * tab_n) + 15) & ~uintptr_t(15));
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  float* sdTab = sTab + tab_n;                     // [8][tab_n] per-warp private dbias accumulators
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sdTab + 8 * tab_n) + 15) & ~uintptr_t(15));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   if (tid == 0) {
-    mbar_init(bars, 1);
+    mbar_init(bars + 0, 1);  // S / dP of the current step ready
+    mbar_init(bars + 1, 1);  // dV / dK / dQ MMAs of the current step retired (P, dS, Q~/dO tile buffers free)
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -370,35 +383,25 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   }
   if (tid < 64) sRed[tid] = 0.f;
   for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
-  for (int i = tid; i < 4 * tab_n; i += blockDim.x) sdTab[i] = 0.f;
+  for (int i = tid; i < 8 * tab_n; i += blockDim.x) sdTab[i] = 0.f;
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     const int kp = r % p.n;
     sB[r] = (kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw);
   }
-  __syncthreads();
-
-  // ---- Q~, dO, lse, delta for the whole block
+  // ---- lse and delta = rowsum(dO * O) for the whole block
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
     if (valid) {
-      float v[DH];
-      const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
-#pragma unroll
-      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d] * (kScale * kLog2e);
-      store_row_cm(sQ, r, v);
       float go[DH], oo[DH];
       load_head_row(bp.d_o + tok * p.ldo + head * DH, go);
       load_head_row(p.o + tok * p.ldo + head * DH, oo);
-      store_row_cm(sdO, r, go);
       float dl = 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) dl = fmaf(go[d], oo[d], dl);
       sDelta[r] = dl;
       sLse[r] = p.lse[tok * p.heads + head];
     } else {
-      store_zero_row_cm(sQ, r);
-      store_zero_row_cm(sdO, r);
       sDelta[r] = 0.f;
       sLse[r] = INFINITY;  // exp2(x - inf) = 0: invalid query rows contribute nothing
     }
@@ -408,80 +411,131 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 288, tdQ = tmem + 320;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKC, false, false);   // [128 q] x [128 keys], K = 32
   constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
   constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
   constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
+  constexpr uint32_t TILE_B = QT * DH * 2;                               // bytes of one Q~ / dO tile buffer
   float* my_dtab = sdTab + warp * tab_n;
-  uint32_t phase = 0;
+  uint32_t ph_s = 0, ph_m = 0;
+  float acc_qs[DH], acc_ks[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc_qs[d] = acc_ks[d] = 0.f;
 
+  // half 0 builds Q~ rows, half 1 copies dO rows. `pre` holds the raw global row of the NEXT step's tile.
+  uint4 pre[4];
+  auto prefetch_tile_row = [&](int tile) {
+    const int r = tile * QT + rowt;
+    bool valid = false;
+    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    if (valid) {
+      const uint4* src = reinterpret_cast<const uint4*>((half == 0 ? p.q + tok * p.ldq : bp.d_o + tok * p.ldo) + head * DH);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[j] = src[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[j] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  auto store_tile_row = [&](int buf) {
+    if (half == 0) {
+      float v[DH];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w4[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[8 * j + 2 * k] = bf16_lo(w4[k]);
+          v[8 * j + 2 * k + 1] = bf16_hi(w4[k]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < DH; ++d) ss = fmaf(v[d], v[d], ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d] * (kScale * kLog2e);
+      store_row_cm(sQt + buf * TILE_B, rowt, v);
+    } else {
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sdOt + buf * TILE_B + cm_off(rowt, c8, DH)) = pre[c8];
+    }
+  };
+
+  int step = 0;  // global step counter -> tile buffer parity
   for (int c = 0; c < nchunks; ++c) {
-    // ---- K^_c, V_c (thread = key row)
-    const int kr = c * BKC + tid;
+    // ---- K^_c (half 0) and V_c (half 1); thread = key row
+    const int kr = c * BKC + rowt;
     bool kvalid = false;
     const long long ktok = (kr < R) ? row_token(p, blk, kr, kvalid) : 0;
     float kraw[DH];
     float kinv = 0.f;
-    if (kvalid) {
-      kinv = load_head_row(p.kv + ktok * p.ldkv + head * DH, kraw);
-      float v[DH];
+    if (half == 0) {
+      if (kvalid) {
+        kinv = load_head_row(p.kv + ktok * p.ldkv + head * DH, kraw);
+        float v[DH];
 #pragma unroll
-      for (int d = 0; d < DH; ++d) v[d] = kraw[d] * kinv * sScale[DH + d];
-      store_row_cm(sK, tid, v);
-      const uint4* s4 = reinterpret_cast<const uint4*>(p.kv + ktok * p.ldkv + p.inner + head * DH);
-#pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sV + cm_off(tid, c8, DH)) = s4[c8];
+        for (int d = 0; d < DH; ++d) v[d] = kraw[d] * kinv * sScale[DH + d];
+        store_row_cm(sK, rowt, v);
+      } else {
+        store_zero_row_cm(sK, rowt);
+      }
     } else {
-      store_zero_row_cm(sK, tid);
-      store_zero_row_cm(sV, tid);
+      if (kvalid) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(p.kv + ktok * p.ldkv + p.inner + head * DH);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sV + cm_off(rowt, c8, DH)) = s4[c8];
+      } else {
+        store_zero_row_cm(sV, rowt);
+      }
     }
+    // first tile of this chunk
+    prefetch_tile_row(0);
+    if (step > 0) {  // previous step's MMAs read the tile buffer we are about to reuse two steps later: parity is safe,
+      // but sK / sV are read by the previous chunk's dQ / S / dP MMAs -> they retired (bars+1 waited in the epilogue)
+    }
+    store_tile_row(step & 1);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      const uint32_t q0 = smem_u32(sQt) + (step & 1) * TILE_B, o0 = smem_u32(sdOt) + (step & 1) * TILE_B;
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k) {
-        mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512),
-                   idesc_s, k > 0);
-        mma_f16_ss(tdP, desc_nosw(smem_u32(sdO) + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512),
-                   idesc_s, k > 0);
+        mma_f16_ss(tS, desc_nosw(q0 + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
+        mma_f16_ss(tdP, desc_nosw(o0 + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
       }
-      mma_commit(bars);
+      mma_commit(bars + 0);
     }
-    for (int i = 0; i < ntiles; ++i) {
-      const int r = i * QT + tid;
+    for (int i = 0; i < ntiles; ++i, ++step) {
+      const int buf = step & 1;
+      const int r = i * QT + rowt;
       const int my_seq = r / p.n;
       const int my_pos = r - my_seq * p.n;
       const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);
       const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
       const float lse_i = sLse[r], delta_i = sDelta[r];
-      mbar_wait(bars, phase);
-      phase ^= 1;
+      if (i + 1 < ntiles) prefetch_tile_row(i + 1);  // global latency hidden behind this step's element-wise work
+      mbar_wait(bars + 0, ph_s);
+      ph_s ^= 1;
       tc_fence_after();
-#pragma unroll 1
-      for (int piece = 0; piece < BKC / 32; ++piece) {
-        const int k0 = c * BKC + piece * 32;
-        if (k0 >= R) {  // warp-uniform: nothing but padding keys in this piece
+      uint32_t pk[32], dk[32];
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            *reinterpret_cast<uint4*>(sP + cm_off(tid, piece * 4 + c8, BKC)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(sdS + cm_off(tid, piece * 4 + c8, BKC)) = make_uint4(0, 0, 0, 0);
-          }
-          continue;
-        }
+      for (int piece = 0; piece < 2; ++piece) {
+        const int col = half * 64 + piece * 32;
+        const int k0 = c * BKC + col;
         uint32_t s[32], dp[32];
-        tmem_ld_32x32(tS + lane_off + piece * 32, s);
-        tmem_ld_32x32(tdP + lane_off + piece * 32, dp);
+        tmem_ld_32x32(tS + lane_off + col, s);
+        tmem_ld_32x32(tdP + lane_off + col, dp);
         tmem_wait_ld();
-        uint32_t pk[16], dk[16];
         if (has_bias) {
           const float* tabp = sTab + a_i;
           float* dtabp = my_dtab + a_i;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const int2 b2 = *reinterpret_cast<const int2*>(sB + k0 + j);
+            const int2 b2 = *reinterpret_cast<const int2*>(sB + min(k0 + j, p.r_pad - 2));
             const float x0 = __uint_as_float(s[j]) - lse_i + tabp[-b2.x];
             const float x1 = __uint_as_float(s[j + 1]) - lse_i + tabp[-b2.y];
             const float p0 = (k0 + j < key_hi) ? exp2f(x0) : 0.f;
@@ -493,8 +547,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
             __syncwarp();
             if (r < R) dtabp[-b2.y] += d1;
             __syncwarp();
-            pk[j >> 1] = pack_bf16(p0, p1);
-            dk[j >> 1] = pack_bf16(d0, d1);
+            pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);
+            dk[piece * 16 + (j >> 1)] = pack_bf16(d0, d1);
           }
         } else {
 #pragma unroll
@@ -504,60 +558,63 @@ attn_bwd_kernel(const AttnBwdParams bp) {
             const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? exp2f(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
             const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
             const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-            pk[j >> 1] = pack_bf16(p0, p1);
-            dk[j >> 1] = pack_bf16(d0, d1);
+            pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);
+            dk[piece * 16 + (j >> 1)] = pack_bf16(d0, d1);
           }
         }
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          *reinterpret_cast<uint4*>(sP + cm_off(tid, piece * 4 + c8, BKC)) =
-              make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-          *reinterpret_cast<uint4*>(sdS + cm_off(tid, piece * 4 + c8, BKC)) =
-              make_uint4(dk[4 * c8], dk[4 * c8 + 1], dk[4 * c8 + 2], dk[4 * c8 + 3]);
-        }
       }
+      // the previous step's dV / dK / dQ MMAs must have finished reading the P / dS tiles
+      if (step > 0) {
+        mbar_wait(bars + 1, ph_m);
+        ph_m ^= 1;
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        *reinterpret_cast<uint4*>(sP + cm_off(rowt, half * 8 + c8, BKC)) =
+            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+        *reinterpret_cast<uint4*>(sdS + cm_off(rowt, half * 8 + c8, BKC)) =
+            make_uint4(dk[4 * c8], dk[4 * c8 + 1], dk[4 * c8 + 2], dk[4 * c8 + 3]);
+      }
+      // next tile's Q~ / dO rows go to the other buffer (its last readers, the MMAs of step-1, have retired)
+      if (i + 1 < ntiles) store_tile_row(buf ^ 1);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        const uint32_t qoff = (uint32_t)i * QT * (DH * 2);
+        const uint32_t qb = smem_u32(sQt) + buf * TILE_B, ob = smem_u32(sdOt) + buf * TILE_B;
 #pragma unroll
         for (int k = 0; k < QT / 16; ++k) {  // reduction over the 128 queries of this tile
           const uint64_t dPt = desc_nosw(smem_u32(sP) + k * 2 * P_RS, P_RS, 128);     // P^T  (MN-major A)
           const uint64_t dSt = desc_nosw(smem_u32(sdS) + k * 2 * P_RS, P_RS, 128);    // dS^T (MN-major A)
-          const uint64_t ddO = desc_nosw(smem_u32(sdO) + qoff + k * 1024, 512, 128);  // dO_i  (MN-major B)
-          const uint64_t dQt = desc_nosw(smem_u32(sQ) + qoff + k * 1024, 512, 128);   // Q~_i  (MN-major B)
-          mma_f16_ss(tdV, dPt, ddO, idesc_kv, (i > 0 || k > 0));
-          mma_f16_ss(tdK, dSt, dQt, idesc_kv, (i > 0 || k > 0));
+          mma_f16_ss(tdV, dPt, desc_nosw(ob + k * 1024, 512, 128), idesc_kv, (i > 0 || k > 0));   // dO_i (MN-major B)
+          mma_f16_ss(tdK, dSt, desc_nosw(qb + k * 1024, 512, 128), idesc_kv, (i > 0 || k > 0));   // Q~_i
         }
 #pragma unroll
         for (int k = 0; k < BKC / 16; ++k)  // reduction over the 128 keys of this chunk
           mma_f16_ss(tdQ + i * DH, desc_nosw(smem_u32(sdS) + k * 256, 128, P_RS),
                      desc_nosw(smem_u32(sK) + k * 1024, 512, 128), idesc_q, (c > 0 || k > 0));
+        mma_commit(bars + 1);
         if (i + 1 < ntiles) {
-          const uint32_t qn = (uint32_t)(i + 1) * QT * (DH * 2);
+          const uint32_t qn = smem_u32(sQt) + (buf ^ 1) * TILE_B, on = smem_u32(sdOt) + (buf ^ 1) * TILE_B;
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) {
-            mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + qn + k * 256, 128, 512),
-                       desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
-            mma_f16_ss(tdP, desc_nosw(smem_u32(sdO) + qn + k * 256, 128, 512),
-                       desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
+            mma_f16_ss(tS, desc_nosw(qn + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
+            mma_f16_ss(tdP, desc_nosw(on + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
           }
+          mma_commit(bars + 0);
         }
-        mma_commit(bars);
       }
     }
-    // ---- chunk epilogue: dV_c, dK^_c -> dkv rows (thread = key row)
-    mbar_wait(bars, phase);
-    phase ^= 1;
+    // ---- chunk epilogue: wait for the last dV / dK MMAs; half 1 stores dV_c rows, half 0 stores dK_c rows
+    mbar_wait(bars + 1, ph_m);
+    ph_m ^= 1;
     tc_fence_after();
     {
-      uint32_t a[32], b[32];
-      tmem_ld_32x32(tdV + lane_off, a);
-      tmem_ld_32x32(tdK + lane_off, b);
+      uint32_t a[32];
+      tmem_ld_32x32((half ? tdV : tdK) + lane_off, a);
       tmem_wait_ld();
-      if (kvalid) {
+      if (kvalid && half == 1) {
         uint4* dv = reinterpret_cast<uint4*>(bp.dkv + ktok * p.ldkv + p.inner + head * DH);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -565,13 +622,15 @@ attn_bwd_kernel(const AttnBwdParams bp) {
                              pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
                              pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
                              pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+      }
+      if (kvalid && half == 0) {
         // k^ = ks * k / |k| : dk = (g - kbar (kbar.g)) / |k|, g = ks * dk^ ; dks += dk^ * kbar
         float g[DH], dot = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; ++d) {
-          const float dkh = __uint_as_float(b[d]) * (1.f / kLog2e);
+          const float dkh = __uint_as_float(a[d]) * (1.f / kLog2e);
           const float kbar = kraw[d] * kinv;
-          atomicAdd(&sRed[DH + d], dkh * kbar);
+          acc_ks[d] = fmaf(dkh, kbar, acc_ks[d]);
           g[d] = dkh * sScale[DH + d];
           dot = fmaf(g[d], kbar, dot);
         }
@@ -586,14 +645,17 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         }
       }
     }
+    // the step counter keeps running across chunks; the bars+1 phase consumed above belongs to the last step, so the
+    // first step of the next chunk must not wait on it again
     tc_fence_before();
     __syncthreads();
+    step = 0;  // restart parity bookkeeping for the next chunk (all MMAs retired, all buffers free)
   }
 
-  // ---- dQ epilogue (thread = query row)
+  // ---- dQ epilogue (thread = query row; tile i handled by column-half i & 1)
   tc_fence_after();
-  for (int i = 0; i < ntiles; ++i) {
-    const int r = i * QT + tid;
+  for (int i = half; i < ntiles; i += 2) {
+    const int r = i * QT + rowt;
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
     uint32_t a[32];
@@ -607,7 +669,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       for (int d = 0; d < DH; ++d) {
         const float dqh = __uint_as_float(a[d]) * kScale;  // d/dq^ = 8 * dz K^
         const float qbar = qraw[d] * qinv;
-        atomicAdd(&sRed[d], dqh * qbar);
+        acc_qs[d] = fmaf(dqh, qbar, acc_qs[d]);
         g[d] = dqh * sScale[d];
         dot = fmaf(g[d], qbar, dot);
       }
@@ -624,14 +686,33 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   }
   tc_fence_before();
   __syncthreads();
+  {
+    // cross-thread reduction of the scale gradients through the (now idle) P / dS tiles: [256 threads][64 + 1] floats
+    float* scratch = reinterpret_cast<float*>(smem);  // 66.5 KB <= tiles + K + V + P + dS (112 KB)
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      scratch[tid * 65 + d] = acc_qs[d];
+      scratch[tid * 65 + DH + d] = acc_ks[d];
+    }
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+      for (int r = 0; r < 256; ++r) t += scratch[r * 65 + tid];
+      sRed[tid] = t;
+    }
+    __syncthreads();
+  }
   if (tid < DH) {
     if (bp.dq_scale != nullptr) atomicAdd(bp.dq_scale + tid, sRed[tid]);
     if (bp.dk_scale != nullptr) atomicAdd(bp.dk_scale + tid, sRed[DH + tid]);
   }
   if (has_bias && bp.dbias_table != nullptr)
-    for (int i = tid; i < tab_n; i += blockDim.x)
-      atomicAdd(bp.dbias_table + (long long)head * tab_n + i,
-                (sdTab[i] + sdTab[tab_n + i]) + (sdTab[2 * tab_n + i] + sdTab[3 * tab_n + i]));
+    for (int i = tid; i < tab_n; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sdTab[w * tab_n + i];
+      atomicAdd(bp.dbias_table + (long long)head * tab_n + i, t);
+    }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -640,13 +721,14 @@ attn_bwd_kernel(const AttnBwdParams bp) {
 
 size_t bwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
-  return (size_t)p.r_pad * DH * 2 * 2 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
-         (size_t)tab_n * 4 * 5 + 128 * 4 + 64 + 16;
+  return (size_t)QT * DH * 2 * 4 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
+         (size_t)tab_n * 4 * 9 + 128 * 4 + 64 + 16;
 }
 
 size_t fwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) + p.n : 0;
-  return (size_t)p.r_pad * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 256 * 4 +
+  const size_t kv_rows = (size_t)((p.ns * p.n + KC - 1) / KC) * KC;
+  return kv_rows * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 256 * 4 +
          (size_t)p.r_pad * 4 + 64 + 16;
 }
 
@@ -718,6 +800,6 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream) {
     configured = smem;
   }
   const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
-  attn_bwd_kernel<<<(unsigned)(blocks * p.heads), 128, smem, (cudaStream_t)stream>>>(bp);
+  attn_bwd_kernel<<<(unsigned)(blocks * p.heads), 256, smem, (cudaStream_t)stream>>>(bp);
   return ctclip::check_launch("attn_bwd");
 }

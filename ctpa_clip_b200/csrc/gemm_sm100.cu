@@ -31,7 +31,8 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kStageOut = kStages * kStageBytes;             // 4 epilogue warps x 32 rows x 128 B staging
+  static constexpr int kBarOffset = kStageOut + 4 * 32 * 128;
   static constexpr int kTotal = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
 };
 
@@ -109,6 +110,73 @@ __device__ __forceinline__ void store_row_chunk(const GemmKernelParams& p, int r
       for (int j = 0; j < 32; ++j)
         if (j < ncols) c[j] = __float2bfloat16_rn(v[j]);
     }
+  }
+}
+
+// Coalesced epilogue for a full, aligned 32-column chunk: the warp's 32x32 accumulator block (one row per thread) is
+// transposed through a swizzled shared-memory staging tile so that global loads/stores cover whole 128-byte lines
+// (fp32: 8 lanes x 16 B per row, 4 rows per instruction; bf16: 4 lanes x 16 B per row, 8 rows per instruction).
+__device__ __forceinline__ void store_chunk_coalesced(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
+                                                      const float (&v)[32], int lane) {
+  if (p.c_is_f32) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8)
+      *reinterpret_cast<float4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) =
+          make_float4(v[4 * c8], v[4 * c8 + 1], v[4 * c8 + 2], v[4 * c8 + 3]);
+    __syncwarp();
+    const int c8 = lane & 7;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + col0 + c8 * 4);
+    // all residual loads of the chunk are issued before the first store (resid may alias C: no reordering by the compiler)
+    float4 rr[8];
+    if (p.resid != nullptr && !p.atomic) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + (lane >> 3);
+        rr[it] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + c8 * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) rr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = it * 4 + (lane >> 3);
+      const int grow = row0 + i;
+      float4 x = *reinterpret_cast<const float4*>(stg + i * 128 + ((c8 ^ (i & 7)) << 4));
+      x.x += bias4.x + rr[it].x; x.y += bias4.y + rr[it].y; x.z += bias4.z + rr[it].z; x.w += bias4.w + rr[it].w;
+      if (grow < p.M) {
+        float* c = reinterpret_cast<float*>(p.C) + (long long)grow * p.ldc + col0 + c8 * 4;
+        if (p.atomic) {
+          atomicAdd(c + 0, x.x); atomicAdd(c + 1, x.y); atomicAdd(c + 2, x.z); atomicAdd(c + 3, x.w);
+        } else {
+          *reinterpret_cast<float4*>(c) = x;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float b[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) b[e] = v[8 * c4 + e] + (p.bias != nullptr ? __ldg(p.bias + col0 + 8 * c4 + e) : 0.f);
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((c4 ^ sw) << 4)) =
+          make_uint4(pack_bf16(b[0], b[1]), pack_bf16(b[2], b[3]), pack_bf16(b[4], b[5]), pack_bf16(b[6], b[7]));
+    }
+    __syncwarp();
+    const int c4 = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = it * 8 + (lane >> 2);
+      const int grow = row0 + i;
+      const uint4 x = *reinterpret_cast<const uint4*>(stg + i * 64 + ((c4 ^ ((i >> 1) & 3)) << 4));
+      if (grow < p.M)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)grow * p.ldc + col0 + c4 * 8) = x;
+    }
+    __syncwarp();
   }
 }
 
@@ -230,6 +298,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
+    // 16-byte alignment of every row start of C / resid / bias -> the coalesced 128-bit epilogue is legal
+    const bool aligned_out =
+        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc * (p.c_is_f32 ? 4 : 2)) % 16 == 0) &&
+        (p.resid == nullptr || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && ((p.ldr * 4) % 16 == 0))) &&
+        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -264,14 +337,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
-        if (n_t * BN + c >= p.N) break;  // warp-uniform
+        const int col0 = n_t * BN + c;
+        if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
         tmem_wait_ld();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        store_row_chunk(p, row, n_t * BN + c, v);
+        if (aligned_out && col0 + 32 <= p.N)
+          store_chunk_coalesced(p, smem + L::kStageOut + ew * (32 * 128), m_t * BM + ew * 32, col0, v, lane);
+        else
+          store_row_chunk(p, row, col0, v);
       }
       tc_fence_before();
       __syncwarp();

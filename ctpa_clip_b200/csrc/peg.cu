@@ -150,6 +150,7 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
                  float* __restrict__ dw27, float* __restrict__ dbias, PegGrid g, int dim) {
   __shared__ float planes[3][PH * PW][32];
   __shared__ float dyp[MODE == 2 ? TH * TW : 1][32];
+  __shared__ int tok[PH * PW];  // canonical token index of every position of the current plane (-1 outside the grid)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = blockIdx.y * 32 + lane;
   const int tiles_w = (g.w + TW - 1) / TW;
@@ -180,29 +181,31 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
 
   for (int step = 0; step < g.t; ++step) {
     const int vt = flip ? g.t - 1 - step : step;
+    // ---- token indices of this plane (one thread per position: the divisions happen once, not per warp)
+    if (threadIdx.x < PH * PW) {
+      const int vh = h0 - 1 + threadIdx.x / PW, vw = w0 - 1 + threadIdx.x % PW;
+      tok[threadIdx.x] = (vh >= 0 && vh < g.h && vw >= 0 && vw < g.w) ? virtual_to_canon(vt, vh, vw, g) : -1;
+    }
+    __syncthreads();
     // ---- load plane vt into slot step % 3 (zero outside the grid)
     float (*slot)[32] = planes[step % 3];
     for (int pos = warp; pos < PH * PW; pos += 8) {
-      const int vh = h0 - 1 + pos / PW, vw = w0 - 1 + pos % PW;
-      float v = 0.f;
-      if (vh >= 0 && vh < g.h && vw >= 0 && vw < g.w) v = base[(long long)virtual_to_canon(vt, vh, vw, g) * dim + ch];
-      slot[pos][lane] = v;
+      const int tk = tok[pos];
+      slot[pos][lane] = (tk >= 0) ? base[(long long)tk * dim + ch] : 0.f;
     }
     if (MODE == 2) {
       const float* base2 = in2 + b * per_b * dim;
       for (int pos = warp; pos < TH * TW; pos += 8) {
-        const int vh = h0 + pos / TW, vw = w0 + pos % TW;
-        float v = 0.f;
-        if (vh < g.h && vw < g.w) v = base2[(long long)virtual_to_canon(vt, vh, vw, g) * dim + ch];
-        dyp[pos][lane] = v;
+        const int tk = tok[(pos / TW + 1) * PW + pos % TW + 1];
+        dyp[pos][lane] = (tk >= 0) ? base2[(long long)tk * dim + ch] : 0.f;
       }
     }
     __syncthreads();
     // ---- outputs of plane vt
     for (int pos = warp; pos < TH * TW; pos += 8) {
       const int oh = pos / TW, ow = pos % TW;
-      const int vh = h0 + oh, vw = w0 + ow;
-      if (vh >= g.h || vw >= g.w) continue;
+      const int tk = tok[(oh + 1) * PW + ow + 1];
+      if (tk < 0) continue;
       if (MODE != 2) {
         float acc = planes[step % 3][(oh + 1) * PW + ow + 1][lane] + bval;
 #pragma unroll
@@ -216,7 +219,7 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
             for (int kw = 0; kw < 3; ++kw)
               acc = fmaf(wt[(kt * 3 + kh) * 3 + kw], pl[(oh + kh) * PW + ow + kw][lane], acc);
         }
-        const long long o = (b * per_b + virtual_to_canon(vt, vh, vw, g)) * dim + ch;
+        const long long o = (b * per_b + tk) * dim + ch;
         out[o] = acc;
         if (MODE == 1 && out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(acc);
       } else {

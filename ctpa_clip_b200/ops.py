@@ -229,7 +229,8 @@ def attn_fwd(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table=None, bi
     lse = torch.empty((tokens, heads), device=q.device, dtype=torch.float32)
     d = _attn_desc(q, kv, grid, heads, temporal, q_scale, k_scale, bias_table, bias_rowmax)
     d.o, d.ldo, d.lse = o.data_ptr(), o.stride(0), lse.data_ptr()
-    _call("ctclip_attn_fwd", C.byref(d), _stream())
+    with _Span("attn_fwd:" + ("temporal" if temporal else "spatial")):
+        _lib.check(_lib.lib().ctclip_attn_fwd(C.byref(d), _stream()), "ctclip_attn_fwd")
     return o, lse
 
 
@@ -247,7 +248,8 @@ def attn_bwd(q, kv, o, lse, d_o, grid, heads, temporal, q_scale, k_scale, dq_sca
     d.dq_scale, d.dk_scale = dq_scale.data_ptr(), dk_scale.data_ptr()
     if dbias_table is not None and not temporal:
         d.dbias_table = dbias_table.data_ptr()
-    _call("ctclip_attn_bwd", C.byref(d), _stream())
+    with _Span("attn_bwd:" + ("temporal" if temporal else "spatial")):
+        _lib.check(_lib.lib().ctclip_attn_bwd(C.byref(d), _stream()), "ctclip_attn_bwd")
     return dq, dkv
 
 

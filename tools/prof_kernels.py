@@ -1,0 +1,43 @@
+"""Runs one production-size launch of each hot kernel (for `ncu --set full -k regex:...`)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from ctpa_clip_b200 import ops
+from ctpa_clip_b200.ct_clip.attention import pair_index
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = "cuda"
+t = h = w = 24
+T, D, heads = B * t * h * w, 512, 8
+grid = (B, t, h, w)
+g = torch.Generator(device=dev).manual_seed(0)
+x = torch.randn(T, D, device=dev, generator=g)
+w27 = torch.randn(27, D, device=dev, generator=g) / 5
+bias = torch.randn(D, device=dev, generator=g)
+for temporal in (False, True):
+    y = ops.peg_fwd(x, w27, bias, grid, temporal)
+    dx, _ = ops.peg_bwd_data(x, w27, grid, temporal)
+    dw = torch.zeros(27, D, device=dev); db = torch.zeros(D, device=dev)
+    ops.peg_bwd_weight(x, y, dw, db, grid, temporal)
+q = torch.randn(T, 256, device=dev, generator=g).bfloat16()
+kv = torch.randn(T, 512, device=dev, generator=g).bfloat16()
+qs = torch.ones(32, device=dev); ks = torch.ones(32, device=dev)
+tab = torch.randn(heads, 47 * 47, device=dev, generator=g)
+rowmax = tab[:, pair_index(h, w, dev)].amax(-1).contiguous()
+for temporal in (False, True):
+    o, lse = ops.attn_fwd(q, kv, grid, heads, temporal, qs, ks, tab, rowmax)
+    d_o = torch.randn_like(o)
+    dqs = torch.zeros(32, device=dev); dks = torch.zeros(32, device=dev); dtab = torch.zeros_like(tab)
+    ops.attn_bwd(q, kv, o, lse, d_o, grid, heads, temporal, qs, ks, dqs, dks, tab, rowmax, dtab)
+xf = torch.randn(T, 512, device=dev, generator=g).bfloat16()
+w1 = torch.randn(2736, 512, device=dev, generator=g).bfloat16()
+h1 = ops.gemm(xf, w1)                                             # ff1 forward, bf16 out
+wo = torch.randn(512, 256, device=dev, generator=g).bfloat16()
+x2 = ops.gemm(q, wo, out_dtype=torch.float32, resid=x)            # out-proj + residual, fp32 out
+dw1 = torch.zeros(2736, 512, device=dev)
+ops.gemm(h1, xf, a_t=True, b_t=True, out=dw1, accumulate=True, splits=0)   # wgrad ff1
+dy = torch.randn(T, D, device=dev, generator=g)
+gam = torch.ones(D, device=dev)
+dg = torch.zeros(D, device=dev)
+ops.layernorm_bwd(dy, x, gam, add_in=dy, dgamma=dg, want_bf16=True)
+torch.cuda.synchronize()
+print("done")
