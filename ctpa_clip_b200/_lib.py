@@ -87,4 +87,5 @@ class PrepDesc(C.Structure):
         ("oD", C.c_int), ("oH", C.c_int), ("oW", C.c_int),
         ("tD", C.c_int), ("tH", C.c_int), ("tW", C.c_int),
         ("pad_value", C.c_float),
+        ("lut_workspace", C.c_void_p),
     ]

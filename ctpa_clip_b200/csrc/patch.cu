@@ -79,6 +79,48 @@ patch_ln_fwd_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__
   }
 }
 
+// 128-bit variant (patch width % 4 == 0, so every 4-element group lies inside one contiguous w-run of the volume)
+__global__ void __launch_bounds__(kThreads)
+patch_ln_fwd_vec4_kernel(const float* __restrict__ video, __nv_bfloat16* __restrict__ out, long long ld_out,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, PatchGeom g) {
+  __shared__ float red[kThreads / 32];
+  const long long token = blockIdx.x;
+  const float* base = patch_base(video, g, token);
+  constexpr int kSlots = kMaxPer / 4;
+  const int nvec = g.pdim >> 2;
+  float4 v[kSlots];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int f = threadIdx.x + j * kThreads;
+    v[j] = (f < nvec) ? *reinterpret_cast<const float4*>(base + patch_elem_off(g, 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = block_sum(s, red) / g.pdim;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int f = threadIdx.x + j * kThreads;
+    if (f < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / g.pdim + eps);
+  __nv_bfloat16* orow = out + token * ld_out;
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int f = threadIdx.x + j * kThreads;
+    if (f < nvec) {
+      const float4 gm = reinterpret_cast<const float4*>(gamma)[f];
+      const float4 bt = reinterpret_cast<const float4*>(beta)[f];
+      const float o0 = (v[j].x - mean) * rstd * gm.x + bt.x, o1 = (v[j].y - mean) * rstd * gm.y + bt.y;
+      const float o2 = (v[j].z - mean) * rstd * gm.z + bt.z, o3 = (v[j].w - mean) * rstd * gm.w + bt.w;
+      reinterpret_cast<uint2*>(orow)[f] = make_uint2(ptx::pack_bf16(o0, o1), ptx::pack_bf16(o2, o3));
+    }
+  }
+}
+
 // LayerNorm(pdim) parameter gradients WITHOUT the tokens x pdim dgrad GEMM. With A = xhat*gamma + beta (the GEMM operand),
 // Y = A W^T + b and s = colsum(dY) (= the Linear's bias gradient):
 //   dW[n][e]  = sum_tok dY[tok][n] A[tok][e] = gamma[e] * M[n][e] + beta[e] * s[n],   M = dY^T xhat
@@ -125,8 +167,15 @@ extern "C" int ctclip_patch_ln_fwd(const float* video, int batch, int frames, in
   if (rc) return rc;
   if (batch <= 0) return CTCLIP_OK;
   const long long tokens = (long long)batch * g.gt * g.gh * g.gw;
-  patch_ln_fwd_kernel<<<(unsigned)tokens, kThreads, 0, (cudaStream_t)stream>>>(video, (__nv_bfloat16*)out, ld_out, gamma,
-                                                                              beta, eps, g);
+  const bool vec4 = (ps % 4 == 0) && (width % 4 == 0) && (ld_out % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(video) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 8 == 0);
+  if (vec4)
+    patch_ln_fwd_vec4_kernel<<<(unsigned)tokens, kThreads, 0, (cudaStream_t)stream>>>(video, (__nv_bfloat16*)out, ld_out,
+                                                                                     gamma, beta, eps, g);
+  else
+    patch_ln_fwd_kernel<<<(unsigned)tokens, kThreads, 0, (cudaStream_t)stream>>>(video, (__nv_bfloat16*)out, ld_out, gamma,
+                                                                                beta, eps, g);
   return ctclip::check_launch("patch_ln_fwd");
 }
 

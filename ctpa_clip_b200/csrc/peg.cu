@@ -201,40 +201,48 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
       }
     }
     __syncthreads();
-    // ---- outputs of plane vt
-    for (int pos = warp; pos < TH * TW; pos += 8) {
-      const int oh = pos / TW, ow = pos % TW;
-      const int tk = tok[(oh + 1) * PW + ow + 1];
-      if (tk < 0) continue;
-      if (MODE != 2) {
-        float acc = planes[step % 3][(oh + 1) * PW + ow + 1][lane] + bval;
+    // ---- outputs of plane vt: warp = output row, lane = channel; each staged value feeds up to 3 outputs of the row
+    {
+      const int oh = warp;  // TH == 8 == warps per CTA
+      float acc[TW];
+      float dcur[TW];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (step - a < 0) continue;
-          float (*pl)[32] = planes[(step - a) % 3];
-          const int kt = 2 - a;
+      for (int ow = 0; ow < TW; ++ow) {
+        acc[ow] = planes[step % 3][(oh + 1) * PW + ow + 1][lane] + bval;  // residual + bias (MODE 0/1)
+        dcur[ow] = (MODE == 2) ? dyp[oh * TW + ow][lane] : 0.f;
+        if (MODE == 2) bsum += dcur[ow];
+      }
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
+      for (int a = 0; a < 3; ++a) {
+        if (step - a < 0) continue;
+        float (*pl)[32] = planes[(step - a) % 3];
+        const int kt = 2 - a;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              acc = fmaf(wt[(kt * 3 + kh) * 3 + kw], pl[(oh + kh) * PW + ow + kw][lane], acc);
+        for (int kh = 0; kh < 3; ++kh) {
+          float in[PW];
+#pragma unroll
+          for (int x = 0; x < PW; ++x) in[x] = pl[(oh + kh) * PW + x][lane];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int wi = (kt * 3 + kh) * 3 + kw;
+            if (MODE != 2) {
+#pragma unroll
+              for (int ow = 0; ow < TW; ++ow) acc[ow] = fmaf(wt[wi], in[ow + kw], acc[ow]);
+            } else {
+#pragma unroll
+              for (int ow = 0; ow < TW; ++ow) wt[wi] = fmaf(dcur[ow], in[ow + kw], wt[wi]);
+            }
+          }
         }
-        const long long o = (b * per_b + tk) * dim + ch;
-        out[o] = acc;
-        if (MODE == 1 && out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(acc);
-      } else {
-        const float d = dyp[pos][lane];
-        bsum += d;
+      }
+      if (MODE != 2) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (step - a < 0) continue;
-          float (*pl)[32] = planes[(step - a) % 3];
-          const int kt = 2 - a;
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              wt[(kt * 3 + kh) * 3 + kw] = fmaf(d, pl[(oh + kh) * PW + ow + kw][lane], wt[(kt * 3 + kh) * 3 + kw]);
+        for (int ow = 0; ow < TW; ++ow) {
+          const int tk = tok[(oh + 1) * PW + ow + 1];
+          if (tk < 0) continue;
+          const long long o = (b * per_b + tk) * dim + ch;
+          out[o] = acc[ow];
+          if (MODE == 1 && out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(acc[ow]);
         }
       }
     }

@@ -56,19 +56,38 @@ __device__ __forceinline__ float load_norm(const PrepParams& p, long long off) {
   return reinterpret_cast<const float*>(p.in)[off];
 }
 
+// exact HU normalisation table: lut[v - lut_lo] = float(clip(slope*v + intercept, -1000, 1000) / 1000) for raw values v in
+// [lut_lo, lut_hi]; outside that range the function is saturated, so clamping the index is exact.
+__global__ void prep_lut_kernel(float* lut, int lut_lo, int n, double slope, double intercept) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = __dmul_rn(slope, (double)(lut_lo + i));
+  v = __dadd_rn(v, intercept);
+  v = fmin(fmax(v, -1000.0), 1000.0);
+  lut[i] = (float)__ddiv_rn(v, 1000.0);
+}
+
+constexpr int OHB = 16;  // output rows (h) produced per CTA: input rows are staged once and reused
+
+// CTA = (TD x OHB x TW) output brick. The input rows (two per output row, shared between consecutive output rows)
+// rotate through three shared-memory slots; depth/width taps are computed once per CTA.
 __global__ void __launch_bounds__(kThreads)
-prep_resample_kernel(const PrepParams p) {
-  extern __shared__ float tile[];  // [2][kn_max][jn_pad]
+prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_lo, int lut_n) {
+  extern __shared__ float tile[];  // [3][kn_max][jn_pad] then the LUT copy
   __shared__ int s_d0[TD], s_d1[TD], s_w0[TW], s_w1[TW];
   __shared__ float s_wd0[TD], s_wd1[TD], s_ww0[TW], s_ww1[TW];
   const int jn_pad = p.jn_max | 1;
+  const int slot_elems = p.kn_max * jn_pad;
+  float* s_lut = tile + 3 * slot_elems;
   const int n_wt = (p.wwn + TW - 1) / TW;
-  const int oh = p.wh0 + blockIdx.x;                 // consecutive CTAs share input rows through L2
+  const int oh_base = p.wh0 + blockIdx.x * OHB;
+  const int n_oh = min(OHB, p.wh0 + p.whn - oh_base);
   const int od_base = p.wd0 + (blockIdx.y / n_wt) * TD;
   const int ow_base = p.ww0 + (blockIdx.y % n_wt) * TW;
   const int nd = min(TD, p.wd0 + p.wdn - od_base);
   const int nw = min(TW, p.ww0 + p.wwn - ow_base);
   const long long in_b = (long long)blockIdx.z * p.sbatch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   if (threadIdx.x < TD) {
     int a = 0, b = 0; float x = 0.f, y = 0.f;
@@ -80,54 +99,79 @@ prep_resample_kernel(const PrepParams p) {
     if (t < nw) taps(p.W, p.oW, ow_base + t, a, b, x, y);
     s_w0[t] = a; s_w1[t] = b; s_ww0[t] = x; s_ww1[t] = y;
   }
-  int h0, h1; float wh0, wh1;
-  taps(p.H, p.oH, oh, h0, h1, wh0, wh1);
+  for (int i = threadIdx.x; i < lut_n; i += kThreads) s_lut[i] = lut[i];
   __syncthreads();
   const int k_lo = s_d0[0], k_hi = s_d1[nd - 1];
   const int j_lo = s_w0[0], j_hi = s_w1[nw - 1];
   const int kn = k_hi - k_lo + 1, jn = j_hi - j_lo + 1;
+  const bool use_lut = lut_n > 0;
 
-  // ---- stage the two input rows: inner index runs along the contiguous input axis
-  const int total = 2 * kn * jn;
-  if (p.sd == 1) {  // raw scan layout (H, W, N): depth contiguous
-    for (int e = threadIdx.x; e < total; e += kThreads) {
-      const int k = e % kn;
-      const int j = (e / kn) % jn;
-      const int r = e / (kn * jn);
-      const long long off = in_b + (long long)(r ? h1 : h0) * p.sh + (long long)(j_lo + j) * p.sw + (k_lo + k);
-      tile[(r * p.kn_max + k) * jn_pad + j] = load_norm(p, off);
+  int loaded[3] = {-1, -1, -1};  // input row held by each slot (CTA-uniform bookkeeping)
+  auto stage_row = [&](int row) {
+    float* dst = tile + (row % 3) * slot_elems;
+    const long long row_off = in_b + (long long)row * p.sh;
+    if (p.sd == 1) {  // raw scan (H, W, N): depth contiguous -> lanes run along k, warps along j
+      for (int j = warp; j < jn; j += kThreads / 32) {
+        const long long off = row_off + (long long)(j_lo + j) * p.sw + k_lo;
+        for (int k = lane; k < kn; k += 32) {
+          float v;
+          if (p.in_is_i16) {
+            const int raw = reinterpret_cast<const short*>(p.in)[off + k];
+            v = use_lut ? s_lut[min(max(raw, lut_lo), lut_lo + lut_n - 1) - lut_lo] : load_norm(p, off + k);
+          } else {
+            v = reinterpret_cast<const float*>(p.in)[off + k];
+          }
+          dst[k * jn_pad + j] = v;
+        }
+      }
+    } else {  // (D, H, W): width contiguous -> lanes run along j, warps along k
+      for (int k = warp; k < kn; k += kThreads / 32) {
+        const long long off = row_off + (long long)(k_lo + k) * p.sd + (long long)j_lo * p.sw;
+        for (int j = lane; j < jn; j += 32) {
+          float v;
+          if (p.in_is_i16) {
+            const int raw = reinterpret_cast<const short*>(p.in)[off + (long long)j * p.sw];
+            v = use_lut ? s_lut[min(max(raw, lut_lo), lut_lo + lut_n - 1) - lut_lo] : load_norm(p, off + (long long)j * p.sw);
+          } else {
+            v = reinterpret_cast<const float*>(p.in)[off + (long long)j * p.sw];
+          }
+          dst[k * jn_pad + j] = v;
+        }
+      }
     }
-  } else {
-    for (int e = threadIdx.x; e < total; e += kThreads) {
-      const int j = e % jn;
-      const int k = (e / jn) % kn;
-      const int r = e / (kn * jn);
-      const long long off = in_b + (long long)(k_lo + k) * p.sd + (long long)(r ? h1 : h0) * p.sh + (long long)(j_lo + j) * p.sw;
-      tile[(r * p.kn_max + k) * jn_pad + j] = load_norm(p, off);
-    }
-  }
-  __syncthreads();
+  };
 
   float* out_b = p.out + (long long)blockIdx.z * p.obatch;
-  const int dh = oh - p.wh0 + p.ph0;
-  for (int e = threadIdx.x; e < nd * TW; e += kThreads) {
-    const int x = e % TW, z = e / TW;
-    if (x >= nw) continue;
-    const int ka = s_d0[z] - k_lo, kb = s_d1[z] - k_lo;
-    const int ja = s_w0[x] - j_lo, jb = s_w1[x] - j_lo;
-    const float wa = s_ww0[x], wb = s_ww1[x];
-    const float* r0 = tile;
-    const float* r1 = tile + p.kn_max * jn_pad;
-    const float a = combine(r0[ka * jn_pad + ja], wa, r0[ka * jn_pad + jb], wb);   // d0, h0
-    const float b = combine(r1[ka * jn_pad + ja], wa, r1[ka * jn_pad + jb], wb);   // d0, h1
-    const float c = combine(r0[kb * jn_pad + ja], wa, r0[kb * jn_pad + jb], wb);   // d1, h0
-    const float d = combine(r1[kb * jn_pad + ja], wa, r1[kb * jn_pad + jb], wb);   // d1, h1
-    const float ab = combine(a, wh0, b, wh1);
-    const float cd = combine(c, wh0, d, wh1);
-    const float v = combine(ab, s_wd0[z], cd, s_wd1[z]);
-    const int dd = od_base + z - p.wd0 + p.pd0;
-    const int dw = ow_base + x - p.ww0 + p.pw0;
-    out_b[((long long)dd * p.tH + dh) * p.tW + dw] = v;
+  for (int t = 0; t < n_oh; ++t) {
+    const int oh = oh_base + t;
+    int h0, h1; float wh0, wh1;
+    taps(p.H, p.oH, oh, h0, h1, wh0, wh1);
+    bool staged = false;
+    if (loaded[h0 % 3] != h0) { stage_row(h0); loaded[h0 % 3] = h0; staged = true; }
+    if (loaded[h1 % 3] != h1) { stage_row(h1); loaded[h1 % 3] = h1; staged = true; }
+    if (staged) __syncthreads();
+    const float* r0 = tile + (h0 % 3) * slot_elems;
+    const float* r1 = tile + (h1 % 3) * slot_elems;
+    const int dh = oh - p.wh0 + p.ph0;
+    for (int e = threadIdx.x; e < nd * TW; e += kThreads) {
+      const int x = e % TW, z = e / TW;
+      if (x >= nw) continue;
+      const int ka = (s_d0[z] - k_lo) * jn_pad, kb = (s_d1[z] - k_lo) * jn_pad;
+      const int ja = s_w0[x] - j_lo, jb = s_w1[x] - j_lo;
+      const float wa = s_ww0[x], wb = s_ww1[x];
+      const float a = combine(r0[ka + ja], wa, r0[ka + jb], wb);   // d0, h0
+      const float b = combine(r1[ka + ja], wa, r1[ka + jb], wb);   // d0, h1
+      const float c = combine(r0[kb + ja], wa, r0[kb + jb], wb);   // d1, h0
+      const float d = combine(r1[kb + ja], wa, r1[kb + jb], wb);   // d1, h1
+      const float ab = combine(a, wh0, b, wh1);
+      const float cd = combine(c, wh0, d, wh1);
+      const float v = combine(ab, s_wd0[z], cd, s_wd1[z]);
+      const int dd = od_base + z - p.wd0 + p.pd0;
+      const int dw = ow_base + x - p.ww0 + p.pw0;
+      out_b[((long long)dd * p.tH + dh) * p.tW + dw] = v;
+    }
+    // the next output row may overwrite the slot of a row that is no longer needed: wait for all readers
+    __syncthreads();
   }
 }
 
@@ -193,7 +237,19 @@ extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
   p.obatch = (long long)p.tD * p.tH * p.tW;
   p.kn_max = max_span(p.D, p.oD, p.wd0, p.wdn, TD);
   p.jn_max = max_span(p.W, p.oW, p.ww0, p.wwn, TW);
-  const size_t smem = (size_t)2 * p.kn_max * (p.jn_max | 1) * sizeof(float);
+  // HU normalisation table (int16 input): index range where slope*v+intercept is not clipped, +-1 guard entries
+  int lut_lo = 0, lut_n = 0;
+  if (p.in_is_i16 && d->lut_workspace != nullptr && p.slope != 0.0) {
+    const double a = (-1000.0 - p.intercept) / p.slope, b = (1000.0 - p.intercept) / p.slope;
+    double lo = floor(a < b ? a : b) - 2.0, hi = ceil(a < b ? b : a) + 2.0;
+    if (lo < -32768.0) lo = -32768.0;
+    if (hi > 32767.0) hi = 32767.0;
+    if (hi >= lo && hi - lo + 1.0 <= 8192.0) {
+      lut_lo = (int)lo;
+      lut_n = (int)(hi - lo + 1.0);
+    }
+  }
+  const size_t smem = ((size_t)3 * p.kn_max * (p.jn_max | 1) + (size_t)lut_n) * sizeof(float);
   if (smem > 200 * 1024) return ctclip::fail(CTCLIP_E_SHAPE, "prep_resample: down-sampling factor too large for the shared tile (%zu B)", smem);
   cudaStream_t s = (cudaStream_t)stream;
   if (padded) {
@@ -209,7 +265,13 @@ extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
     if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "prep_resample: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  dim3 grid((unsigned)p.whn, (unsigned)(((p.wdn + TD - 1) / TD) * ((p.wwn + TW - 1) / TW)), (unsigned)d->batch);
-  prep_resample_kernel<<<grid, kThreads, smem, s>>>(p);
+  if (lut_n > 0) {
+    prep_lut_kernel<<<(lut_n + 255) / 256, 256, 0, s>>>(d->lut_workspace, lut_lo, lut_n, p.slope, p.intercept);
+    rc = ctclip::check_launch("prep_lut");
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)((p.whn + OHB - 1) / OHB), (unsigned)(((p.wdn + TD - 1) / TD) * ((p.wwn + TW - 1) / TW)),
+            (unsigned)d->batch);
+  prep_resample_kernel<<<grid, kThreads, smem, s>>>(p, d->lut_workspace, lut_lo, lut_n);
   return ctclip::check_launch("prep_resample");
 }

@@ -421,5 +421,8 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
     d.oD, d.oH, d.oW = (int(v) for v in out_grid)
     d.tD, d.tH, d.tW = (int(v) for v in tgt)
     d.pad_value = pad_value
+    if inp.dtype == torch.int16:
+        lut = torch.empty(8192, device=inp.device, dtype=torch.float32)
+        d.lut_workspace = lut.data_ptr()
     _call("ctclip_prep_resample", C.byref(d), _stream())
     return out

@@ -172,6 +172,7 @@ typedef struct ctclip_prep_desc {
   int oD, oH, oW;
   int tD, tH, tW;
   float pad_value;
+  float* lut_workspace; /* device scratch of >= 8192 floats for the exact HU table (int16 input); NULL -> per-voxel fp64 */
 } ctclip_prep_desc;
 int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream);
 
