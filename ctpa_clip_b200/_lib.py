@@ -88,4 +88,5 @@ class PrepDesc(C.Structure):
         ("tD", C.c_int), ("tH", C.c_int), ("tW", C.c_int),
         ("pad_value", C.c_float),
         ("lut_workspace", C.c_void_p),
+        ("force_generic", C.c_int),
     ]

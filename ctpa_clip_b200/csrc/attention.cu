@@ -244,8 +244,8 @@ attn_fwd_kernel(const AttnParams p) {
           const int2 b2 = *reinterpret_cast<const int2*>(sB + k0 + j);
           float x0 = __uint_as_float(s[j]) - m_i + tabp[-b2.x];
           float x1 = __uint_as_float(s[j + 1]) - m_i + tabp[-b2.y];
-          float e0 = (k0 + j < key_hi) ? exp2f(x0) : 0.f;
-          float e1 = (k0 + j + 1 < key_hi) ? exp2f(x1) : 0.f;
+          float e0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
+          float e1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
           l += e0 + e1;
           pk[j >> 1] = pack_bf16(e0, e1);
         }
@@ -253,8 +253,8 @@ attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const int ka = k0 + j;
-          float e0 = (ka >= key_lo && ka < key_hi) ? exp2f(__uint_as_float(s[j]) - m_i) : 0.f;
-          float e1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? exp2f(__uint_as_float(s[j + 1]) - m_i) : 0.f;
+          float e0 = (ka >= key_lo && ka < key_hi) ? ex2_approx(__uint_as_float(s[j]) - m_i) : 0.f;
+          float e1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? ex2_approx(__uint_as_float(s[j + 1]) - m_i) : 0.f;
           l += e0 + e1;
           pk[j >> 1] = pack_bf16(e0, e1);
         }
@@ -532,21 +532,22 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         tmem_wait_ld();
         if (has_bias) {
           const float* tabp = sTab + a_i;
-          float* dtabp = my_dtab + a_i;
+          // Per-warp private table. The lanes of a warp are consecutive query positions (distinct A_i), so one warp
+          // instruction never touches an address twice; consecutive instructions of the warp do (lane l at key j+1 hits
+          // what lane l-1 hit at key j), which is ordered by the in-order LSU pipe of a converged warp: the accesses are
+          // volatile (no compiler reordering) and unconditional (invalid rows add an exact 0), so there is no divergence.
+          volatile float* dtabp = my_dtab + a_i;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const int2 b2 = *reinterpret_cast<const int2*>(sB + min(k0 + j, p.r_pad - 2));
             const float x0 = __uint_as_float(s[j]) - lse_i + tabp[-b2.x];
             const float x1 = __uint_as_float(s[j + 1]) - lse_i + tabp[-b2.y];
-            const float p0 = (k0 + j < key_hi) ? exp2f(x0) : 0.f;
-            const float p1 = (k0 + j + 1 < key_hi) ? exp2f(x1) : 0.f;
+            const float p0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
+            const float p1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
             const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
             const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-            // lanes of a warp are consecutive query positions -> distinct A_i: plain read-modify-write is race free
-            if (r < R) dtabp[-b2.x] += d0;
-            __syncwarp();
-            if (r < R) dtabp[-b2.y] += d1;
-            __syncwarp();
+            dtabp[-b2.x] = dtabp[-b2.x] + d0;
+            dtabp[-b2.y] = dtabp[-b2.y] + d1;
             pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);
             dk[piece * 16 + (j >> 1)] = pack_bf16(d0, d1);
           }
@@ -554,8 +555,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const int ka = k0 + j;
-            const float p0 = (ka >= key_lo && ka < key_hi) ? exp2f(__uint_as_float(s[j]) - lse_i) : 0.f;
-            const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? exp2f(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
+            const float p0 = (ka >= key_lo && ka < key_hi) ? ex2_approx(__uint_as_float(s[j]) - lse_i) : 0.f;
+            const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? ex2_approx(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
             const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
             const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
             pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);

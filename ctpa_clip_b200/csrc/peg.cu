@@ -7,6 +7,7 @@
 // re-interpretation through index arithmetic (valid for any t, h, w, not only the cubic production grid).
 #include "ptx.cuh"
 #include "ctclip_internal.h"
+#include <type_traits>
 
 namespace {
 
@@ -265,10 +266,196 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ marching kernels
+// Fast path for grids whose virtual axes are affine in the canonical token index (every spatial call; the temporal call
+// when t == h == w, i.e. the production 24^3 grid): token(vt, vh, vw) = vt*st + vh*sh + vw*sw, with w % MTW == 0.
+// A warp owns one output row segment of MTW positions x 64 channels (lane = channel pair, 256-byte coalesced token
+// slices) and marches along vt with THREE rolling accumulator rows in registers: input plane p is loaded once
+// (3 rows x (MTW+2) positions, straight from L1/L2 — no shared memory, no barriers) and scattered into the outputs
+// p, p+1, p+2 it feeds: 4.5 LDG.64 + 27 FMA x 2 channels per output position. Out-of-grid rows are handled by zeroing the
+// nine taps of that row (row validity is per-warp constant) and clamping the address; the two halo columns by a select.
+// Neighbouring warps / CTAs share halo rows through L1 / L2, so HBM sees every input exactly once.
+// MODE 0: y = x + conv(x) + bias; MODE 1: dx = dy + conv^T(dy) (marches downwards, spatial taps mirrored);
+// MODE 2: dw27 / dbias accumulation (x planes march, three dy rows roll).
+constexpr int MTW = 4, MTH = 8, MCH = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+peg_march_kernel(const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out,
+                 __nv_bfloat16* __restrict__ out_bf16, const float* __restrict__ w27, const float* __restrict__ bias,
+                 float* __restrict__ dw27, float* __restrict__ dbias, int T, int H, int W, int st, int sh, int sw,
+                 int dim) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ch = blockIdx.y * MCH + 2 * lane;
+  const int tiles_w = W / MTW;
+  const int h0 = (blockIdx.x / tiles_w) * MTH, w0 = (blockIdx.x % tiles_w) * MTW;
+  const int oh = h0 + warp;
+  const long long vol = (long long)blockIdx.z * T * H * W * dim;
+  const bool row_ok = oh < H;
+  constexpr bool flip = (MODE == 1);
+  const bool left_ok = w0 > 0, right_ok = w0 + MTW < W;
+  bool rv[3];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) rv[kh] = row_ok && oh + kh - 1 >= 0 && oh + kh - 1 < H;
+
+  float2 wt[27];
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int src = flip ? ((kt * 3 + (2 - kh)) * 3 + (2 - kw)) : ((kt * 3 + kh) * 3 + kw);
+        float2 w = make_float2(0.f, 0.f);
+        if (MODE != 2 && rv[kh]) w = __ldg(reinterpret_cast<const float2*>(w27 + src * dim + ch));
+        wt[(kt * 3 + kh) * 3 + kw] = w;
+      }
+  float2 bval = make_float2(0.f, 0.f);
+  if (MODE == 0 && bias != nullptr) bval = __ldg(reinterpret_cast<const float2*>(bias + ch));
+  float2 bsum = make_float2(0.f, 0.f);
+
+  // BYTE offsets of the 3 x (MTW+2) neighbourhood inside plane 0 (rows / halo columns clamped into the grid):
+  // roff is per thread (row, channel pair), coff is CTA-uniform (column) -> address = uniform base + roff + coff
+  unsigned roff[3], coff[MTW + 2];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) roff[kh] = (unsigned)((min(max(oh + kh - 1, 0), H - 1) * sh * dim + ch) * 4);
+#pragma unroll
+  for (int x = 0; x < MTW + 2; ++x) coff[x] = (unsigned)(min(max(w0 + x - 1, 0), W - 1) * sw * dim * 4);
+  const long long pstride = (long long)st * dim * 4;   // bytes
+  const char* base = reinterpret_cast<const char*>(in + vol);
+  const char* base2 = reinterpret_cast<const char*>(in2 + vol);
+  char* obase = reinterpret_cast<char*>(out + vol);
+  char* obase_bf = reinterpret_cast<char*>(out_bf16 + vol);
+
+  float2 acc[3][MTW];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int ow = 0; ow < MTW; ++ow) acc[s][ow] = make_float2(0.f, 0.f);
+
+  if (MODE == 2 && row_ok) {  // dy rows of planes 0 and 1
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int ow = 0; ow < MTW; ++ow)
+        if (s < T) acc[s][ow] = __ldg(reinterpret_cast<const float2*>(base2 + s * pstride + roff[1] + coff[ow + 1]));
+  }
+
+  auto body = [&](auto phc, int step) {
+    constexpr int PH = decltype(phc)::value;
+    const int p = flip ? T - 1 - step : step;
+    const char* pb = base + p * pstride;
+    if (MODE == 2) {
+      // dy row of plane p + 2 replaces the slot that held plane p - 1
+      const char* b2 = base2 + (p + 2) * pstride;
+#pragma unroll
+      for (int ow = 0; ow < MTW; ++ow)
+        acc[(PH + 2) % 3][ow] = (row_ok && p + 2 < T) ? __ldg(reinterpret_cast<const float2*>(b2 + roff[1] + coff[ow + 1]))
+                                                      : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ow = 0; ow < MTW; ++ow) { bsum.x += acc[PH][ow].x; bsum.y += acc[PH][ow].y; }
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      float2 v[MTW + 2];
+      const char* rp = pb + roff[kh];
+#pragma unroll
+      for (int x = 0; x < MTW + 2; ++x) v[x] = __ldg(reinterpret_cast<const float2*>(rp + coff[x]));
+      if (!left_ok) v[0] = make_float2(0.f, 0.f);
+      if (!right_ok) v[MTW + 1] = make_float2(0.f, 0.f);
+      if (MODE != 2 && kh == 1) {  // residual: the centre tap of the plane that completes at this step
+#pragma unroll
+        for (int ow = 0; ow < MTW; ++ow) {
+          acc[PH][ow].x += v[ow + 1].x + bval.x;
+          acc[PH][ow].y += v[ow + 1].y + bval.y;
+        }
+      }
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int slot = (PH + 2 - kt) % 3;  // plane p feeds output p + 2 - kt (MODE 2: pairs with dy of that plane)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wi = (kt * 3 + kh) * 3 + kw;
+#pragma unroll
+          for (int ow = 0; ow < MTW; ++ow) {
+            if (MODE != 2) acc[slot][ow] = ptx::ffma2(wt[wi], v[ow + kw], acc[slot][ow]);
+            else wt[wi] = ptx::ffma2(acc[slot][ow], v[ow + kw], wt[wi]);
+          }
+        }
+      }
+    }
+    if (MODE != 2) {
+      if (row_ok) {
+        char* ob = obase + p * pstride + roff[1];
+        char* obb = obase_bf + p * (pstride >> 1) + (roff[1] >> 1);
+#pragma unroll
+        for (int ow = 0; ow < MTW; ++ow) {
+          *reinterpret_cast<float2*>(ob + coff[ow + 1]) = acc[PH][ow];
+          if (MODE == 1 && out_bf16 != nullptr)
+            *reinterpret_cast<uint32_t*>(obb + (coff[ow + 1] >> 1)) = ptx::pack_bf16(acc[PH][ow].x, acc[PH][ow].y);
+        }
+      }
+#pragma unroll
+      for (int ow = 0; ow < MTW; ++ow) acc[PH][ow] = make_float2(0.f, 0.f);
+    }
+  };
+
+  int step = 0;
+  for (; step + 3 <= T; step += 3) {
+    body(std::integral_constant<int, 0>{}, step);
+    body(std::integral_constant<int, 1>{}, step + 1);
+    body(std::integral_constant<int, 2>{}, step + 2);
+  }
+  if (step < T) body(std::integral_constant<int, 0>{}, step);
+  if (step + 1 < T) body(std::integral_constant<int, 1>{}, step + 1);
+
+  if (MODE == 2) {
+    __shared__ float red[8 * 28][32];   // the two channels of a lane are reduced one after the other (28 KB)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int i = (kt * 3 + kh) * 3 + kw;
+            red[warp * 28 + i][lane] = rv[kh] ? (c ? wt[i].y : wt[i].x) : 0.f;   // clamped rows contributed garbage
+          }
+      red[warp * 28 + 27][lane] = c ? bsum.y : bsum.x;
+      __syncthreads();
+      for (int i = warp; i < 28; i += 8) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * 28 + i][lane];
+        if (i < 27) atomicAdd(dw27 + i * dim + ch + c, s);
+        else if (dbias != nullptr) atomicAdd(dbias + ch + c, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// virtual-axis token strides when the mapping is affine; false otherwise
+bool affine_strides(int t, int h, int w, int temporal, int& st, int& sh, int& sw) {
+  if (!temporal) { st = h * w; sh = w; sw = 1; return true; }
+  if (t == h && h == w) { st = w; sh = 1; sw = h * w; return true; }   // virtual (vt, vh, vw) = canonical (hi, wi, ti)
+  return false;
+}
+
 template <int MODE>
 int launch_tiled(const float* in, const float* in2, float* out, void* out_bf16, const float* w27, const float* bias,
                  float* dw27, float* dbias, int batch, int t, int h, int w, int dim, int temporal, void* stream,
                  const char* what) {
+  int st, sh, sw;
+  if (affine_strides(t, h, w, temporal, st, sh, sw) && (long long)t * h * w * dim < (1ll << 31) && w % MTW == 0 &&
+      dim % MCH == 0) {
+    dim3 grid((unsigned)(((h + MTH - 1) / MTH) * (w / MTW)), (unsigned)(dim / MCH), (unsigned)batch);
+    peg_march_kernel<MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(in, in2, out, (__nv_bfloat16*)out_bf16, w27, bias, dw27,
+                                                                  dbias, t, h, w, st, sh, sw, dim);
+    return ctclip::check_launch(what);
+  }
   PegGrid g{t, h, w, temporal};
   int vt = t, vh = h, vw = w;  // the virtual grid has the same extents (reshape, not permute)
   (void)vt;

@@ -175,6 +175,218 @@ prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fast path
+// Raw scans as NIfTI stores them — int16 (H, W, N), depth contiguous, N % 8 == 0 — resampled into (D', H', W') fp32.
+// A CTA owns an (ftd x FOH x fw) output brick: lane = output column, warp = a run of consecutive output depths. The
+// input rows (h) the brick needs rotate through three shared-memory slots [k][j] (fp32, HU-normalised while staging;
+// global loads are 16-byte chunks along the contiguous depth axis, prefetched into registers one output row ahead).
+//
+// Register marching, two levels: a thread keeps the w-interpolated values W(k) of its <= KMAX input depth planes for
+// the two input rows (h0, h1) of the current output row IN REGISTERS. Stepping to the next output row re-uses the h1
+// row as the new h0 (one new row = 2 LDS + 2 FP per plane); P(k) = lerp_h(W_h0(k), W_h1(k)) is then 2 FP per plane and
+// every output is one more lerp of P(k), P(k+1) — ~18 instructions per output instead of 8 LDS + 8 index reads + 14 FP.
+// The w taps live in registers, the d / h taps in small shared tables; fw <= 32 is chosen by the host so that the input
+// columns of one warp span at most 32 words (conflict-free). Same operation order as the generic kernel (w, then h,
+// then d, each level fma(t0, w0, t1 * w1)) -> bit-identical results.
+//
+// HU normalisation: ARITH = true when slope == 1 and the intercept is an integer (the usual CT rescale): then
+// c = clip(raw + intercept) is an integer in [-1000, 1000] and float(double(c) / 1000.0) == q1 with
+// q0 = c * 0.001f, q1 = fma(fma(-q0, 1000, c), 0.001f, q0) for all 2001 values (checked exhaustively in
+// tests/test_resample_oracle.py) — three FP32 instructions instead of a random-bank table look-up. Otherwise the exact
+// LUT is used.
+constexpr int FG = 8, FOH = 32, FCPR = 2;  // depth groups (warps), oh per CTA, 16-byte chunks per thread per row
+constexpr int FJP = 33;                    // shared row pitch (words): <= 32 columns + 1 -> transposing stores hit 32 banks
+constexpr int FKMAX = 16;                  // input depth planes a thread keeps in registers
+
+template <bool ARITH>
+__global__ void __launch_bounds__(256, 2)
+prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_lo, int lut_n, int icpt, int ftd, int fw,
+                    int kn8_max) {
+  extern __shared__ float tile[];  // [3][kn8_max + 1][FJP] + FKMAX rows of slack | d taps [ftd] | h taps [FOH] | lut
+  const int slot_elems = (kn8_max + 1) * FJP;
+  float4* s_dtap = reinterpret_cast<float4*>(tile + ((3 * slot_elems + FKMAX * FJP + 3) & ~3));
+  float4* s_htap = s_dtap + ftd;
+  float* s_lut = reinterpret_cast<float*>(s_htap + FOH);
+  const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+  const int n_wt = (p.wwn + fw - 1) / fw;
+  const int oh_base = p.wh0 + blockIdx.x * FOH;
+  const int n_oh = min(FOH, p.wh0 + p.whn - oh_base);
+  const int od_base = p.wd0 + (blockIdx.y / n_wt) * ftd;
+  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * fw;
+  const int nd = min(ftd, p.wd0 + p.wdn - od_base);
+  const int nw = min(fw, p.ww0 + p.wwn - ow_base);
+  const short* in16 = reinterpret_cast<const short*>(p.in) + (long long)blockIdx.z * p.sbatch;
+
+  for (int z = tid; z < nd; z += 256) {
+    int a, b; float x, y;
+    taps(p.D, p.oD, od_base + z, a, b, x, y);
+    s_dtap[z] = make_float4(__int_as_float(a), x, y, __int_as_float(b));
+  }
+  if (tid < n_oh) {
+    int a, b; float x, y;
+    taps(p.H, p.oH, oh_base + tid, a, b, x, y);
+    s_htap[tid] = make_float4(__int_as_float(a), x, y, __int_as_float(b));
+  }
+  if (!ARITH)
+    for (int i = tid; i < lut_n; i += 256) s_lut[i] = lut[i];
+  // CTA-uniform input extents (every thread evaluates the same taps)
+  int k_lo, k_hi, j_lo, j_hi, t0, t1; float f0, f1;
+  taps(p.D, p.oD, od_base, k_lo, t1, f0, f1);
+  taps(p.D, p.oD, od_base + nd - 1, t0, t1, f0, f1);
+  k_hi = min(p.D - 1, max(t1, t0 + 1));
+  taps(p.W, p.oW, ow_base, j_lo, t1, f0, f1);
+  taps(p.W, p.oW, ow_base + nw - 1, t0, j_hi, f0, f1);
+  const int k_lo8 = k_lo & ~7;
+  const int kc_n = (k_hi - k_lo8) / 8 + 1;   // 16-byte chunks per input column
+  const int jn = j_hi - j_lo + 1;
+  const int chunks = kc_n * jn;
+  // this thread's w taps
+  const bool ow_ok = lane < nw;
+  int ja, jb; float wa, wb;
+  taps(p.W, p.oW, ow_base + (ow_ok ? lane : nw - 1), ja, jb, wa, wb);
+  ja -= j_lo; jb -= j_lo;
+  const int lut_hi = lut_lo + lut_n - 1;
+  // chunk -> (column j, depth chunk kc) of this thread's staging slots (same for every row)
+  int cj[FCPR], ck[FCPR];
+#pragma unroll
+  for (int u = 0; u < FCPR; ++u) {
+    const int idx = tid + u * 256;
+    ck[u] = idx / jn;
+    cj[u] = idx - ck[u] * jn;
+  }
+
+  const short* cptr[FCPR];   // chunk address inside input row 0
+#pragma unroll
+  for (int u = 0; u < FCPR; ++u) cptr[u] = in16 + (long long)(j_lo + cj[u]) * p.sw + k_lo8 + 8 * ck[u];
+  const bool last_chunk_dup = (k_lo8 + 8 * kc_n == p.D);   // the brick reaches the last plane: duplicate it at k = D
+  auto row_load = [&](int row, uint4 (&pf)[FCPR]) {
+    const long long ro = (long long)row * p.sh;
+#pragma unroll
+    for (int u = 0; u < FCPR; ++u)
+      if (tid + u * 256 < chunks) pf[u] = __ldg(reinterpret_cast<const uint4*>(cptr[u] + ro));
+  };
+  auto row_store = [&](int row, const uint4 (&pf)[FCPR]) {
+    float* dst = tile + (row % 3) * slot_elems;
+#pragma unroll
+    for (int u = 0; u < FCPR; ++u) {
+      if (tid + u * 256 < chunks) {
+        const uint32_t w4[4] = {pf[u].x, pf[u].y, pf[u].z, pf[u].w};
+        float* d = dst + (8 * ck[u]) * FJP + cj[u];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r0 = (int)(short)(w4[e] & 0xffffu), r1 = (int)(short)(w4[e] >> 16);
+          float2 y;
+          if (ARITH) {
+            const float2 cf = make_float2((float)min(max(r0 + icpt, -1000), 1000), (float)min(max(r1 + icpt, -1000), 1000));
+            const float2 k3 = make_float2(0.001f, 0.001f);
+            const float2 q0 = ptx::fmul2(cf, k3);
+            y = ptx::ffma2(ptx::ffma2(make_float2(-q0.x, -q0.y), make_float2(1000.f, 1000.f), cf), k3, q0);
+          } else {
+            y.x = s_lut[min(max(r0, lut_lo), lut_hi) - lut_lo];
+            y.y = s_lut[min(max(r1, lut_lo), lut_hi) - lut_lo];
+          }
+          d[(2 * e) * FJP] = y.x;
+          d[(2 * e + 1) * FJP] = y.y;
+          if (e == 3 && last_chunk_dup && ck[u] == kc_n - 1) d[8 * FJP] = y.y;   // P(D) := P(D-1): no select in the march
+        }
+      }
+    }
+  };
+
+  __syncthreads();  // LUT and taps visible
+  // this thread's run of output depths [zbeg, zend) and the input planes kf .. kf + kn_t - 1 it needs
+  const int opt = ftd / FG;
+  const int zbeg = grp * opt, zend = min(zbeg + opt, nd);
+  int kf = 0, kn_t = 0;
+  if (zbeg < zend) {
+    kf = __float_as_int(s_dtap[zbeg].x);
+    kn_t = min(__float_as_int(s_dtap[zend - 1].x) + 1, p.D - 1) - kf + 1;
+  }
+  // depth down-sampling (host-checked): at most one output has its lower tap on a given plane -> a 16-bit mask per warp
+  unsigned emask = 0;
+  for (int z = zbeg; z < zend; ++z) emask |= 1u << (__float_as_int(s_dtap[z].x) - kf);
+  int ld0 = -1, ld1 = -1, ld2 = -1;  // input row held by each slot
+  auto held = [&](int row) { const int m = row % 3; return (m == 0 ? ld0 : m == 1 ? ld1 : ld2) == row; };
+  auto hold = [&](int row) { const int m = row % 3; if (m == 0) ld0 = row; else if (m == 1) ld1 = row; else ld2 = row; };
+  uint4 pfa[FCPR], pfb[FCPR];
+  {
+    const float4 ht = s_htap[0];
+    const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
+    row_load(h0, pfa);
+    if (h1 != h0) row_load(h1, pfb);
+    row_store(h0, pfa); hold(h0);
+    if (h1 != h0) { row_store(h1, pfb); hold(h1); }
+  }
+  __syncthreads();
+
+  const int woff = (kf - k_lo8) * FJP + ja;      // word offset of W(kf) inside a slot
+  const int djb = jb - ja;                       // 0 or 1
+  float wA[FKMAX], wB[FKMAX];                    // w-interpolated planes of two input rows (rowA, rowB)
+  int rowA = -1, rowB = -1;
+  auto wrow = [&](int row, float (&w)[FKMAX]) {  // planes beyond kn_t read slack / stale words: never used
+    const float* ra = tile + (row % 3) * slot_elems + woff;
+    const float* rb = ra + djb;
+#pragma unroll
+    for (int kk = 0; kk < FKMAX; ++kk) w[kk] = combine(ra[kk * FJP], wa, rb[kk * FJP], wb);
+  };
+  const long long oplane = (long long)p.tH * p.tW;
+  float* out_t = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
+                 (ow_base + lane - p.ww0 + p.pw0);
+  for (int t = 0; t < n_oh; ++t) {
+    const int oh = oh_base + t;
+    const float4 ht = s_htap[t];
+    const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
+    const float wh0 = ht.y, wh1 = ht.z;
+    int na = -1, nb = -1;
+    if (t + 1 < n_oh) {
+      const float4 hx = s_htap[t + 1];
+      const int g0 = __float_as_int(hx.x), g1 = __float_as_int(hx.w);
+      if (!held(g0)) na = g0;
+      if (g1 != g0 && !held(g1)) nb = g1;
+      if (na >= 0) row_load(na, pfa);
+      if (nb >= 0) row_load(nb, pfb);
+    }
+    if (kn_t > 0) {
+      float* optr = out_t + (long long)(oh - p.wh0 + p.ph0) * p.tW;
+      auto march = [&](const float (&x)[FKMAX], const float (&y)[FKMAX]) {   // x: row h0, y: row h1
+        float pc = combine(x[0], wh0, y[0], wh1);
+        const float4* wp = s_dtap + zbeg;     // depth taps of the next output of this run
+        float* op = optr;
+#pragma unroll
+        for (int kk = 0; kk < FKMAX; ++kk) {
+          const float pn = (kk + 1 < FKMAX) ? combine(x[(kk + 1) % FKMAX], wh0, y[(kk + 1) % FKMAX], wh1) : pc;
+          if (emask & (1u << kk)) {           // warp-uniform
+            const float4 tp = *wp++;
+            const float v = combine(pc, tp.y, pn, tp.z);
+            if (ow_ok) *op = v;
+            op += oplane;
+          }
+          pc = pn;
+        }
+      };
+      // the two register planes swap roles instead of being copied: whichever already holds h0 stays
+      if (rowA == h0) {
+        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
+        if (h1 != h0) march(wA, wB); else march(wA, wA);
+      } else if (rowB == h0) {
+        if (h1 != h0 && rowA != h1) { wrow(h1, wA); rowA = h1; }
+        if (h1 != h0) march(wB, wA); else march(wB, wB);
+      } else {
+        wrow(h0, wA); rowA = h0;
+        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
+        if (h1 != h0) march(wA, wB); else march(wA, wA);
+      }
+    }
+    if (na >= 0 || nb >= 0) {
+      __syncthreads();  // every reader of the slots being replaced is done
+      if (na >= 0) { row_store(na, pfa); hold(na); }
+      if (nb >= 0) { row_store(nb, pfb); hold(nb); }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 fill_f32_kernel(float4* __restrict__ x, long long nvec, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
@@ -205,6 +417,8 @@ int max_span(int in, int out, int lo, int n, int tile) {
 }
 
 }  // namespace
+
+static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s);
 
 extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
   if (d == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "prep_resample: null descriptor");
@@ -270,8 +484,80 @@ extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
     rc = ctclip::check_launch("prep_lut");
     if (rc) return rc;
   }
+  if (lut_n > 0 && !d->force_generic) {
+    rc = launch_fast(p, d->batch, d->lut_workspace, lut_lo, lut_n, s);
+    if (rc <= 0) return rc;
+  }
   dim3 grid((unsigned)((p.whn + OHB - 1) / OHB), (unsigned)(((p.wdn + TD - 1) / TD) * ((p.wwn + TW - 1) / TW)),
             (unsigned)d->batch);
   prep_resample_kernel<<<grid, kThreads, smem, s>>>(p, d->lut_workspace, lut_lo, lut_n);
   return ctclip::check_launch("prep_resample");
+}
+
+// fast path (see prep_hwn_i16_kernel); returns 1 when it does not apply
+template <bool ARITH>
+static int launch_fast_t(const PrepParams& p, dim3 grid, size_t smem, float* lut_ws, int lut_lo, int lut_n, int icpt,
+                         int ftd, int fw, int kn8, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(prep_hwn_i16_kernel<ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return 1;
+    configured = smem;
+  }
+  prep_hwn_i16_kernel<ARITH><<<grid, 256, smem, s>>>(p, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8);
+  return ctclip::check_launch("prep_resample(hwn/i16)");
+}
+
+static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s) {
+  if (!p.in_is_i16 || lut_n <= 0 || p.sd != 1 || p.sw != p.D || (p.D % 8) || (p.sh % 8) || (p.sbatch % 8) ||
+      (reinterpret_cast<uintptr_t>(p.in) % 16) || p.D < p.oD /* the k-indexed tap table needs depth down-sampling */)
+    return 1;
+  // depth run per warp: as long as the input planes it spans fit the FKMAX register planes
+  int opt = 12;
+  auto planes_ok = [&](int o) {
+    for (int b = p.wd0; b < p.wd0 + p.wdn; b += o) {
+      const int e = (b + o < p.wd0 + p.wdn ? b + o : p.wd0 + p.wdn) - 1;
+      int a0, a1, b0, b1;
+      taps_host(p.D, p.oD, b, a0, a1);
+      taps_host(p.D, p.oD, e, b0, b1);
+      int hi = b0 + 1 < p.D - 1 ? b0 + 1 : p.D - 1;
+      if (hi - a0 + 1 > FKMAX) return false;
+    }
+    return true;
+  };
+  while (opt > 1 && !planes_ok(opt)) --opt;
+  if (opt < 4) return 1;  // strong depth down-sampling: generic kernel
+  // prefer a run length that tiles the kept depth range without a ragged last brick
+  for (int o = opt; o >= opt - 3 && o >= 4; --o)
+    if (p.wdn % (o * FG) == 0) { opt = o; break; }
+  const int ftd = opt * FG;
+  // shared tile extents over all bricks
+  int kn8 = 8;
+  for (int b = p.wd0; b < p.wd0 + p.wdn; b += ftd) {
+    const int e = (b + ftd < p.wd0 + p.wdn ? b + ftd : p.wd0 + p.wdn) - 1;
+    int a0, a1, b0, b1;
+    taps_host(p.D, p.oD, b, a0, a1);
+    taps_host(p.D, p.oD, e, b0, b1);
+    int hi = b1 > b0 + 1 ? b1 : b0 + 1;
+    if (hi > p.D - 1) hi = p.D - 1;
+    const int n8 = ((hi - (a0 & ~7)) / 8 + 1) * 8;
+    if (n8 > kn8) kn8 = n8;
+  }
+  // widest warp row (<= 32 outputs) whose input columns fit the 32 shared-memory banks
+  int fw = 32;
+  while (fw >= 16 && max_span(p.W, p.oW, p.ww0, p.wwn, fw) > 32) --fw;
+  if (fw < 16) return 1;
+  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, fw);
+  if ((kn8 / 8) * jn > FCPR * 256) return 1;
+  p.jn_max = jn;
+  const bool arith = p.slope == 1.0 && p.intercept == floor(p.intercept) && fabs(p.intercept) <= 32768.0;
+  const size_t smem = (((size_t)3 * (kn8 + 1) * FJP + FKMAX * FJP + 3) & ~(size_t)3) * sizeof(float) +
+                      (size_t)(ftd + FOH) * 16 + (arith ? 0 : (size_t)lut_n * sizeof(float));
+  if (smem > 100 * 1024) return 1;
+  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + fw - 1) / fw)),
+            (unsigned)batch);
+  const int icpt = arith ? (int)p.intercept : 0;
+  return arith ? launch_fast_t<true>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s)
+               : launch_fast_t<false>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s);
 }

@@ -389,7 +389,7 @@ def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max
           _f(beta2), _f(eps), step, _ptr(norm_sq), _f(max_norm), int(zero_grad), _stream())
 
 
-def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0):
+def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0, force_generic=False):
     """Trilinear resample (align_corners=False) of a batch of volumes on the GPU.
     layout "dhw": inp is [b, D, H, W] (fp32, or int16 with hu=(slope, intercept));
     layout "hwn": inp is [b, H, W, N] as stored in a NIfTI array (depth contiguous).
@@ -421,6 +421,7 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
     d.oD, d.oH, d.oW = (int(v) for v in out_grid)
     d.tD, d.tH, d.tW = (int(v) for v in tgt)
     d.pad_value = pad_value
+    d.force_generic = int(force_generic)
     if inp.dtype == torch.int16:
         lut = torch.empty(8192, device=inp.device, dtype=torch.float32)
         d.lut_workspace = lut.data_ptr()

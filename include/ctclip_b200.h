@@ -173,6 +173,7 @@ typedef struct ctclip_prep_desc {
   int tD, tH, tW;
   float pad_value;
   float* lut_workspace; /* device scratch of >= 8192 floats for the exact HU table (int16 input); NULL -> per-voxel fp64 */
+  int force_generic;    /* 1: skip the depth-marching fast path for int16 (H,W,N) scans (test hook; results are identical) */
 } ctclip_prep_desc;
 int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream);
 

@@ -334,3 +334,27 @@ def test_resample_full_size_volume_bit_exact_and_properties(ops):
     both = preprocess_volumes(pair, 1.0, 0.0, 0.703125, 1.125)
     single = preprocess_volumes(pair[1:].contiguous(), 1.0, 0.0, 0.703125, 1.125)
     assert torch.equal(both[1], single[0])
+
+
+@pytest.mark.parametrize("shape,spacing,target,hu", [
+    ((40, 48, 64), (0.703125, 1.125), None, (1.0, 0.0)),          # depth 64 -> 48 (down), 40x48 -> 37x45
+    ((33, 70, 16), (0.9, 2.0), None, (1.0, -1024.0)),             # depth up-sampled 16 -> 21, ragged H / W
+    ((50, 50, 24), (0.75, 1.5), None, (2.0, -1000.0)),            # identity grid on every axis
+    ((64, 64, 40), (0.703125, 1.125), (24, 70, 48), (1.0, 0.0)),  # centre crop (h) + pad(-1) (w) window
+    ((30, 30, 128), (1.6, 4.0), None, (0.5, 12.5)),               # strong down-sampling on every axis, fractional HU
+])
+def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spacing, target, hu):
+    """the depth-marching int16 (H,W,N) kernel and the generic brick kernel must agree bit for bit with the C oracle"""
+    from ctpa_clip_b200.data_prep.preprocess import resize_shape
+    rng = np.random.default_rng(11)
+    raw = rng.integers(-2000, 3000, size=shape, dtype=np.int16)
+    want = R.preprocess_volume(raw, hu[0], hu[1], spacing[0], spacing[1])
+    if target is not None:
+        want = R.crop_pad(want, target, -1.0)
+    H, W, N = shape
+    grid = resize_shape((N, H, W), (spacing[1], spacing[0], spacing[0]), (1.5, 0.75, 0.75))
+    dev = torch.from_numpy(raw)[None].cuda()
+    for force in (False, True):
+        got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
+        assert got.shape == want.shape
+        assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force}"

@@ -72,3 +72,37 @@ def test_crop_pad_matches_data_py_arithmetic():
         tensor = torch.nn.functional.pad(tensor, tuple(pads), value=-1).permute(2, 0, 1)
         got = R.crop_pad(np.ascontiguousarray(vol), target, -1.0)
         assert np.array_equal(got, tensor.numpy())
+
+
+def test_fp32_newton_division_equals_numpy_double_path_for_all_integer_hu():
+    """prep_hwn_i16_kernel<ARITH>: for slope 1 and an integer intercept, c = clip(raw + intercept) is an integer in
+    [-1000, 1000]; the kernel computes q0 = c * 0.001f, q1 = fma(fma(-q0, 1000, c), 0.001f, q0) in fp32. This must equal
+    numpy's float32(float64(c) / 1000.0) (preprocess_train.py:103-105) for every one of the 2001 values (exact rational
+    emulation of the fp32 roundings)."""
+    import math
+    from fractions import Fraction as F
+
+    def rnd32(x):
+        if x == 0:
+            return F(0)
+        s = -1 if x < 0 else 1
+        x = abs(x)
+        e = math.floor(math.log2(float(x))) - 23
+        while x / F(2) ** e >= 2 ** 24:
+            e += 1
+        while x / F(2) ** e < 2 ** 23:
+            e -= 1
+        y = x / F(2) ** e
+        m = math.floor(y)
+        fr = y - m
+        if fr > F(1, 2) or (fr == F(1, 2) and m % 2 == 1):
+            m += 1
+        return s * m * F(2) ** e
+
+    r = rnd32(F(1, 1000))
+    assert float(r) == float(np.float32(0.001))
+    for c in range(-1000, 1001):
+        want = np.float32(np.float64(c) / 1000.0)
+        q0 = rnd32(F(c) * r)
+        q1 = rnd32(rnd32(-q0 * 1000 + c) * r + q0)
+        assert float(q1) == float(want), c

@@ -41,3 +41,9 @@ dg = torch.zeros(D, device=dev)
 ops.layernorm_bwd(dy, x, gam, add_in=dy, dgamma=dg, want_bf16=True)
 torch.cuda.synchronize()
 print("done")
+# data_prep fast path (one production scan) and the generic brick kernel
+from ctpa_clip_b200.data_prep import preprocess_volumes
+raw = torch.randint(-1024, 3071, (2, 512, 512, 320), device=dev, dtype=torch.int16, generator=g)
+preprocess_volumes(raw, 1.0, 0.0, 0.703125, 1.125)
+torch.cuda.synchronize()
+print("prep done")
