@@ -152,7 +152,7 @@ attn_fwd_kernel(const AttnParams p) {
     for (int i = tid; i < p.n; i += blockDim.x) sRowMax[i] = p.bias_rowmax[(long long)head * p.n + i] * kLog2e;
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     const int kp = r % p.n;
-    sB[r] = (kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw);
+    sB[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));   // byte offset of key r inside the bias table
   }
   __syncthreads();
   float cmax = 0.f;  // bound of |8 log2e q^.k^|
@@ -238,16 +238,31 @@ attn_fwd_kernel(const AttnParams p) {
       const int k0 = c * KC + half * 32;  // first key of this thread's 32 columns
       uint32_t pk[16];
       if (has_bias) {
-        const float* tabp = sTab + a_i;
+        const char* tabb = reinterpret_cast<const char*>(sTab + a_i);
+        const int2* nbp = reinterpret_cast<const int2*>(sB + k0);
+        if (k0 >= key_hi) {              // whole piece beyond the sequence (warp-uniform)
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int2 b2 = *reinterpret_cast<const int2*>(sB + k0 + j);
-          float x0 = __uint_as_float(s[j]) - m_i + tabp[-b2.x];
-          float x1 = __uint_as_float(s[j + 1]) - m_i + tabp[-b2.y];
-          float e0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
-          float e1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
-          l += e0 + e1;
-          pk[j >> 1] = pack_bf16(e0, e1);
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        } else if (k0 + 32 <= key_hi) {  // fully valid piece: no per-key predicates
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int2 nb = nbp[j >> 1];
+            const float e0 = ex2_approx((__uint_as_float(s[j]) - m_i) + *reinterpret_cast<const float*>(tabb + nb.x));
+            const float e1 = ex2_approx((__uint_as_float(s[j + 1]) - m_i) + *reinterpret_cast<const float*>(tabb + nb.y));
+            l += e0 + e1;
+            pk[j >> 1] = pack_bf16(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int2 nb = nbp[j >> 1];
+            const float x0 = (__uint_as_float(s[j]) - m_i) + *reinterpret_cast<const float*>(tabb + nb.x);
+            const float x1 = (__uint_as_float(s[j + 1]) - m_i) + *reinterpret_cast<const float*>(tabb + nb.y);
+            const float e0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
+            const float e1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
+            l += e0 + e1;
+            pk[j >> 1] = pack_bf16(e0, e1);
+          }
         }
       } else {
 #pragma unroll
@@ -334,12 +349,19 @@ struct AttnBwdParams {
 };
 
 constexpr int BKC = 128;  // keys per chunk (backward)
+constexpr int BKH = 64;   // keys per sub-step: S / dP of the two 64-key halves have their own TMEM columns and barriers
 
+// Pipeline of one (key chunk c, query tile i) step n — 256 threads, thread = (row t & 127, 32-column quarter of the
+// 64-key half):
+//   top      : Q~/dO rows of tile n+1 (prefetched to registers during step n-1) -> tile buffer (n+1) % 3
+//   half A   : wait S_A/dP_A(n) -> tcgen05.ld -> barrier -> thread 0 issues S_A/dP_A(n+1) -> softmax / dS math
+//   half B   : wait S_B/dP_B(n) -> tcgen05.ld -> math
+//   tail     : wait dV/dK/dQ(n-1) retired -> P, dS tiles to shared memory -> barrier -> thread 0 issues
+//              S_B/dP_B(n+1), then dV_c += P^T dO_i, dK^_c += dS^T Q~_i, dQ_i += dS K^_c
+// so the tensor pipe works on S/dP of the next tile and on the three gradient MMAs of this tile while the CUDA cores
+// do the element-wise work; TMEM: S 128 + dP 128 + dV 32 + dK 32 + dQ 32 x (tiles <= 6) = 512 columns.
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const AttnBwdParams bp) {
-  // 256 threads: thread t owns row (t & 127) of the current 128-row tile and the 64-column half (t >> 7) of the
-  // 128-key chunk. Q~_i / dO_i tiles are (re)built per step into double-buffered shared tiles (global rows are
-  // prefetched into registers one step ahead), so that 8 private dbias tables fit next to the P / dS tiles.
   const AttnParams& p = bp.f;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int head = blockIdx.x % p.heads;
@@ -352,14 +374,15 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   const bool has_bias = p.bias_table != nullptr;
   const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
 
-  uint8_t* sQt = smem;                             // 2 x (128 x 32)  Q~ tile, double buffered
-  uint8_t* sdOt = sQt + 2 * QT * DH * 2;           // 2 x (128 x 32)  dO tile
-  uint8_t* sK = sdOt + 2 * QT * DH * 2;            // 128 x 32
+  constexpr uint32_t TILE_B = QT * DH * 2;         // bytes of one Q~ / dO tile buffer
+  uint8_t* sQt = smem;                             // 3 x (128 x 32)  Q~ tile ring
+  uint8_t* sdOt = sQt + 3 * TILE_B;                // 3 x (128 x 32)  dO tile ring
+  uint8_t* sK = sdOt + 3 * TILE_B;                 // 128 x 32
   uint8_t* sV = sK + BKC * DH * 2;                 // 128 x 32
   uint8_t* sP = sV + BKC * DH * 2;                 // 128 x 128
   uint8_t* sdS = sP + QT * BKC * 2;                // 128 x 128
-  int* sB = reinterpret_cast<int*>(sdS + QT * BKC * 2);  // [r_pad] key offsets B_j
-  float* sLse = reinterpret_cast<float*>(sB + p.r_pad);
+  int* sBn = reinterpret_cast<int*>(sdS + QT * BKC * 2);  // [r_pad] -4 * B_j: byte offset of key j inside the bias table
+  float* sLse = reinterpret_cast<float*>(sBn + p.r_pad);
   float* sDelta = sLse + p.r_pad;
   float* sScale = sDelta + p.r_pad;                // [64]
   float* sRed = sScale + 64;                       // [64]
@@ -369,8 +392,9 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   if (tid == 0) {
-    mbar_init(bars + 0, 1);  // S / dP of the current step ready
-    mbar_init(bars + 1, 1);  // dV / dK / dQ MMAs of the current step retired (P, dS, Q~/dO tile buffers free)
+    mbar_init(bars + 0, 1);  // S_A / dP_A of the current step ready
+    mbar_init(bars + 1, 1);  // S_B / dP_B of the current step ready
+    mbar_init(bars + 2, 1);  // dV / dK / dQ MMAs of the current step retired (P, dS tiles and old tile buffers free)
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -386,7 +410,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   for (int i = tid; i < 8 * tab_n; i += blockDim.x) sdTab[i] = 0.f;
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     const int kp = r % p.n;
-    sB[r] = (kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw);
+    sBn[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));
   }
   // ---- lse and delta = rowsum(dO * O) for the whole block
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
@@ -412,18 +436,19 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 288, tdQ = tmem + 320;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKC, false, false);   // [128 q] x [128 keys], K = 32
+  constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKH, false, false);   // [128 q] x [64 keys], K = 32
   constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
   constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
   constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
-  constexpr uint32_t TILE_B = QT * DH * 2;                               // bytes of one Q~ / dO tile buffer
+  constexpr uint32_t KH_B = BKH * DH * 2;                                // bytes of 64 key rows of sK / sV
   float* my_dtab = sdTab + warp * tab_n;
-  uint32_t ph_s = 0, ph_m = 0;
+  uint32_t ph_a = 0, ph_b = 0, ph_m = 0;
+  bool mma_pending = false;
   float acc_qs[DH], acc_ks[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) acc_qs[d] = acc_ks[d] = 0.f;
 
-  // half 0 builds Q~ rows, half 1 copies dO rows. `pre` holds the raw global row of the NEXT step's tile.
+  // half 0 builds Q~ rows, half 1 copies dO rows. `pre` holds the raw global row of a tile not yet in shared memory.
   uint4 pre[4];
   auto prefetch_tile_row = [&](int tile) {
     const int r = tile * QT + rowt;
@@ -462,10 +487,22 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(sdOt + buf * TILE_B + cm_off(rowt, c8, DH)) = pre[c8];
     }
   };
+  // S_h = Q~ K^_h^T and dP_h = dO V_h^T for the 64-key half h of the chunk (thread 0 only)
+  auto issue_s = [&](int buf, int h) {
+    const uint32_t q0 = smem_u32(sQt) + buf * TILE_B, o0 = smem_u32(sdOt) + buf * TILE_B;
+#pragma unroll
+    for (int k = 0; k < DH / 16; ++k) {
+      mma_f16_ss(tS + h * BKH, desc_nosw(q0 + k * 256, 128, 512), desc_nosw(smem_u32(sK) + h * KH_B + k * 256, 128, 512),
+                 idesc_s, k > 0);
+      mma_f16_ss(tdP + h * BKH, desc_nosw(o0 + k * 256, 128, 512), desc_nosw(smem_u32(sV) + h * KH_B + k * 256, 128, 512),
+                 idesc_s, k > 0);
+    }
+    mma_commit(bars + h);
+  };
 
-  int step = 0;  // global step counter -> tile buffer parity
+  int gstep = 0;  // running step counter -> tile ring slot
   for (int c = 0; c < nchunks; ++c) {
-    // ---- K^_c (half 0) and V_c (half 1); thread = key row
+    // ---- K^_c (half 0) and V_c (half 1); thread = key row. Every MMA that reads sK / sV has retired (chunk epilogue).
     const int kr = c * BKC + rowt;
     bool kvalid = false;
     const long long ktok = (kr < R) ? row_token(p, blk, kr, kvalid) : 0;
@@ -490,66 +527,94 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         store_zero_row_cm(sV, rowt);
       }
     }
-    // first tile of this chunk
     prefetch_tile_row(0);
-    if (step > 0) {  // previous step's MMAs read the tile buffer we are about to reuse two steps later: parity is safe,
-      // but sK / sV are read by the previous chunk's dQ / S / dP MMAs -> they retired (bars+1 waited in the epilogue)
-    }
-    store_tile_row(step & 1);
+    store_tile_row(gstep % 3);
+    if (ntiles > 1) prefetch_tile_row(1);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t q0 = smem_u32(sQt) + (step & 1) * TILE_B, o0 = smem_u32(sdOt) + (step & 1) * TILE_B;
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k) {
-        mma_f16_ss(tS, desc_nosw(q0 + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
-        mma_f16_ss(tdP, desc_nosw(o0 + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
-      }
-      mma_commit(bars + 0);
+      issue_s(gstep % 3, 0);
+      issue_s(gstep % 3, 1);
     }
-    for (int i = 0; i < ntiles; ++i, ++step) {
-      const int buf = step & 1;
+    for (int i = 0; i < ntiles; ++i, ++gstep) {
+      const int buf = gstep % 3, nbuf = (gstep + 1) % 3;
       const int r = i * QT + rowt;
       const int my_seq = r / p.n;
       const int my_pos = r - my_seq * p.n;
       const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);
       const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
       const float lse_i = sLse[r], delta_i = sDelta[r];
-      if (i + 1 < ntiles) prefetch_tile_row(i + 1);  // global latency hidden behind this step's element-wise work
-      mbar_wait(bars + 0, ph_s);
-      ph_s ^= 1;
-      tc_fence_after();
+      // next tile's rows -> ring slot nbuf (last read by the MMAs of step n-2, retired before step n-1 wrote P / dS)
+      if (i + 1 < ntiles) {
+        store_tile_row(nbuf);
+        if (i + 2 < ntiles) prefetch_tile_row(i + 2);
+      }
       uint32_t pk[32], dk[32];
 #pragma unroll
-      for (int piece = 0; piece < 2; ++piece) {
-        const int col = half * 64 + piece * 32;
+      for (int h = 0; h < 2; ++h) {
+        const int col = h * BKH + half * 32;
         const int k0 = c * BKC + col;
+        if (h == 0) { mbar_wait(bars + 0, ph_a); ph_a ^= 1; } else { mbar_wait(bars + 1, ph_b); ph_b ^= 1; }
+        tc_fence_after();
         uint32_t s[32], dp[32];
         tmem_ld_32x32(tS + lane_off + col, s);
         tmem_ld_32x32(tdP + lane_off + col, dp);
         tmem_wait_ld();
+        if (h == 0) {
+          // S_A / dP_A columns are in registers everywhere after this barrier: the tensor pipe may overwrite them
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncthreads();
+          if (tid == 0 && i + 1 < ntiles) {
+            tc_fence_after();
+            issue_s(nbuf, 0);
+          }
+        }
         if (has_bias) {
-          const float* tabp = sTab + a_i;
-          // Per-warp private table. The lanes of a warp are consecutive query positions (distinct A_i), so one warp
-          // instruction never touches an address twice; consecutive instructions of the warp do (lane l at key j+1 hits
-          // what lane l-1 hit at key j), which is ordered by the in-order LSU pipe of a converged warp: the accesses are
-          // volatile (no compiler reordering) and unconditional (invalid rows add an exact 0), so there is no divergence.
-          volatile float* dtabp = my_dtab + a_i;
+          const char* tabb = reinterpret_cast<const char*>(sTab + a_i);
+          // Per-warp private dbias table. The lanes of a warp are consecutive query positions (distinct A_i), so one
+          // warp instruction never touches an address twice; consecutive instructions of the warp do (lane l at key j+1
+          // hits what lane l-1 hit at key j), which is ordered by the in-order LSU pipe of a converged warp: the
+          // accesses are volatile (no compiler reordering) and unconditional (invalid rows / keys add an exact 0).
+          volatile char* dtb = reinterpret_cast<volatile char*>(my_dtab + a_i);
+          const int2* nbp = reinterpret_cast<const int2*>(sBn + k0);
+          if (k0 >= key_hi) {            // whole 32-key piece beyond the sequence (warp-uniform): nothing to do
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const int2 b2 = *reinterpret_cast<const int2*>(sB + min(k0 + j, p.r_pad - 2));
-            const float x0 = __uint_as_float(s[j]) - lse_i + tabp[-b2.x];
-            const float x1 = __uint_as_float(s[j + 1]) - lse_i + tabp[-b2.y];
-            const float p0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
-            const float p1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
-            const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
-            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-            dtabp[-b2.x] = dtabp[-b2.x] + d0;
-            dtabp[-b2.y] = dtabp[-b2.y] + d1;
-            pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);
-            dk[piece * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            for (int j = 0; j < 16; ++j) pk[h * 16 + j] = dk[h * 16 + j] = 0u;
+          } else if (k0 + 32 <= key_hi) {  // fully valid piece: no per-key predicates
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int2 nb = nbp[j >> 1];
+              const float p0 = ex2_approx((__uint_as_float(s[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x));
+              const float p1 = ex2_approx((__uint_as_float(s[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y));
+              const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
+              const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
+              volatile float* q0 = reinterpret_cast<volatile float*>(dtb + nb.x);
+              *q0 = *q0 + d0;
+              volatile float* q1 = reinterpret_cast<volatile float*>(dtb + nb.y);
+              *q1 = *q1 + d1;
+              pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
+              dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int2 nb = nbp[j >> 1];
+              const float x0 = (__uint_as_float(s[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x);
+              const float x1 = (__uint_as_float(s[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y);
+              const float p0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
+              const float p1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
+              const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
+              const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
+              volatile float* q0 = reinterpret_cast<volatile float*>(dtb + nb.x);
+              *q0 = *q0 + d0;
+              volatile float* q1 = reinterpret_cast<volatile float*>(dtb + nb.y);
+              *q1 = *q1 + d1;
+              pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
+              dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            }
           }
         } else {
 #pragma unroll
@@ -559,30 +624,33 @@ attn_bwd_kernel(const AttnBwdParams bp) {
             const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? ex2_approx(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
             const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
             const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-            pk[piece * 16 + (j >> 1)] = pack_bf16(p0, p1);
-            dk[piece * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
+            dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
           }
         }
       }
       // the previous step's dV / dK / dQ MMAs must have finished reading the P / dS tiles
-      if (step > 0) {
-        mbar_wait(bars + 1, ph_m);
+      if (mma_pending) {
+        mbar_wait(bars + 2, ph_m);
         ph_m ^= 1;
       }
+      // this thread's 2 x 32 columns of the P / dS tiles (K-major core matrices): half-chunk h, quarter `half`
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        *reinterpret_cast<uint4*>(sP + cm_off(rowt, half * 8 + c8, BKC)) =
-            make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-        *reinterpret_cast<uint4*>(sdS + cm_off(rowt, half * 8 + c8, BKC)) =
-            make_uint4(dk[4 * c8], dk[4 * c8 + 1], dk[4 * c8 + 2], dk[4 * c8 + 3]);
-      }
-      // next tile's Q~ / dO rows go to the other buffer (its last readers, the MMAs of step-1, have retired)
-      if (i + 1 < ntiles) store_tile_row(buf ^ 1);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int cg = h * 8 + half * 4 + c8;   // 8-column group inside the 128-key chunk
+          *reinterpret_cast<uint4*>(sP + cm_off(rowt, cg, BKC)) =
+              make_uint4(pk[h * 16 + 4 * c8], pk[h * 16 + 4 * c8 + 1], pk[h * 16 + 4 * c8 + 2], pk[h * 16 + 4 * c8 + 3]);
+          *reinterpret_cast<uint4*>(sdS + cm_off(rowt, cg, BKC)) =
+              make_uint4(dk[h * 16 + 4 * c8], dk[h * 16 + 4 * c8 + 1], dk[h * 16 + 4 * c8 + 2], dk[h * 16 + 4 * c8 + 3]);
+        }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
+        if (i + 1 < ntiles) issue_s(nbuf, 1);   // S_B / dP_B of the next tile go first: they are short
         const uint32_t qb = smem_u32(sQt) + buf * TILE_B, ob = smem_u32(sdOt) + buf * TILE_B;
 #pragma unroll
         for (int k = 0; k < QT / 16; ++k) {  // reduction over the 128 queries of this tile
@@ -595,21 +663,14 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         for (int k = 0; k < BKC / 16; ++k)  // reduction over the 128 keys of this chunk
           mma_f16_ss(tdQ + i * DH, desc_nosw(smem_u32(sdS) + k * 256, 128, P_RS),
                      desc_nosw(smem_u32(sK) + k * 1024, 512, 128), idesc_q, (c > 0 || k > 0));
-        mma_commit(bars + 1);
-        if (i + 1 < ntiles) {
-          const uint32_t qn = smem_u32(sQt) + (buf ^ 1) * TILE_B, on = smem_u32(sdOt) + (buf ^ 1) * TILE_B;
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            mma_f16_ss(tS, desc_nosw(qn + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512), idesc_s, k > 0);
-            mma_f16_ss(tdP, desc_nosw(on + k * 256, 128, 512), desc_nosw(smem_u32(sV) + k * 256, 128, 512), idesc_s, k > 0);
-          }
-          mma_commit(bars + 0);
-        }
+        mma_commit(bars + 2);
       }
+      mma_pending = true;
     }
     // ---- chunk epilogue: wait for the last dV / dK MMAs; half 1 stores dV_c rows, half 0 stores dK_c rows
-    mbar_wait(bars + 1, ph_m);
+    mbar_wait(bars + 2, ph_m);
     ph_m ^= 1;
+    mma_pending = false;
     tc_fence_after();
     {
       uint32_t a[32];
@@ -646,11 +707,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         }
       }
     }
-    // the step counter keeps running across chunks; the bars+1 phase consumed above belongs to the last step, so the
-    // first step of the next chunk must not wait on it again
     tc_fence_before();
-    __syncthreads();
-    step = 0;  // restart parity bookkeeping for the next chunk (all MMAs retired, all buffers free)
+    __syncthreads();  // all TMEM reads of dV / dK done before the next chunk's first MMA overwrites them
   }
 
   // ---- dQ epilogue (thread = query row; tile i handled by column-half i & 1)
@@ -688,8 +746,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   tc_fence_before();
   __syncthreads();
   {
-    // cross-thread reduction of the scale gradients through the (now idle) P / dS tiles: [256 threads][64 + 1] floats
-    float* scratch = reinterpret_cast<float*>(smem);  // 66.5 KB <= tiles + K + V + P + dS (112 KB)
+    // cross-thread reduction of the scale gradients through the (now idle) tile buffers: [256 threads][64 + 1] floats
+    float* scratch = reinterpret_cast<float*>(smem);  // 66.5 KB <= tile rings + K + V + P (112 KB)
 #pragma unroll
     for (int d = 0; d < DH; ++d) {
       scratch[tid * 65 + d] = acc_qs[d];
@@ -722,7 +780,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
 
 size_t bwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
-  return (size_t)QT * DH * 2 * 4 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
+  return (size_t)QT * DH * 2 * 6 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
          (size_t)tab_n * 4 * 9 + 128 * 4 + 64 + 16;
 }
 
