@@ -271,7 +271,8 @@ def run_ours(args):
                                f"{B} volumes 480x480x240 + {B} reports x 512 ids per rank, fwd+bwd+allreduce+clip+Adam",
                    "global_batch": world * B, "per_rank_batch": B, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2: 1.77 GB of volumes and >10 GB of activations per step vs 126 MB L2",
-                   "text_tower": "HF BertModel under torch bf16 autocast (library kernels; ~11% of step FLOPs)"},
+                   "text_tower": "BERT-base forward+backward on libctclip_sm100.so (tcgen05 GEMMs incl. batched per-head QK^T/PV, "
+                                 "native softmax/GELU/LayerNorm/dropout kernels); HF module only holds the parameters"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(video_h.numel() * 4), "d2h_bytes_per_step": 4,
                 "note": "pinned host volumes, double-buffered copy stream, loss.item() every step"},

@@ -28,6 +28,10 @@ class GemmDesc(C.Structure):
         ("atomic", C.c_int),
         ("splits", C.c_int),
         ("top2_out", C.c_void_p),
+        ("batch_h", C.c_int), ("batch_b", C.c_int),
+        ("a_stride_h", C.c_longlong), ("a_stride_b", C.c_longlong),
+        ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
+        ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
     ]
 
 

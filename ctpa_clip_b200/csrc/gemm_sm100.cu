@@ -12,7 +12,8 @@
 //   warp 0   : TMA producer (one elected lane)         smem ring: full/empty mbarriers
 //   warp 1   : tcgen05.mma issuer (one elected lane)   TMEM ring: tmem_full/tmem_empty
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue, tcgen05.ld 32x32b (one accumulator row per thread) -> global
+//   warps 4-11: epilogue (two per TMEM lane quadrant, half of the tile's columns each), tcgen05.ld 32x32b (one
+//               accumulator row per thread, next chunk's load in flight while this chunk is stored) -> global
 // Tile 128 x BN x 64, SWIZZLE_128B operand tiles, 2 accumulator buffers (2*BN TMEM columns).
 #include "ptx.cuh"
 #include "ctclip_internal.h"
@@ -23,7 +24,8 @@ using namespace ptx;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant, each owning half of the tile's columns
 
 template <int BN>
 struct SmemLayout {
@@ -31,8 +33,8 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageOut = kStages * kStageBytes;             // 4 epilogue warps x 32 rows x 128 B staging
-  static constexpr int kBarOffset = kStageOut + 4 * 32 * 128;
+  static constexpr int kStageOut = kStages * kStageBytes;             // epilogue warps x 32 rows x 128 B staging
+  static constexpr int kBarOffset = kStageOut + kEpiWarps * 32 * 128;
   static constexpr int kTotal = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
 };
 
@@ -48,6 +50,10 @@ struct GemmKernelParams {
   long long ldr;
   float alpha;
   float4* top2;  // non-null: per (row, n-tile) best two (value, column) instead of storing C
+  // batched mode (BERT attention): Z = zh_n * zb_n independent problems, z = b * zh_n + h
+  int zh_n, z_n;
+  int a_hpos, b_hpos;          // 1: tensor-map coordinates are (c0, h, row, b); 2: (c0, row, h, b)
+  long long c_stride_h, c_stride_b;
 };
 
 // ---------------------------------------------------------------- epilogue helpers
@@ -197,7 +203,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_work = p.m_tiles * p.n_tiles * p.splits;
+  const int num_work = p.m_tiles * p.n_tiles * p.splits * (p.z_n > 1 ? p.z_n : 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -210,7 +216,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 4);
+      mbar_init(tmem_empty + a, kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -231,27 +237,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int n_t = w % p.n_tiles;
         const int m_t = (w / p.n_tiles) % p.m_tiles;
-        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int zs = w / (p.n_tiles * p.m_tiles);      // split index, or problem index in batched mode
+        const int sp = p.z_n > 1 ? 0 : zs;
+        const int zh = p.z_n > 1 ? zs % p.zh_n : 0, zb = p.z_n > 1 ? zs / p.zh_n : 0;
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        // operand tiles: coordinates (contiguous, row) plus the (head, batch) pair of the problem
+        auto load = [&](uint8_t* dst, const CUtensorMap* m, int hpos, int c0, int crow) {
+          if (hpos == 1) tma_load_4d(dst, m, full_bar + stage, c0, zh, crow, zb);
+          else tma_load_4d(dst, m, full_bar + stage, c0, crow, zh, zb);
+        };
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(full_bar + stage, L::kStageBytes);
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, m_t * BM);
+            load(sa, &tmap_a, p.a_hpos, kb * BK, m_t * BM);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar + stage, m_t * BM + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmap_a, p.a_hpos, m_t * BM + j * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmap_b, full_bar + stage, kb * BK, n_t * BN);
+            load(sb, &tmap_b, p.b_hpos, kb * BK, n_t * BN);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar + stage, n_t * BN + j * 64, kb * BK);
+            for (int j = 0; j < BN / 64; ++j) load(sb + j * (BK * 128), &tmap_b, p.b_hpos, n_t * BN + j * 64, kb * BK);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -266,7 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int sp = w / (p.n_tiles * p.m_tiles);
+        const int sp = p.z_n > 1 ? 0 : w / (p.n_tiles * p.m_tiles);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -297,58 +308,75 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
+    const int ew = warp & 3;          // TMEM lane quadrant this warp may read
+    const int ch = (warp - 4) >> 2;   // column half of the tile
+    constexpr int kHalf = BN / 2, kChunks = kHalf / 32;
+    uint8_t* stg = smem + L::kStageOut + (warp - 4) * (32 * 128);
     // 16-byte alignment of every row start of C / resid / bias -> the coalesced 128-bit epilogue is legal
     const bool aligned_out =
         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc * (p.c_is_f32 ? 4 : 2)) % 16 == 0) &&
         (p.resid == nullptr || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && ((p.ldr * 4) % 16 == 0))) &&
-        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+        (p.z_n <= 1 || (((p.c_stride_h | p.c_stride_b) * (p.c_is_f32 ? 4 : 2)) % 16 == 0));
     int acc = 0;
     uint32_t acc_phase = 0;
+    GemmKernelParams pz = p;   // per-problem view: C shifted to the (head, batch) slice in batched mode
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int n_t = w % p.n_tiles;
       const int m_t = (w / p.n_tiles) % p.m_tiles;
+      if (p.z_n > 1) {
+        const int zs = w / (p.n_tiles * p.m_tiles);
+        const long long off = (long long)(zs % p.zh_n) * p.c_stride_h + (long long)(zs / p.zh_n) * p.c_stride_b;
+        pz.C = p.c_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.C) + off)
+                          : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
+      }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const int row = m_t * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
       if (p.top2 != nullptr) {
-        // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column)
-        float v1 = -INFINITY, v2 = -INFINITY;
-        int i1 = -1, i2 = -1;
+        // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column); one warp per
+        // lane quadrant scans the whole tile so that a row's result stays in one thread
+        if (ch == 0) {
+          float v1 = -INFINITY, v2 = -INFINITY;
+          int i1 = -1, i2 = -1;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n_t * BN + c >= p.N) break;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_wait_ld();
+          for (int c = 0; c < BN; c += 32) {
+            if (n_t * BN + c >= p.N) break;
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c, r);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = n_t * BN + c + j;
-            const float x = __uint_as_float(r[j]);
-            if (col < p.N) {
-              if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = col; }
-              else if (x > v2) { v2 = x; i2 = col; }
+            for (int j = 0; j < 32; ++j) {
+              const int col = n_t * BN + c + j;
+              const float x = __uint_as_float(r[j]);
+              if (col < p.N) {
+                if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = col; }
+                else if (x > v2) { v2 = x; i2 = col; }
+              }
             }
           }
+          if (row < p.M)
+            p.top2[(long long)row * p.n_tiles + n_t] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
         }
-        if (row < p.M)
-          p.top2[(long long)row * p.n_tiles + n_t] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
-      } else
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int col0 = n_t * BN + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_wait_ld();
-        float v[32];
+      } else {
+        const int cbase = n_t * BN + ch * kHalf;
+        uint32_t r[2][32];
+        if (cbase < p.N) tmem_ld_32x32(taddr + ch * kHalf, r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (aligned_out && col0 + 32 <= p.N)
-          store_chunk_coalesced(p, smem + L::kStageOut + ew * (32 * 128), m_t * BM + ew * 32, col0, v, lane);
-        else
-          store_row_chunk(p, row, col0, v);
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = cbase + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          tmem_wait_ld();
+          if (c + 1 < kChunks && col0 + 32 < p.N) tmem_ld_32x32(taddr + ch * kHalf + (c + 1) * 32, r[(c + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c & 1][j]) * p.alpha;
+          if (aligned_out && col0 + 32 <= p.N)
+            store_chunk_coalesced(pz, stg, m_t * BM + ew * 32, col0, v, lane);
+          else
+            store_row_chunk(pz, row, col0, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -366,20 +394,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---------------------------------------------------------------- host side
-int encode_operand_map(CUtensorMap* map, const void* ptr, bool mn_major, long long rows_mn, long long k,
-                       long long ld_elems, int box_mn) {
-  // K-major: global tensor is [rows_mn][k] (k contiguous): dims {k, rows_mn}, box {64, box_mn}
-  // MN-major: global tensor is [k][rows_mn] (mn contiguous): dims {rows_mn, k}, box {64, 64}
-  cuuint64_t dims[2];
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-  cuuint32_t box[2];
-  cuuint32_t estr[2] = {1, 1};
-  if (!mn_major) {
-    dims[0] = k; dims[1] = rows_mn; box[0] = BK; box[1] = box_mn;
+// 4-D operand map: (contiguous dim, rows) of one problem plus the (head, batch) dimensions of batched mode; the two
+// middle dimensions are ordered by stride. K-major: the tensor is [rows_mn][k] (k contiguous), box {64, box_mn};
+// MN-major: [k][rows_mn] (mn contiguous), box {64, 64}. Extents are per problem, so every edge is TMA zero fill.
+int encode_operand_map(CUtensorMap* map, int* hpos, const void* ptr, bool mn_major, long long rows_mn, long long k,
+                       long long ld_elems, int box_mn, int zh_n, int zb_n, long long stride_h, long long stride_b) {
+  const cuuint64_t inner = mn_major ? rows_mn : k, rows = mn_major ? k : rows_mn;
+  const cuuint32_t box_rows = mn_major ? BK : box_mn;
+  if (zh_n <= 1) stride_h = (long long)rows * ld_elems;        // extent-1 dimensions: any legal stride
+  if (zb_n <= 1) stride_b = (stride_h > (long long)rows * ld_elems ? stride_h : (long long)rows * ld_elems) *
+                            (zh_n > 1 ? zh_n : 1);
+  const bool h_first = zh_n > 1 && stride_h < ld_elems;        // e.g. heads interleaved inside a token row
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  dims[0] = inner; box[0] = 64;
+  if (h_first) {
+    dims[1] = zh_n > 1 ? zh_n : 1; strides[0] = (cuuint64_t)stride_h * 2; box[1] = 1;
+    dims[2] = rows; strides[1] = (cuuint64_t)ld_elems * 2; box[2] = box_rows;
   } else {
-    dims[0] = rows_mn; dims[1] = k; box[0] = 64; box[1] = BK;
+    dims[1] = rows; strides[0] = (cuuint64_t)ld_elems * 2; box[1] = box_rows;
+    dims[2] = zh_n > 1 ? zh_n : 1; strides[1] = (cuuint64_t)stride_h * 2; box[2] = 1;
   }
-  return ctclip::encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+  dims[3] = zb_n > 1 ? zb_n : 1; strides[2] = (cuuint64_t)stride_b * 2; box[3] = 1;
+  *hpos = h_first ? 1 : 2;
+  return ctclip::encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
                              estr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -423,10 +463,22 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   const int sms = ctclip::sm_count();
   if (splits <= 0) {  // auto: only when the caller allows atomic accumulation
     splits = 1;
-    if (d->atomic && tiles < sms) {
-      splits = (sms + tiles - 1) / tiles;
-      const int max_splits = kp.kb_total / 4 > 0 ? kp.kb_total / 4 : 1;
-      if (splits > max_splits) splits = max_splits;
+    if (d->atomic) {
+      // fill whole waves of SMs: the smallest split count whose last wave is (nearly) as full as the best one; each
+      // split keeps >= 8 k-blocks so that the fp32 atomic epilogue stays a small fraction of its work
+      int max_splits = kp.kb_total / 8 > 0 ? kp.kb_total / 8 : 1;
+      if (max_splits > 64) max_splits = 64;
+      double best = 0.0;
+      for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long units = (long long)tiles * sp;
+        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+        if (eff > best) best = eff;
+      }
+      for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long units = (long long)tiles * sp;
+        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+        if (eff >= 0.97 * best) { splits = sp; break; }
+      }
     }
   }
   if (splits > 1 && !(d->atomic && d->c_is_f32))
@@ -442,13 +494,24 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   if (kp.splits > 1 && (d->bias || d->resid))
     return ctclip::fail(CTCLIP_E_SHAPE, "gemm: bias/resid not supported with split-K");
 
+  const int zh_n = d->batch_h > 1 ? d->batch_h : 1, zb_n = d->batch_b > 1 ? d->batch_b : 1;
+  kp.zh_n = zh_n; kp.z_n = zh_n * zb_n;
+  kp.c_stride_h = d->c_stride_h; kp.c_stride_b = d->c_stride_b;
+  if (kp.z_n > 1) {
+    if (kp.splits > 1 || d->atomic || d->resid || kp.top2)
+      return ctclip::fail(CTCLIP_E_SHAPE, "gemm: batched mode supports neither split-K / atomic output nor resid / top2");
+    if ((d->a_stride_h % 8) || (d->a_stride_b % 8) || (d->b_stride_h % 8) || (d->b_stride_b % 8))
+      return ctclip::fail(CTCLIP_E_ALIGN, "gemm: batch strides must be multiples of 8 elements");
+  }
   CUtensorMap ta, tb;
-  rc = encode_operand_map(&ta, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM);
+  rc = encode_operand_map(&ta, &kp.a_hpos, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM, zh_n, zb_n, d->a_stride_h,
+                          d->a_stride_b);
   if (rc) return rc;
-  rc = encode_operand_map(&tb, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, BN);
+  rc = encode_operand_map(&tb, &kp.b_hpos, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, BN, zh_n, zb_n, d->b_stride_h,
+                          d->b_stride_b);
   if (rc) return rc;
 
-  const int num_work = tiles * kp.splits;
+  const int num_work = tiles * kp.splits * kp.z_n;
   const int grid = num_work < sms ? num_work : sms;
   const int sel = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   switch (sel) {

@@ -158,7 +158,9 @@ class CTCLIP(nn.Module):
         self.to_visual_latent_extra = copy.deepcopy(self.to_visual_latent)
         self.multiview_loss_weight = multiview_loss_weight
         self.tokenizer = tokenizer  # the reference downloads a BertTokenizer here (ct_clip.py:585); inject one instead
-        self.text_autocast = True   # run the injected HF text encoder under bf16 autocast on the GPU
+        self.text_autocast = True   # non-BERT text encoders: run the injected torch module under bf16 autocast
+        self.native_text = True     # HF BertModel (what CT-CLIP injects): forward/backward on libctclip_sm100.so
+        self._native_text = None
         self._sh_text, self._sh_vis = _Shadow(), _Shadow()
 
     def load(self, path):
@@ -169,6 +171,15 @@ class CTCLIP(nn.Module):
     # ---------------------------------------------------------------- towers
     def encode_text(self, text):
         dev = self.to_text_latent.weight.device
+        if self.native_text and dev.type == "cuda":
+            from ..text import NativeBert, supports
+            from ..text.bert import encode
+            if self._native_text is None and supports(self.text_transformer):
+                self._native_text = NativeBert(self.text_transformer)
+            if self._native_text is not None:   # BERT on the sm_100a kernels (ct_clip.py:685-686)
+                training = self.training and self.text_transformer.training and torch.is_grad_enabled()
+                return encode(self._native_text, text.input_ids, text.attention_mask, training)
+        # any other injected text encoder runs as the torch module it is (library kernels)
         if self.text_autocast and dev.type == "cuda":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 enc_text = self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]

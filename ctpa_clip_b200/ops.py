@@ -427,3 +427,86 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
         d.lut_workspace = lut.data_ptr()
     _call("ctclip_prep_resample", C.byref(d), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ BERT text tower
+def gemm_batched(a_ptr, lda, a_t, a_sh, a_sb, b_ptr, ldb, b_t, b_sh, b_sb, out, ldc, c_sh, c_sb, M, N, K, H, Bn,
+                 alpha=1.0, tag="bmm"):
+    """H*Bn independent products C_z[M,N] = alpha * op(A_z) op(B_z)^T on the tcgen05 GEMM (batched mode).
+    Operands are raw device addresses (int) of bf16 data + leading dimensions / (head, batch) strides in elements; `out` is a
+    bf16 or fp32 tensor that owns the memory written (its data_ptr is the C of problem (0, 0))."""
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn_major = a_ptr, lda, int(a_t)
+    d.B, d.ldb, d.b_mn_major = b_ptr, ldb, int(b_t)
+    d.C, d.ldc = out if isinstance(out, int) else out.data_ptr(), ldc
+    d.c_is_f32 = 1
+    d.alpha, d.atomic, d.splits = alpha, 0, 1
+    d.batch_h, d.batch_b = H, Bn
+    d.a_stride_h, d.a_stride_b = a_sh, a_sb
+    d.b_stride_h, d.b_stride_b = b_sh, b_sb
+    d.c_stride_h, d.c_stride_b = c_sh, c_sb
+    return d
+
+
+def run_gemm_desc(d, c_is_f32: bool, tag: str, flops: float):
+    d.c_is_f32 = int(c_is_f32)
+    with _Span("gemm:" + tag, flops):
+        _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16(batched)")
+
+
+def bert_embed_fwd(ids, seq_len, word, pos, type0):
+    tokens, dim = ids.numel(), word.shape[1]
+    out = torch.empty((tokens, dim), device=word.device, dtype=torch.float32)
+    _call("ctclip_bert_embed_fwd", _ptr(ids), _ll(tokens), seq_len, _ptr(word), _ptr(pos), _ptr(type0), dim, word.shape[0],
+          _ptr(out), _stream())
+    return out
+
+
+def bert_embed_bwd(ids, seq_len, dx, dword, dpos, pad_id=-1):
+    _call("ctclip_bert_embed_bwd", _ptr(ids), _ll(ids.numel()), seq_len, _ptr(dx), dx.shape[1], dword.shape[0],
+          _ll(-1 if pad_id is None else pad_id), _ptr(dword), _ptr(dpos), _stream())
+
+
+def bert_softmax_fwd(scores, mask, batch, heads, seq_len, scale, p_drop=0.0, seed=0):
+    probs = torch.empty(scores.shape, device=scores.device, dtype=torch.bfloat16)
+    dropped = torch.empty_like(probs) if p_drop > 0 else None
+    _call("ctclip_bert_softmax_fwd", _ptr(scores), _ptr(mask), batch, heads, seq_len, _f(scale), _ptr(probs), _ptr(dropped),
+          _f(p_drop), C.c_uint(seed & 0xFFFFFFFF), _stream())
+    return probs, dropped
+
+
+def bert_softmax_bwd(probs, dprobs, batch, heads, seq_len, scale, p_drop=0.0, seed=0):
+    ds = torch.empty(probs.shape, device=probs.device, dtype=torch.bfloat16)
+    _call("ctclip_bert_softmax_bwd", _ptr(probs), _ptr(dprobs), batch, heads, seq_len, _f(scale), _ptr(ds), _f(p_drop),
+          C.c_uint(seed & 0xFFFFFFFF), _stream())
+    return ds
+
+
+def gelu_fwd(h):
+    _req(h, torch.bfloat16, "gelu_fwd.h")
+    out = torch.empty_like(h)
+    _call("ctclip_gelu_fwd", _ptr(h), _ptr(out), _ll(h.numel()), _stream())
+    return out
+
+
+def gelu_bwd(h, dy):
+    dh = torch.empty_like(h)
+    _call("ctclip_gelu_bwd", _ptr(h), _ptr(dy), _ptr(dh), _ll(h.numel()), _stream())
+    return dh
+
+
+def dropout_add(y, resid, p_drop, seed):
+    """dropout(y) (+ resid); with resid=None this is also the dropout gradient (same seed -> same mask)"""
+    _req(y, torch.float32, "dropout_add.y")
+    out = torch.empty_like(y)
+    _call("ctclip_dropout_add", _ptr(y), _ptr(resid), _ptr(out), _ll(y.numel()), _f(p_drop), C.c_uint(seed & 0xFFFFFFFF),
+          _stream())
+    return out
+
+
+def colsum_bf16(x, out, dim=None, ld=None):
+    _req(x, torch.bfloat16, "colsum_bf16.x")
+    rows = x.shape[0]
+    _call("ctclip_colsum_bf16", _ptr(x), _ll(rows), dim if dim is not None else x.shape[1],
+          _ll(ld if ld is not None else x.stride(0)), _ptr(out), _stream())

@@ -1,0 +1,295 @@
+"""The injected BERT text tower of CT-CLIP on the sm_100a kernels.
+
+Reference: `CTCLIP.forward` calls `self.text_transformer(text.input_ids, attention_mask=text.attention_mask)[0]`
+(ct_clip.py:685-686) on the HF `BertModel` injected by pretrained_model.py:9 (microsoft/BiomedVLP-CXR-BERT-specialized:
+BERT-base, post-LayerNorm, absolute position embeddings, erf GELU, LayerNorm eps 1e-12, dropout 0.1 in train mode).
+
+`NativeBert` reads the parameters of that *unchanged* HF module (state_dict keys stay HF's), runs the forward and the
+backward through libctclip_sm100.so — tcgen05 GEMMs for every projection and for the per-head Q K^T / P V products
+(batched mode), memory-bound kernels for embeddings / softmax / GELU / LayerNorm / dropout — and hands the parameter
+gradients back to autograd. There is no fallback: unsupported BERT variants are reported by `supports()` and the caller
+keeps the HF module (a library path) for them.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops
+
+
+def supports(module) -> bool:
+    """True for a transformers BertModel with the architecture CT-CLIP uses (absolute positions, gelu, encoder only)"""
+    cfg = getattr(module, "config", None)
+    if cfg is None or module.__class__.__name__ != "BertModel":
+        return False
+    if getattr(cfg, "position_embedding_type", "absolute") != "absolute" or getattr(cfg, "is_decoder", False):
+        return False
+    if getattr(cfg, "hidden_act", "gelu") != "gelu" or getattr(cfg, "add_cross_attention", False):
+        return False
+    hd = cfg.hidden_size // cfg.num_attention_heads
+    return cfg.hidden_size % 8 == 0 and hd % 8 == 0 and cfg.intermediate_size % 8 == 0 and cfg.hidden_size <= 1024
+
+
+class _LayerW:
+    pass
+
+
+class NativeBert:
+    def __init__(self, module):
+        assert supports(module)
+        self.m = module
+        cfg = module.config
+        self.D, self.H, self.I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        self.hd = self.D // self.H
+        self.eps = cfg.layer_norm_eps
+        self.p_hidden, self.p_attn = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob
+        self.vocab = cfg.vocab_size
+        self._key, self._layers = None, None
+        self.calls = 0
+        # parameters in a fixed order (the autograd.Function takes them as inputs and returns their gradients)
+        emb = module.embeddings
+        self.names, self.params = [], []
+        for n, p in module.named_parameters():
+            if n.startswith("pooler."):
+                continue  # never reached: CT-CLIP reads last_hidden_state[:, 0] (ct_clip.py:762), not pooler_output
+            self.names.append(n)
+            self.params.append(p)
+        self.index = {n: i for i, n in enumerate(self.names)}
+        assert emb.word_embeddings.weight is self.params[self.index["embeddings.word_embeddings.weight"]]
+
+    # bf16 operand copies (derived caches, rebuilt when a parameter changes)
+    def layers(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.params[:8]) + (self.params[-1]._version,)
+        if self._layers is not None and key == self._key:
+            return self._layers
+        out = []
+        for layer in self.m.encoder.layer:
+            a, w = layer.attention, _LayerW()
+            s = a.self
+            w.wqkv = torch.cat((s.query.weight, s.key.weight, s.value.weight), 0).detach().to(torch.bfloat16).contiguous()
+            w.bqkv = torch.cat((s.query.bias, s.key.bias, s.value.bias), 0).detach().float().contiguous()
+            w.wo = a.output.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.bo = a.output.dense.bias.detach()
+            w.g1, w.b1n = a.output.LayerNorm.weight.detach(), a.output.LayerNorm.bias.detach()
+            w.w1 = layer.intermediate.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.b1 = layer.intermediate.dense.bias.detach()
+            w.w2 = layer.output.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.b2 = layer.output.dense.bias.detach()
+            w.g2, w.b2n = layer.output.LayerNorm.weight.detach(), layer.output.LayerNorm.bias.detach()
+            out.append(w)
+        self._key, self._layers = key, out
+        return out
+
+    def invalidate(self):
+        self._key = None
+
+    # ------------------------------------------------------------------------------------------ attention products
+    def _scores(self, qkv, B, L):
+        """S[b,h] = Q_bh K_bh^T  (fp32 [B,H,L,L])"""
+        D, H, hd = self.D, self.H, self.hd
+        S = torch.empty((B * H, L, L), device=qkv.device, dtype=torch.float32)
+        base = qkv.data_ptr()
+        d = ops.gemm_batched(base, 3 * D, False, hd, L * 3 * D, base + 2 * D, 3 * D, False, hd, L * 3 * D,
+                             S, L, L * L, H * L * L, L, L, hd, H, B)
+        ops.run_gemm_desc(d, True, f"bert_qk:{B}x{H}x{L}x{L}x{hd}", 2.0 * B * H * L * L * hd)
+        return S
+
+    def _pv(self, P, qkv, B, L):
+        """ctx[b, :, h] = P_bh V_bh  (bf16 [B*L, D])"""
+        D, H, hd = self.D, self.H, self.hd
+        ctx = torch.empty((B * L, D), device=qkv.device, dtype=torch.bfloat16)
+        d = ops.gemm_batched(P.data_ptr(), L, False, L * L, H * L * L, qkv.data_ptr() + 2 * (2 * D), 3 * D, True, hd,
+                             L * 3 * D, ctx, D, hd, L * D, L, hd, L, H, B)
+        ops.run_gemm_desc(d, False, f"bert_pv:{B}x{H}x{L}x{hd}x{L}", 2.0 * B * H * L * L * hd)
+        return ctx
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, ids, mask, training: bool):
+        B, L = ids.shape
+        D, H, hd, I = self.D, self.H, self.hd, self.I
+        T = B * L
+        emb = self.m.embeddings
+        ph = self.p_hidden if training else 0.0
+        pa = self.p_attn if training else 0.0
+        self.calls += 1
+        seed0 = (self.calls * 7919 + 17) & 0x7FFFFFFF
+        ids = ids.contiguous()
+        mask = mask.contiguous().to(torch.long)
+        ctx = {"B": B, "L": L, "ph": ph, "pa": pa, "seed0": seed0, "ids": ids, "mask": mask, "layers": []}
+        pre0 = ops.bert_embed_fwd(ids.reshape(-1), L, emb.word_embeddings.weight.detach(),
+                                  emb.position_embeddings.weight.detach(),
+                                  emb.token_type_embeddings.weight.detach()[0].contiguous())
+        xb, _, x = ops.layernorm_fwd(pre0, emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), eps=self.eps,
+                                     want_bf16=(ph == 0), want_f32=True)
+        if ph > 0:
+            x = ops.dropout_add(x, None, ph, seed0)
+            xb = ops.cast_bf16(x)
+        ctx["pre0"] = pre0
+        scale = 1.0 / math.sqrt(hd)
+        for li, w in enumerate(self.layers()):
+            c = {}
+            sd = seed0 + 101 * (li + 1)
+            qkv = ops.gemm(xb, w.wqkv, bias=w.bqkv, tag=f"bert_qkv:{T}x{3 * D}x{D}")
+            S = self._scores(qkv, B, L)
+            P, Pd = ops.bert_softmax_fwd(S, mask, B, H, L, scale, pa, sd + 1)
+            del S
+            cv = self._pv(Pd if Pd is not None else P, qkv, B, L)
+            if ph > 0:
+                ao = ops.gemm(cv, w.wo, out_dtype=torch.float32, bias=w.bo, tag=f"bert_out:{T}x{D}x{D}")
+                pre1 = ops.dropout_add(ao, x, ph, sd + 2)
+            else:
+                pre1 = ops.gemm(cv, w.wo, out_dtype=torch.float32, bias=w.bo, resid=x, tag=f"bert_out:{T}x{D}x{D}")
+            x1b, _, x1 = ops.layernorm_fwd(pre1, w.g1, w.b1n, eps=self.eps, want_bf16=True, want_f32=True)
+            h = ops.gemm(x1b, w.w1, bias=w.b1, tag=f"bert_ff1:{T}x{I}x{D}")
+            a = ops.gelu_fwd(h)
+            if ph > 0:
+                y = ops.gemm(a, w.w2, out_dtype=torch.float32, bias=w.b2, tag=f"bert_ff2:{T}x{D}x{I}")
+                pre2 = ops.dropout_add(y, x1, ph, sd + 3)
+            else:
+                pre2 = ops.gemm(a, w.w2, out_dtype=torch.float32, bias=w.b2, resid=x1, tag=f"bert_ff2:{T}x{D}x{I}")
+            x2b, _, x2 = ops.layernorm_fwd(pre2, w.g2, w.b2n, eps=self.eps, want_bf16=True, want_f32=True)
+            c["xb"], c["qkv"], c["P"], c["Pd"], c["cv"], c["pre1"], c["x1b"], c["h"], c["a"], c["pre2"], c["sd"] = \
+                xb, qkv, P, Pd, cv, pre1, x1b, h, a, pre2, sd
+            ctx["layers"].append(c)
+            x, xb = x2, x2b
+        return x.view(B, L, D), ctx
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, ctx, g_out):
+        """g_out: dL/d(last_hidden_state) fp32 [B, L, D]. Returns the list of parameter gradients in self.params order."""
+        B, L, ph, pa = ctx["B"], ctx["L"], ctx["ph"], ctx["pa"]
+        D, H, hd, I = self.D, self.H, self.hd, self.I
+        T = B * L
+        dev = g_out.device
+        grads = [None] * len(self.params)
+
+        def put(name, g):
+            grads[self.index[name]] = g
+
+        def zeros(*shape):
+            return torch.zeros(shape, device=dev, dtype=torch.float32)
+
+        def wgrad(dy_bf, x_bf, n_out, n_in):
+            dw = zeros(n_out, n_in)
+            ops.gemm(dy_bf, x_bf, a_t=True, b_t=True, out=dw, accumulate=True, splits=0, tag=f"bert_wgrad:{n_out}x{n_in}x{T}")
+            return dw
+
+        scale = 1.0 / math.sqrt(hd)
+        g = g_out.reshape(T, D).contiguous().float()
+        layers = self.layers()
+        for li in reversed(range(len(layers))):
+            w, c = layers[li], ctx["layers"][li]
+            sd = c["sd"]
+            pfx = f"encoder.layer.{li}."
+            # ---- BertOutput: LayerNorm(dropout(dense(a)) + x1)
+            dg, db = zeros(D), zeros(D)
+            dpre2, dpre2_b = ops.layernorm_bwd(g, c["pre2"], w.g2, eps=self.eps, dgamma=dg, dbeta=db, want_bf16=(ph == 0))
+            put(pfx + "output.LayerNorm.weight", dg)
+            put(pfx + "output.LayerNorm.bias", db)
+            if ph > 0:
+                dy = ops.dropout_add(dpre2, None, ph, sd + 3)
+                dy_b = ops.cast_bf16(dy)
+            else:
+                dy, dy_b = dpre2, dpre2_b
+            db2 = zeros(D)
+            ops.colsum(dy, db2)
+            put(pfx + "output.dense.bias", db2)
+            put(pfx + "output.dense.weight", wgrad(dy_b, c["a"], D, I))
+            da = ops.gemm(dy_b, w.w2, b_t=True, tag=f"bert_dgrad:{T}x{I}x{D}")
+            # ---- BertIntermediate: gelu(dense(x1))
+            dh = ops.gelu_bwd(c["h"], da)
+            db1 = zeros(I)
+            ops.colsum_bf16(dh, db1)
+            put(pfx + "intermediate.dense.bias", db1)
+            put(pfx + "intermediate.dense.weight", wgrad(dh, c["x1b"], I, D))
+            # x1 feeds the FFN and, as the residual, pre2: its gradient is the FFN data gradient + dpre2 (GEMM epilogue)
+            dx1 = ops.gemm(dh, w.w1, b_t=True, out_dtype=torch.float32, resid=dpre2, tag=f"bert_dgrad:{T}x{D}x{I}")
+            del dh, da
+            # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
+            dg, db = zeros(D), zeros(D)
+            dpre1, dpre1_b = ops.layernorm_bwd(dx1, c["pre1"], w.g1, eps=self.eps, dgamma=dg, dbeta=db, want_bf16=(ph == 0))
+            put(pfx + "attention.output.LayerNorm.weight", dg)
+            put(pfx + "attention.output.LayerNorm.bias", db)
+            if ph > 0:
+                dao = ops.dropout_add(dpre1, None, ph, sd + 2)
+                dao_b = ops.cast_bf16(dao)
+            else:
+                dao, dao_b = dpre1, dpre1_b
+            dbo = zeros(D)
+            ops.colsum(dao, dbo)
+            put(pfx + "attention.output.dense.bias", dbo)
+            put(pfx + "attention.output.dense.weight", wgrad(dao_b, c["cv"], D, D))
+            dcv = ops.gemm(dao_b, w.wo, b_t=True, tag=f"bert_dgrad:{T}x{D}x{D}")
+            # ---- BertSelfAttention
+            qkv, P, Pd = c["qkv"], c["P"], c["Pd"]
+            Pop = Pd if Pd is not None else P
+            base = qkv.data_ptr()
+            dqkv = torch.empty_like(qkv)
+            dbase = dqkv.data_ptr()
+            fl = 2.0 * B * H * L * L * hd
+            # dP = dctx V^T   (fp32 [B,H,L,L])
+            dP = torch.empty((B * H, L, L), device=dev, dtype=torch.float32)
+            d = ops.gemm_batched(dcv.data_ptr(), D, False, hd, L * D, base + 2 * (2 * D), 3 * D, False, hd, L * 3 * D,
+                                 dP, L, L * L, H * L * L, L, L, hd, H, B)
+            ops.run_gemm_desc(d, True, f"bert_dp:{B}x{H}x{L}x{L}x{hd}", fl)
+            # dV = P^T dctx  -> v slice of dqkv
+            d = ops.gemm_batched(Pop.data_ptr(), L, True, L * L, H * L * L, dcv.data_ptr(), D, True, hd, L * D,
+                                 dbase + 2 * (2 * D), 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+            ops.run_gemm_desc(d, False, f"bert_dv:{B}x{H}x{L}x{hd}x{L}", fl)
+            dS = ops.bert_softmax_bwd(P, dP, B, H, L, scale, pa, sd + 1)
+            del dP
+            # dQ = dS K -> q slice ; dK = dS^T Q -> k slice
+            d = ops.gemm_batched(dS.data_ptr(), L, False, L * L, H * L * L, base + 2 * D, 3 * D, True, hd, L * 3 * D,
+                                 dbase, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+            ops.run_gemm_desc(d, False, f"bert_dq:{B}x{H}x{L}x{hd}x{L}", fl)
+            d = ops.gemm_batched(dS.data_ptr(), L, True, L * L, H * L * L, base, 3 * D, True, hd, L * 3 * D,
+                                 dbase + 2 * D, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+            ops.run_gemm_desc(d, False, f"bert_dk:{B}x{H}x{L}x{hd}x{L}", fl)
+            del dS
+            dbqkv = zeros(3 * D)
+            ops.colsum_bf16(dqkv, dbqkv)
+            dwqkv = wgrad(dqkv, c["xb"], 3 * D, D)
+            for j, nm in enumerate(("query", "key", "value")):
+                put(pfx + f"attention.self.{nm}.weight", dwqkv[j * D:(j + 1) * D])
+                put(pfx + f"attention.self.{nm}.bias", dbqkv[j * D:(j + 1) * D])
+            g = ops.gemm(dqkv, w.wqkv, b_t=True, out_dtype=torch.float32, resid=dpre1, tag=f"bert_dgrad:{T}x{D}x{3 * D}")
+            ctx["layers"][li] = None
+        # ---- embeddings: LayerNorm(word + pos + type) (+ dropout)
+        emb = self.m.embeddings
+        if ph > 0:
+            g = ops.dropout_add(g, None, ph, ctx["seed0"])
+        dg, db = zeros(D), zeros(D)
+        dpre0, _ = ops.layernorm_bwd(g, ctx["pre0"], emb.LayerNorm.weight.detach(), eps=self.eps, dgamma=dg, dbeta=db)
+        put("embeddings.LayerNorm.weight", dg)
+        put("embeddings.LayerNorm.bias", db)
+        dword = zeros(*emb.word_embeddings.weight.shape)
+        dpos = zeros(*emb.position_embeddings.weight.shape)
+        ops.bert_embed_bwd(ctx["ids"].reshape(-1), L, dpre0, dword, dpos, emb.word_embeddings.padding_idx)
+        dtype_ = zeros(*emb.token_type_embeddings.weight.shape)
+        ops.colsum(dpre0, dtype_[0])
+        put("embeddings.word_embeddings.weight", dword)
+        put("embeddings.position_embeddings.weight", dpos)
+        put("embeddings.token_type_embeddings.weight", dtype_)
+        return grads
+
+
+class BertFunction(torch.autograd.Function):
+    """last_hidden_state = BertModel(input_ids, attention_mask)[0] with a hand-written backward"""
+
+    @staticmethod
+    def forward(ctx, engine, ids, mask, training, *params):
+        out, saved = engine.forward(ids, mask, training)
+        ctx.engine, ctx.saved = engine, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.engine.backward(ctx.saved, g)
+        ctx.saved = None
+        return (None, None, None, None, *grads)
+
+
+def encode(engine: NativeBert, ids, mask, training: bool):
+    return BertFunction.apply(engine, ids, mask, training, *engine.params)

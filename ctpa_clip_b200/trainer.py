@@ -90,6 +90,8 @@ class CTClipTrainStep:
         self.model.visual_transformer.invalidate_weights()
         self.model._sh_text.key = None
         self.model._sh_vis.key = None
+        if getattr(self.model, "_native_text", None) is not None:
+            self.model._native_text.invalidate()
 
     def step(self, text, video):
         loss = self.forward_backward(text, video)

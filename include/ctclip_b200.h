@@ -56,6 +56,11 @@ typedef struct ctclip_gemm_desc {
   int atomic;
   int splits;
   void* top2_out; /* non-NULL: float4 [M][ceil(N/BN)] = per n-tile best two (value, column-as-int-bits); C unused */
+  /* batched mode (multi-head attention products of the BERT text tower, transformers BertSelfAttention): batch_h * batch_b
+   * independent M x N x K problems; problem (b, h) reads A + b*a_stride_b + h*a_stride_h (elements; same for B, C).
+   * M, N, K are per-problem extents: tiles never read a neighbouring problem (TMA zero fill). 0 / 1 = not batched. */
+  int batch_h, batch_b;
+  long long a_stride_h, a_stride_b, b_stride_h, b_stride_b, c_stride_h, c_stride_b;
 } ctclip_gemm_desc;
 /* N-tile width the kernel will use for a given N (128 or 256): sizes the top2_out buffer */
 int ctclip_gemm_tile_n(int N);
@@ -76,6 +81,33 @@ int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, in
 int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
 /* out[c] += sum_rows x[row][c]  (bias gradients) */
 int ctclip_colsum(const float* x, long long rows, int dim, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BERT text tower (reference: ct_clip.py:685-686 -> transformers.BertModel(input_ids, attention_mask)[0];
+ * pretrained_model.py:9 injects the BERT-base sized CXR-BERT). The projections and the per-head Q K^T / P V products
+ * (and their gradients) run on ctclip_gemm_bf16 (batched mode); these are the kernels between them.
+ *   bert_embed_fwd/bwd : BertEmbeddings word + position + token_type(0) gather, and its gradient scatter
+ *   bert_softmax_fwd   : BertSelfAttention softmax(scale * scores + key mask) (+ attention-probs dropout)
+ *                        scores fp32 [batch*heads][seq][seq], mask int64 [batch][seq] (1 = attend), probs bf16
+ *   bert_softmax_bwd   : dscores = scale * P * (dP - rowsum(P dP)), dP = dropout'(dprobs_dropped)
+ *   gelu_fwd/bwd       : exact (erf) GELU of BertIntermediate on bf16
+ *   dropout_add        : out = dropout(y) (+ resid) (BertSelfOutput / BertOutput hidden dropout; resid NULL = the
+ *                        dropout gradient); masks are a stateless hash of (seed, element index), never stored
+ *   colsum_bf16        : out[c] += sum_rows x[row][c] on bf16 (bias gradients) */
+int ctclip_bert_embed_fwd(const long long* ids, long long tokens, int seq_len, const float* word, const float* pos,
+                          const float* type0, int dim, int vocab, float* out, void* stream);
+int ctclip_bert_embed_bwd(const long long* ids, long long tokens, int seq_len, const float* dx, int dim, int vocab,
+                          long long pad_id /* nn.Embedding padding_idx: no gradient; -1 = none */, float* dword, float* dpos,
+                          void* stream);
+int ctclip_bert_softmax_fwd(const float* scores, const long long* mask, int batch, int heads, int seq_len, float scale,
+                            void* probs, void* probs_dropped, float p_drop, unsigned seed, void* stream);
+int ctclip_bert_softmax_bwd(const void* probs, const float* dprobs_dropped, int batch, int heads, int seq_len, float scale,
+                            void* dscores, float p_drop, unsigned seed, void* stream);
+int ctclip_gelu_fwd(const void* h, void* out, long long n, void* stream);
+int ctclip_gelu_bwd(const void* h, const void* dy, void* dh, long long n, void* stream);
+int ctclip_dropout_add(const float* y, const float* resid, float* out, long long n, float p_drop, unsigned seed,
+                       void* stream);
+int ctclip_colsum_bf16(const void* x, long long rows, int dim, long long ld, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PEG (attention.py:56-84): y = x + dwconv3x3x3_causal(x) + bias on tokens kept in the canonical (b,t,h,w,d) layout.
