@@ -71,8 +71,10 @@ embed_bwd_kernel(const long long* __restrict__ ids, int L, const float* __restri
 
 // ------------------------------------------------------------------------------------------ softmax
 // P = softmax(scale * S + (mask ? 0 : -inf)) over the keys of one (batch, head, query) row; Pd = dropout(P).
-// S: fp32 [Z][L][L] with z = b * H + h; mask: [B][L] (1 = attend). kPer = ceil(L / 32) <= 32 values per lane.
-template <int kPer>
+// S: fp32 [Z][L][L] with z = b * H + h; mask: [B][L] (1 = attend). One warp per row; lane l owns the 4 consecutive
+// columns 128 j + 4 l .. + 3 of every 128-column block j (128-bit loads, 64-bit bf16 stores); kBlk = ceil(L / 128).
+// L % 4 == 0 takes the vector path, anything else the scalar one (same arithmetic).
+template <int kBlk>
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ S, const long long* __restrict__ mask, int H, int L, float scale,
                    __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, float p_drop, unsigned seed,
@@ -83,38 +85,67 @@ softmax_fwd_kernel(const float* __restrict__ S, const long long* __restrict__ ma
   const long long b = row / ((long long)H * L);
   const float* s = S + row * L;
   const long long* m = mask + b * L;
-  float v[kPer];
+  const bool vec = (L & 3) == 0;
+  float v[kBlk][4];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int c = lane + 32 * j;
-    v[j] = (c < L && m[c] != 0) ? s[c] * scale : -INFINITY;
-    mx = fmaxf(mx, v[j]);
+  for (int j = 0; j < kBlk; ++j) {
+    const int c = 128 * j + 4 * lane;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+      if (c < L) x = *reinterpret_cast<const float4*>(s + c);
+    } else {
+      if (c < L) x.x = s[c];
+      if (c + 1 < L) x.y = s[c + 1];
+      if (c + 2 < L) x.z = s[c + 2];
+      if (c + 3 < L) x.w = s[c + 3];
+    }
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[j][e] = (c + e < L && m[c + e] != 0) ? xs[e] * scale : -INFINITY;
+      mx = fmaxf(mx, v[j][e]);
+    }
   }
   mx = warp_max(mx);
   if (mx == -INFINITY) mx = 0.f;  // fully masked row: all probabilities 0
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    v[j] = __expf(v[j] - mx);
-    sum += v[j];
-  }
+  for (int j = 0; j < kBlk; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[j][e] = __expf(v[j][e] - mx);
+      sum += v[j][e];
+    }
   sum = warp_sum(sum);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
   const float keep_scale = 1.f / (1.f - p_drop);
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int c = lane + 32 * j;
-    if (c < L) {
-      const float pr = v[j] * inv;
-      P[row * L + c] = __float2bfloat16_rn(pr);
+  for (int j = 0; j < kBlk; ++j) {
+    const int c = 128 * j + 4 * lane;
+    if (c >= L) continue;
+    float pr[4], pd[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      pr[e] = v[j][e] * inv;
+      pd[e] = (Pd != nullptr && keep_elem((unsigned long long)(row * L + c + e), seed, p_drop)) ? pr[e] * keep_scale : 0.f;
+    }
+    if (vec) {
+      *reinterpret_cast<uint2*>(P + row * L + c) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
       if (Pd != nullptr)
-        Pd[row * L + c] = __float2bfloat16_rn(keep_elem((unsigned long long)(row * L + c), seed, p_drop) ? pr * keep_scale : 0.f);
+        *reinterpret_cast<uint2*>(Pd + row * L + c) = make_uint2(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < L) {
+          P[row * L + c + e] = __float2bfloat16_rn(pr[e]);
+          if (Pd != nullptr) Pd[row * L + c + e] = __float2bfloat16_rn(pd[e]);
+        }
     }
   }
 }
 // dS = scale * P * (dP - sum_k P_k dP_k), dP = dropout'(dPd)      (dPd fp32 [Z][L][L], dS bf16)
-template <int kPer>
+template <int kBlk>
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dPd, int L, float scale,
                    __nv_bfloat16* __restrict__ dS, float p_drop, unsigned seed, long long rows) {
@@ -122,25 +153,52 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict_
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float keep_scale = 1.f / (1.f - p_drop);
-  float pr[kPer], g[kPer];
+  const bool vec = (L & 3) == 0;
+  float pr[kBlk][4], g[kBlk][4];
   float dot = 0.f;
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int c = lane + 32 * j;
-    pr[j] = 0.f; g[j] = 0.f;
-    if (c < L) {
-      pr[j] = __bfloat162float(P[row * L + c]);
-      float d = dPd[row * L + c];
-      if (p_drop > 0.f) d = keep_elem((unsigned long long)(row * L + c), seed, p_drop) ? d * keep_scale : 0.f;
-      g[j] = d;
-      dot = fmaf(pr[j], d, dot);
+  for (int j = 0; j < kBlk; ++j) {
+    const int c = 128 * j + 4 * lane;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 pp = make_uint2(0u, 0u);
+    if (vec) {
+      if (c < L) {
+        d = *reinterpret_cast<const float4*>(dPd + row * L + c);
+        pp = *reinterpret_cast<const uint2*>(P + row * L + c);
+      }
+      pr[j][0] = bf16_lo(pp.x); pr[j][1] = bf16_hi(pp.x); pr[j][2] = bf16_lo(pp.y); pr[j][3] = bf16_hi(pp.y);
+    } else {
+      float* dd = &d.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        pr[j][e] = 0.f;
+        if (c + e < L) { dd[e] = dPd[row * L + c + e]; pr[j][e] = __bfloat162float(P[row * L + c + e]); }
+      }
+    }
+    const float ds[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = ds[e];
+      if (p_drop > 0.f) x = keep_elem((unsigned long long)(row * L + c + e), seed, p_drop) ? x * keep_scale : 0.f;
+      g[j][e] = (c + e < L) ? x : 0.f;
+      dot = fmaf(pr[j][e], g[j][e], dot);
     }
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    const int c = lane + 32 * j;
-    if (c < L) dS[row * L + c] = __float2bfloat16_rn(scale * pr[j] * (g[j] - dot));
+  for (int j = 0; j < kBlk; ++j) {
+    const int c = 128 * j + 4 * lane;
+    if (c >= L) continue;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = scale * pr[j][e] * (g[j][e] - dot);
+    if (vec) {
+      *reinterpret_cast<uint2*>(dS + row * L + c) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < L) dS[row * L + c + e] = __float2bfloat16_rn(o[e]);
+    }
   }
 }
 
@@ -243,12 +301,12 @@ extern "C" int ctclip_bert_embed_bwd(const long long* ids, long long tokens, int
 
 #define SOFTMAX_DISPATCH(KERNEL, ...)                                                         \
   do {                                                                                        \
-    const int per = (seq_len + 31) / 32;                                                      \
+    const int blk = (seq_len + 127) / 128;                                                    \
     const unsigned blocks = (unsigned)((rows + 7) / 8);                                       \
-    if (per <= 1) KERNEL<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);           \
-    else if (per <= 4) KERNEL<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);      \
-    else if (per <= 16) KERNEL<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);    \
-    else KERNEL<32><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                   \
+    if (blk <= 1) KERNEL<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);           \
+    else if (blk <= 2) KERNEL<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);      \
+    else if (blk <= 4) KERNEL<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);      \
+    else KERNEL<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                    \
   } while (0)
 
 extern "C" int ctclip_bert_softmax_fwd(const float* scores, const long long* mask, int batch, int heads, int seq_len,
@@ -313,9 +371,9 @@ extern "C" int ctclip_colsum_bf16(const void* x, long long rows, int dim, long l
   if ((dim % 2) || (ld % 2)) return ctclip::fail(CTCLIP_E_ALIGN, "colsum_bf16: dim and ld must be even");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
-  int rpb = 64;
+  int rpb = 8;   // rows per block: enough blocks to fill the chip even for a few thousand rows
   long long blocks = (rows + rpb - 1) / rpb;
-  const long long cap = (long long)ctclip::sm_count() * 8;
+  const long long cap = (long long)ctclip::sm_count() * 16;
   if (blocks > cap) {
     rpb = (int)((rows + cap - 1) / cap);
     blocks = (rows + rpb - 1) / rpb;

@@ -186,6 +186,68 @@ __device__ __forceinline__ void store_chunk_coalesced(const GemmKernelParams& p,
   }
 }
 
+// Lean epilogues for the hot cases (alpha == 1, 16-byte aligned rows, whole 32-column chunks). The warp's accumulator
+// block goes through a swizzled 4 KB staging tile so that every global access is a 128-bit piece of a full 128-byte line.
+// bf16, no bias: 64 columns (two TMEM chunks) per round -> each output row receives one 128-byte line.
+__device__ __forceinline__ void epi_store_bf16x64(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
+                                                  const uint32_t (&a)[32], const uint32_t (&b)[32], int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t* s = g < 4 ? a : b;
+    const int o = (g & 3) * 8;
+    const uint4 v = make_uint4(pack_bf16(__uint_as_float(s[o + 0]), __uint_as_float(s[o + 1])),
+                               pack_bf16(__uint_as_float(s[o + 2]), __uint_as_float(s[o + 3])),
+                               pack_bf16(__uint_as_float(s[o + 4]), __uint_as_float(s[o + 5])),
+                               pack_bf16(__uint_as_float(s[o + 6]), __uint_as_float(s[o + 7])));
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) = v;
+  }
+  __syncwarp();
+  const int g = lane & 7;
+  __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + col0 + g * 8;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int i = it * 4 + (lane >> 3);
+    const uint4 x = *reinterpret_cast<const uint4*>(stg + i * 128 + ((g ^ (i & 7)) << 4));
+    if (row0 + i < p.M) *reinterpret_cast<uint4*>(cb + (long long)(row0 + i) * p.ldc) = x;
+  }
+  __syncwarp();
+}
+// fp32 (+ bias) (+ residual, which may alias C): 32 columns per round
+template <bool RESID, bool BIAS>
+__device__ __forceinline__ void epi_store_f32x32(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
+                                                 const uint32_t (&a)[32], int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+        make_uint4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+  __syncwarp();
+  const int g = lane & 7;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (BIAS) bias4 = *reinterpret_cast<const float4*>(p.bias + col0 + g * 4);
+  float* cb = reinterpret_cast<float*>(p.C) + col0 + g * 4;
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {   // residual loads of four row groups are batched ahead of their stores (resid may alias C)
+    float4 rr[4];
+    if (RESID) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int grow = row0 + (hb * 4 + it) * 4 + (lane >> 3);
+        rr[it] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + g * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = (hb * 4 + it) * 4 + (lane >> 3);
+      float4 x = *reinterpret_cast<const float4*>(stg + i * 128 + ((g ^ (i & 7)) << 4));
+      if (BIAS) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
+      if (RESID) { x.x += rr[it].x; x.y += rr[it].y; x.z += rr[it].z; x.w += rr[it].w; }
+      if (row0 + i < p.M) *reinterpret_cast<float4*>(cb + (long long)(row0 + i) * p.ldc) = x;
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- kernel
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -306,6 +368,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== residual prefetcher =====================
+    // The fp32 residual tile the epilogue adds is read with ordinary loads; this otherwise idle warp pulls the NEXT
+    // tile's residual into L2 while the current tile is being multiplied, pacing itself on the accumulator barrier.
+    if (p.resid != nullptr && p.z_n <= 1) {
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int wn = w + gridDim.x;
+        if (wn < num_work) {
+          const int n_t = wn % p.n_tiles;
+          const int m_t = (wn / p.n_tiles) % p.m_tiles;
+          const int cols = min(BN, p.N - n_t * BN);
+          const int lines = (cols * 4 + 127) / 128;            // 128-byte lines per tile row
+          for (int i = lane; i < BM * lines; i += 32) {
+            const int r = m_t * BM + i / lines;
+            if (r < p.M)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + n_t * BN + (i % lines) * 32));
+          }
+        }
+        mbar_wait_bounded(tmem_full + acc, acc_phase, 1u << 16);   // observe only: the epilogue warps own the hand-shake
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp & 3;          // TMEM lane quadrant this warp may read
@@ -318,6 +404,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         (p.resid == nullptr || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && ((p.ldr * 4) % 16 == 0))) &&
         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
         (p.z_n <= 1 || (((p.c_stride_h | p.c_stride_b) * (p.c_is_f32 ? 4 : 2)) % 16 == 0));
+    // 0: generic; 1: bf16 plain; 2..5: fp32 (+resid) (+bias)
+    const int fast_mode = (!aligned_out || p.atomic || p.alpha != 1.f) ? 0
+                          : (!p.c_is_f32 ? (p.bias == nullptr ? 1 : 0)
+                                         : 2 + (p.resid != nullptr ? 1 : 0) + (p.bias != nullptr ? 2 : 0));
     int acc = 0;
     uint32_t acc_phase = 0;
     GemmKernelParams pz = p;   // per-problem view: C shifted to the (head, batch) slice in batched mode
@@ -358,6 +448,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (row < p.M)
             p.top2[(long long)row * p.n_tiles + n_t] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
+        }
+      } else if (fast_mode == 1 && n_t * BN + (ch + 1) * kHalf <= p.N) {
+        // bf16 plain: 64 columns per round; the next round's TMEM loads fly while this round is stored
+        const int cbase = n_t * BN + ch * kHalf;
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr + ch * kHalf, r[0]);
+        tmem_ld_32x32(taddr + ch * kHalf + 32, r[1]);
+#pragma unroll
+        for (int c = 0; c < kChunks; c += 2) {
+          tmem_wait_ld();
+          uint32_t a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a[j] = r[0][j]; b[j] = r[1][j]; }
+          if (c + 2 < kChunks) {
+            tmem_ld_32x32(taddr + ch * kHalf + (c + 2) * 32, r[0]);
+            tmem_ld_32x32(taddr + ch * kHalf + (c + 3) * 32, r[1]);
+          }
+          epi_store_bf16x64(pz, stg, m_t * BM + ew * 32, cbase + c * 32, a, b, lane);
+        }
+      } else if (fast_mode >= 2 && n_t * BN + (ch + 1) * kHalf <= p.N) {
+        const int cbase = n_t * BN + ch * kHalf;
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr + ch * kHalf, r[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < kChunks) tmem_ld_32x32(taddr + ch * kHalf + (c + 1) * 32, r[(c + 1) & 1]);
+          const int row0 = m_t * BM + ew * 32, col0 = cbase + c * 32;
+          if (fast_mode == 2) epi_store_f32x32<false, false>(pz, stg, row0, col0, r[c & 1], lane);
+          else if (fast_mode == 3) epi_store_f32x32<true, false>(pz, stg, row0, col0, r[c & 1], lane);
+          else if (fast_mode == 4) epi_store_f32x32<false, true>(pz, stg, row0, col0, r[c & 1], lane);
+          else epi_store_f32x32<true, true>(pz, stg, row0, col0, r[c & 1], lane);
         }
       } else {
         const int cbase = n_t * BN + ch * kHalf;

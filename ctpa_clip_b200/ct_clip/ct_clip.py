@@ -202,12 +202,14 @@ class CTCLIP(nn.Module):
                 freeze_image_encoder=False, freeze_text_encoder=False, text_to_image=True, aug_text=None, aug_image=None):
         if exists(aug_text) or exists(aug_image):
             raise NotImplementedError("multiview augmentation is not used by CT-CLIP and not implemented")
-        enc_text = self.encode_text(text)
         if return_encodings:
             vit = self.visual_transformer
-            return enc_text, vit.encode_pooled(image)
-        text_raw = self.text_latents_raw(enc_text)
+            return self.encode_text(text), vit.encode_pooled(image)
+        # the image tower (few, long kernels) is enqueued first so that the host runs ahead of the GPU while it enqueues
+        # the many short kernels of the text tower; the two towers are independent (ct_clip.py:685 / :715)
         image_raw = self.image_latents_raw(image)
+        enc_text = self.encode_text(text)
+        text_raw = self.text_latents_raw(enc_text)
         if return_loss:
             return ClipLossFunction.apply(text_raw, image_raw, self.temperature)
         text_latents, image_latents = L2NormFunction.apply(text_raw), L2NormFunction.apply(image_raw)
