@@ -35,16 +35,18 @@ struct AttnParams {
   int heads, inner, ldq, ldkv, ldo;
   int mode;                 // 0 spatial, 1 temporal
   int n;                    // tokens per sequence
+  int nst;                  // rows a sequence occupies inside a block (n, or n padded to 32 / 64 for packed short sequences)
   int ns;                   // sequences per block
   int num_seqs;             // total sequences
   int gh, gw, gt;           // token grid
   int r_pad;                // rows per block padded to a multiple of 64
+  int num_blocks;           // sequence blocks per head; a CTA (fixed head) walks blocks blockIdx.x / heads, + gridDim.x / heads, ...
 };
 
 __device__ __forceinline__ long long row_token(const AttnParams& p, int blk, int r, bool& valid) {
-  const int sl = r / p.n, pos = r - sl * p.n;
+  const int sl = r / p.nst, pos = r - sl * p.nst;
   const long long seq = (long long)blk * p.ns + sl;
-  valid = (sl < p.ns) && (seq < p.num_seqs);
+  valid = (sl < p.ns) && (pos < p.n) && (seq < p.num_seqs);
   if (!valid) return 0;
   if (p.mode == 0) return seq * p.n + pos;
   const int hw = p.gh * p.gw;
@@ -110,10 +112,9 @@ __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int head = blockIdx.x % p.heads;
-  const int blk = blockIdx.x / p.heads;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int rowt = tid & 127, half = tid >> 7;
-  const int R = p.ns * p.n;
+  const int R = p.ns * p.nst;
   const int nchunks = (R + KC - 1) / KC;
   const int ntiles = (R + QT - 1) / QT;
   const bool has_bias = p.bias_table != nullptr;
@@ -154,12 +155,24 @@ attn_fwd_kernel(const AttnParams p) {
     const int kp = r % p.n;
     sB[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));   // byte offset of key r inside the bias table
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   float cmax = 0.f;  // bound of |8 log2e q^.k^|
 #pragma unroll
   for (int d = 0; d < DH; ++d) cmax = fmaxf(cmax, fabsf(sScale[d] * sScale[DH + d]));
 
-  // ---- K^ and V for the whole block
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem;         // 2 x 64 columns
+  const uint32_t tO = tmem + 128;   // 32 columns
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(QT, KC, false, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
+  uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+
+  // persistent over the sequence blocks of this head: tables, barriers and TMEM are set up once per CTA
+  for (int blk = blockIdx.x / p.heads; blk < p.num_blocks; blk += gridDim.x / p.heads) {
+  // ---- K^ and V for the whole block (every MMA of the previous block has retired: its last tile waited bars + 2)
   for (int r = tid; r < kv_rows; r += blockDim.x) {
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
@@ -180,13 +193,6 @@ attn_fwd_kernel(const AttnParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t tS = tmem;         // 2 x 64 columns
-  const uint32_t tO = tmem + 128;   // 32 columns
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  constexpr uint32_t idesc_s = make_idesc_bf16(QT, KC, false, false);
-  constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
-  uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int r = tile * QT + rowt;
@@ -203,9 +209,9 @@ attn_fwd_kernel(const AttnParams p) {
         store_zero_row_cm(sQ, rowt);
       }
     }
-    const int my_seq = r / p.n;
-    const int my_pos = r - my_seq * p.n;
-    const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);   // keys of this row's own sequence
+    const int my_seq = r / p.nst;
+    const int my_pos = r - my_seq * p.nst;
+    const int key_lo = my_seq * p.nst, key_hi = min(R, key_lo + p.n);   // keys of this row's own sequence
     const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
     const float m_i = cmax + ((has_bias && valid) ? sRowMax[my_pos] : 0.f);
     float l = 0.f;
@@ -264,6 +270,10 @@ attn_fwd_kernel(const AttnParams p) {
             pk[j >> 1] = pack_bf16(e0, e1);
           }
         }
+      } else if (__all_sync(0xffffffffu, k0 + 32 <= key_lo || k0 >= key_hi)) {
+        // packed short sequences: this 32-key piece belongs to other sequences for every row of the warp
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -325,6 +335,7 @@ attn_fwd_kernel(const AttnParams p) {
     tc_fence_before();
     __syncthreads();
   }
+  }  // blocks
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
@@ -365,10 +376,9 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   const AttnParams& p = bp.f;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int head = blockIdx.x % p.heads;
-  const int blk = blockIdx.x / p.heads;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int rowt = tid & 127, half = tid >> 7;
-  const int R = p.ns * p.n;
+  const int R = p.ns * p.nst;
   const int nchunks = (R + BKC - 1) / BKC;
   const int ntiles = (R + QT - 1) / QT;
   const bool has_bias = p.bias_table != nullptr;
@@ -412,6 +422,28 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     const int kp = r % p.n;
     sBn[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 288, tdQ = tmem + 320;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKH, false, false);   // [128 q] x [64 keys], K = 32
+  constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
+  constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
+  constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
+  constexpr uint32_t KH_B = BKH * DH * 2;                                // bytes of 64 key rows of sK / sV
+  float* my_dtab = sdTab + warp * tab_n;
+  uint32_t ph_a = 0, ph_b = 0, ph_m = 0;
+  bool mma_pending = false;
+  float acc_qs[DH], acc_ks[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc_qs[d] = acc_ks[d] = 0.f;
+  int gstep = 0;  // running step counter -> tile ring slot
+
+  // persistent over the sequence blocks of this head: tables, barriers, TMEM and the dbias / scale-gradient
+  // accumulators are set up (and flushed) once per CTA
+  for (int blk = blockIdx.x / p.heads; blk < p.num_blocks; blk += gridDim.x / p.heads) {
   // ---- lse and delta = rowsum(dO * O) for the whole block
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     bool valid = false;
@@ -433,20 +465,6 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 288, tdQ = tmem + 320;
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  constexpr uint32_t idesc_s = make_idesc_bf16(QT, BKH, false, false);   // [128 q] x [64 keys], K = 32
-  constexpr uint32_t idesc_kv = make_idesc_bf16(BKC, DH, true, true);    // [128 keys] x [32], K = 128 queries
-  constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
-  constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
-  constexpr uint32_t KH_B = BKH * DH * 2;                                // bytes of 64 key rows of sK / sV
-  float* my_dtab = sdTab + warp * tab_n;
-  uint32_t ph_a = 0, ph_b = 0, ph_m = 0;
-  bool mma_pending = false;
-  float acc_qs[DH], acc_ks[DH];
-#pragma unroll
-  for (int d = 0; d < DH; ++d) acc_qs[d] = acc_ks[d] = 0.f;
 
   // half 0 builds Q~ rows, half 1 copies dO rows. `pre` holds the raw global row of a tile not yet in shared memory.
   uint4 pre[4];
@@ -500,7 +518,6 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     mma_commit(bars + h);
   };
 
-  int gstep = 0;  // running step counter -> tile ring slot
   for (int c = 0; c < nchunks; ++c) {
     // ---- K^_c (half 0) and V_c (half 1); thread = key row. Every MMA that reads sK / sV has retired (chunk epilogue).
     const int kr = c * BKC + rowt;
@@ -541,9 +558,9 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     for (int i = 0; i < ntiles; ++i, ++gstep) {
       const int buf = gstep % 3, nbuf = (gstep + 1) % 3;
       const int r = i * QT + rowt;
-      const int my_seq = r / p.n;
-      const int my_pos = r - my_seq * p.n;
-      const int key_lo = my_seq * p.n, key_hi = min(R, key_lo + p.n);
+      const int my_seq = r / p.nst;
+      const int my_pos = r - my_seq * p.nst;
+      const int key_lo = my_seq * p.nst, key_hi = min(R, key_lo + p.n);
       const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
       const float lse_i = sLse[r], delta_i = sDelta[r];
       // next tile's rows -> ring slot nbuf (last read by the MMAs of step n-2, retired before step n-1 wrote P / dS)
@@ -616,6 +633,10 @@ attn_bwd_kernel(const AttnBwdParams bp) {
               dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
             }
           }
+        } else if (__all_sync(0xffffffffu, k0 + 32 <= key_lo || k0 >= key_hi)) {
+          // packed short sequences: this 32-key piece belongs to other sequences for every row of the warp
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[h * 16 + j] = dk[h * 16 + j] = 0u;
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -745,6 +766,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   }
   tc_fence_before();
   __syncthreads();
+  }  // blocks
   {
     // cross-thread reduction of the scale gradients through the (now idle) tile buffers: [256 threads][64 + 1] floats
     float* scratch = reinterpret_cast<float*>(smem);  // 66.5 KB <= tile rings + K + V + P (112 KB)
@@ -786,7 +808,7 @@ size_t bwd_smem_bytes(const AttnParams& p) {
 
 size_t fwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) + p.n : 0;
-  const size_t kv_rows = (size_t)((p.ns * p.n + KC - 1) / KC) * KC;
+  const size_t kv_rows = (size_t)((p.ns * p.nst + KC - 1) / KC) * KC;
   return kv_rows * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 256 * 4 +
          (size_t)p.r_pad * 4 + 64 + 16;
 }
@@ -803,13 +825,16 @@ int fill_params(AttnParams& p, const ctclip_attn_desc* d, const char* what) {
   p.mode = d->temporal ? 1 : 0;
   p.gh = d->h; p.gw = d->w; p.gt = d->t;
   if (p.mode == 0) {
-    p.n = d->h * d->w; p.ns = 1; p.num_seqs = d->batch * d->t;
+    p.n = d->h * d->w; p.nst = p.n; p.ns = 1; p.num_seqs = d->batch * d->t;
   } else {
     p.n = d->t;
     if (p.n > QT) return ctclip::fail(CTCLIP_E_SHAPE, "%s: temporal sequences longer than 128 are not supported", what);
-    p.ns = QT / p.n; p.num_seqs = d->batch * d->h * d->w;
+    // short sequences are packed at a 32- / 64-row pitch: a warp (32 rows) then belongs to ONE sequence and touches only
+    // the 32-key pieces of that sequence (everything else is skipped warp-uniformly)
+    p.nst = p.n <= 32 ? 32 : (p.n <= 64 ? 64 : p.n);
+    p.ns = QT / p.nst; p.num_seqs = d->batch * d->h * d->w;
   }
-  p.r_pad = (p.ns * p.n + 127) / 128 * 128;
+  p.r_pad = (p.ns * p.nst + 127) / 128 * 128;
   p.q_scale = d->q_scale; p.k_scale = d->k_scale;
   p.bias_table = d->temporal ? nullptr : d->bias_table;
   p.bias_rowmax = d->temporal ? nullptr : d->bias_rowmax;
@@ -835,7 +860,12 @@ extern "C" int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream) {
     configured = smem;
   }
   const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
-  attn_fwd_kernel<<<(unsigned)(blocks * p.heads), 256, smem, (cudaStream_t)stream>>>(p);
+  p.num_blocks = (int)blocks;
+  // persistent: two CTAs per SM (shared memory / TMEM allow two), the same number of CTAs for every head
+  long long per_head = (2LL * ctclip::sm_count()) / p.heads;
+  if (per_head < 1) per_head = 1;
+  if (per_head > blocks) per_head = blocks;
+  attn_fwd_kernel<<<(unsigned)(per_head * p.heads), 256, smem, (cudaStream_t)stream>>>(p);
   return ctclip::check_launch("attn_fwd");
 }
 
@@ -859,6 +889,10 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream) {
     configured = smem;
   }
   const long long blocks = ((long long)p.num_seqs + p.ns - 1) / p.ns;
-  attn_bwd_kernel<<<(unsigned)(blocks * p.heads), 256, smem, (cudaStream_t)stream>>>(bp);
+  p.num_blocks = (int)blocks;
+  long long per_head = (long long)ctclip::sm_count() / p.heads;   // one CTA per SM (512 TMEM columns each)
+  if (per_head < 1) per_head = 1;
+  if (per_head > blocks) per_head = blocks;
+  attn_bwd_kernel<<<(unsigned)(per_head * p.heads), 256, smem, (cudaStream_t)stream>>>(bp);
   return ctclip::check_launch("attn_bwd");
 }

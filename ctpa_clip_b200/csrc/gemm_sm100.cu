@@ -373,21 +373,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // The fp32 residual tile the epilogue adds is read with ordinary loads; this otherwise idle warp pulls the NEXT
     // tile's residual into L2 while the current tile is being multiplied, pacing itself on the accumulator barrier.
     if (p.resid != nullptr && p.z_n <= 1) {
+      auto prefetch_tile = [&](int wn) {
+        if (wn >= num_work) return;
+        const int n_t = wn % p.n_tiles;
+        const int m_t = (wn / p.n_tiles) % p.m_tiles;
+        const int cols = min(BN, p.N - n_t * BN);
+        const int lines = (cols * 4 + 127) / 128;            // 128-byte lines per tile row
+        for (int i = lane; i < BM * lines; i += 32) {
+          const int r = m_t * BM + i / lines;
+          if (r < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + n_t * BN + (i % lines) * 32));
+        }
+      };
       int acc = 0;
       uint32_t acc_phase = 0;
+      prefetch_tile(blockIdx.x);
+      prefetch_tile(blockIdx.x + gridDim.x);
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int wn = w + gridDim.x;
-        if (wn < num_work) {
-          const int n_t = wn % p.n_tiles;
-          const int m_t = (wn / p.n_tiles) % p.m_tiles;
-          const int cols = min(BN, p.N - n_t * BN);
-          const int lines = (cols * 4 + 127) / 128;            // 128-byte lines per tile row
-          for (int i = lane; i < BM * lines; i += 32) {
-            const int r = m_t * BM + i / lines;
-            if (r < p.M)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + n_t * BN + (i % lines) * 32));
-          }
-        }
+        prefetch_tile(w + 2 * gridDim.x);        // two tiles of lead: a short-K tile is over in ~1 us
         mbar_wait_bounded(tmem_full + acc, acc_phase, 1u << 16);   // observe only: the epilogue warps own the hand-shake
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }

@@ -163,10 +163,13 @@ class GradStore:
         return t
 
 
-def layer_backward(g, c: LayerCtx, L: LayerWeights, grid, heads, temporal, tab, rowmax, dtab, gs: GradStore, prefix, dim):
-    """gradient of one [PEG, attention, feed-forward] layer; g = dL/dx3 fp32 [T, dim]; returns dL/dx"""
+def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal, tab, rowmax, dtab, gs: GradStore, prefix,
+                   dim):
+    """gradient of one [PEG, attention, feed-forward] layer; g = dL/dx3 fp32 [T, dim] (g_bf: its bf16 copy, written by
+    the kernel that produced g); returns (dL/dx, its bf16 copy)"""
     inner = L.wq.shape[0]
-    g_bf = ops.cast_bf16(g)
+    if g_bf is None:
+        g_bf = ops.cast_bf16(g)
     # ---- feed-forward (attention.py:44-52)
     du = ops.gemm(g_bf, L.w2p, b_t=True)                                                     # [T, ffp]
     dw2 = gs.zeros(prefix + "3.4.weight", (dim, L.ffp))
@@ -200,8 +203,7 @@ def layer_backward(g, c: LayerCtx, L: LayerWeights, grid, heads, temporal, tab, 
     dw27 = gs.zeros(prefix + "0.dsconv.weight", (27, dim))
     dpb = gs.zeros(prefix + "0.dsconv.bias", (dim,))
     ops.peg_bwd_weight(c.x, g1, dw27, dpb, grid, temporal)
-    g0, _ = ops.peg_bwd_data(g1, L.w27, grid, temporal)
-    return g0
+    return ops.peg_bwd_data(g1, L.w27, grid, temporal, want_bf16=True)
 
 
 def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
@@ -213,17 +215,17 @@ def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
     v = ""
     # temporal transformer
     dgo = gs.zeros("enc_temporal_transformer.norm_out.gamma", (dim,))
-    g, _ = ops.layernorm_bwd(g_tokens, ctx.t_pre, W.t_out, dgamma=dgo)
+    g, g_bf = ops.layernorm_bwd(g_tokens, ctx.t_pre, W.t_out, dgamma=dgo, want_bf16=True)
     for i in reversed(range(len(W.temporal))):
-        g = layer_backward(g, ctx.temporal[i], W.temporal[i], grid, W.heads, True, None, None, None, gs,
-                           f"enc_temporal_transformer.layers.{i}.", dim)
+        g, g_bf = layer_backward(g, g_bf, ctx.temporal[i], W.temporal[i], grid, W.heads, True, None, None, None, gs,
+                                 f"enc_temporal_transformer.layers.{i}.", dim)
         ctx.temporal[i] = None
     dgo = gs.zeros("enc_spatial_transformer.norm_out.gamma", (dim,))
-    g, _ = ops.layernorm_bwd(g, ctx.s_pre, W.s_out, dgamma=dgo)
+    g, g_bf = ops.layernorm_bwd(g, ctx.s_pre, W.s_out, dgamma=dgo, want_bf16=True)
     dtab = torch.zeros_like(ctx.tab)
     for i in reversed(range(len(W.spatial))):
-        g = layer_backward(g, ctx.spatial[i], W.spatial[i], grid, W.heads, False, ctx.tab, ctx.rowmax, dtab, gs,
-                           f"enc_spatial_transformer.layers.{i}.", dim)
+        g, g_bf = layer_backward(g, g_bf, ctx.spatial[i], W.spatial[i], grid, W.heads, False, ctx.tab, ctx.rowmax, dtab, gs,
+                                 f"enc_spatial_transformer.layers.{i}.", dim)
         ctx.spatial[i] = None
     # patch embedding (ctvit.py:169-174)
     a, y0 = ctx.pe
