@@ -571,13 +571,20 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       uint32_t pk[32], dk[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int col = h * BKH + half * 32;
-        const int k0 = c * BKC + col;
+        // This thread's 32 columns of the 64-key half are two 16-column sub-pieces. With the bias table they lie 32
+        // keys apart: their table offsets differ by >= 55 entries, more than the spread of a warp's 32 query positions
+        // (<= 54), so the two read-modify-write chains of the dbias accumulation never touch the same word and can be
+        // interleaved (two chains in flight instead of one). Without bias the sub-pieces are simply adjacent.
+        const int col0 = h * BKH + (has_bias ? half * 16 : half * 32);
+        const int col1 = col0 + (has_bias ? 32 : 16);
+        const int k0 = c * BKC + col0, k1 = c * BKC + col1;
         if (h == 0) { mbar_wait(bars + 0, ph_a); ph_a ^= 1; } else { mbar_wait(bars + 1, ph_b); ph_b ^= 1; }
         tc_fence_after();
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(tS + lane_off + col, s);
-        tmem_ld_32x32(tdP + lane_off + col, dp);
+        uint32_t s0[16], s1[16], dp0[16], dp1[16];
+        tmem_ld_32x16(tS + lane_off + col0, s0);
+        tmem_ld_32x16(tS + lane_off + col1, s1);
+        tmem_ld_32x16(tdP + lane_off + col0, dp0);
+        tmem_ld_32x16(tdP + lane_off + col1, dp1);
         tmem_wait_ld();
         if (h == 0) {
           // S_A / dP_A columns are in registers everywhere after this barrier: the tensor pipe may overwrite them
@@ -589,6 +596,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
             issue_s(nbuf, 0);
           }
         }
+        uint32_t* pk0 = pk + h * 16;      // packed P of sub-piece 0 (8 words), sub-piece 1 at +8
+        uint32_t* dk0 = dk + h * 16;
         if (has_bias) {
           const char* tabb = reinterpret_cast<const char*>(sTab + a_i);
           // Per-warp private dbias table. The lanes of a warp are consecutive query positions (distinct A_i), so one
@@ -596,57 +605,83 @@ attn_bwd_kernel(const AttnBwdParams bp) {
           // hits what lane l-1 hit at key j), which is ordered by the in-order LSU pipe of a converged warp: the
           // accesses are volatile (no compiler reordering) and unconditional (invalid rows / keys add an exact 0).
           volatile char* dtb = reinterpret_cast<volatile char*>(my_dtab + a_i);
-          const int2* nbp = reinterpret_cast<const int2*>(sBn + k0);
-          if (k0 >= key_hi) {            // whole 32-key piece beyond the sequence (warp-uniform): nothing to do
+          const int2* nb0 = reinterpret_cast<const int2*>(sBn + k0);
+          const int2* nb1 = reinterpret_cast<const int2*>(sBn + k1);
+          if (k0 >= key_hi) {               // both sub-pieces beyond the sequence (warp-uniform): nothing to do
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[h * 16 + j] = dk[h * 16 + j] = 0u;
-          } else if (k0 + 32 <= key_hi) {  // fully valid piece: no per-key predicates
+            for (int j = 0; j < 16; ++j) pk0[j] = dk0[j] = 0u;
+          } else if (k1 + 16 <= key_hi) {   // both sub-pieces fully valid: no per-key predicates, two chains interleaved
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int2 nb = nbp[j >> 1];
-              const float p0 = ex2_approx((__uint_as_float(s[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x));
-              const float p1 = ex2_approx((__uint_as_float(s[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y));
-              const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
-              const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-              volatile float* q0 = reinterpret_cast<volatile float*>(dtb + nb.x);
-              *q0 = *q0 + d0;
-              volatile float* q1 = reinterpret_cast<volatile float*>(dtb + nb.y);
-              *q1 = *q1 + d1;
-              pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
-              dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            for (int j = 0; j < 16; j += 2) {
+              const int2 na = nb0[j >> 1], nb = nb1[j >> 1];
+              const float pa0 = ex2_approx((__uint_as_float(s0[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + na.x));
+              const float pb0 = ex2_approx((__uint_as_float(s1[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x));
+              const float pa1 = ex2_approx((__uint_as_float(s0[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + na.y));
+              const float pb1 = ex2_approx((__uint_as_float(s1[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y));
+              const float da0 = pa0 * (__uint_as_float(dp0[j]) - delta_i);
+              const float db0 = pb0 * (__uint_as_float(dp1[j]) - delta_i);
+              const float da1 = pa1 * (__uint_as_float(dp0[j + 1]) - delta_i);
+              const float db1 = pb1 * (__uint_as_float(dp1[j + 1]) - delta_i);
+              volatile float* qa0 = reinterpret_cast<volatile float*>(dtb + na.x);
+              volatile float* qb0 = reinterpret_cast<volatile float*>(dtb + nb.x);
+              const float ta0 = *qa0, tb0 = *qb0;     // loads of both chains first, then both stores
+              *qa0 = ta0 + da0;
+              *qb0 = tb0 + db0;
+              volatile float* qa1 = reinterpret_cast<volatile float*>(dtb + na.y);
+              volatile float* qb1 = reinterpret_cast<volatile float*>(dtb + nb.y);
+              const float ta1 = *qa1, tb1 = *qb1;
+              *qa1 = ta1 + da1;
+              *qb1 = tb1 + db1;
+              pk0[j >> 1] = pack_bf16(pa0, pa1);
+              pk0[8 + (j >> 1)] = pack_bf16(pb0, pb1);
+              dk0[j >> 1] = pack_bf16(da0, da1);
+              dk0[8 + (j >> 1)] = pack_bf16(db0, db1);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int2 nb = nbp[j >> 1];
-              const float x0 = (__uint_as_float(s[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x);
-              const float x1 = (__uint_as_float(s[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y);
-              const float p0 = (k0 + j < key_hi) ? ex2_approx(x0) : 0.f;
-              const float p1 = (k0 + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
-              const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
-              const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-              volatile float* q0 = reinterpret_cast<volatile float*>(dtb + nb.x);
-              *q0 = *q0 + d0;
-              volatile float* q1 = reinterpret_cast<volatile float*>(dtb + nb.y);
-              *q1 = *q1 + d1;
-              pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
-              dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
+            for (int q = 0; q < 2; ++q) {
+              const int kq = q ? k1 : k0;
+              const int2* nbp = q ? nb1 : nb0;
+              const uint32_t* sq = q ? s1 : s0;
+              const uint32_t* dq_ = q ? dp1 : dp0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const int2 nb = nbp[j >> 1];
+                const float x0 = (__uint_as_float(sq[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x);
+                const float x1 = (__uint_as_float(sq[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y);
+                const float p0 = (kq + j < key_hi) ? ex2_approx(x0) : 0.f;
+                const float p1 = (kq + j + 1 < key_hi) ? ex2_approx(x1) : 0.f;
+                const float d0 = p0 * (__uint_as_float(dq_[j]) - delta_i);
+                const float d1 = p1 * (__uint_as_float(dq_[j + 1]) - delta_i);
+                volatile float* q0 = reinterpret_cast<volatile float*>(dtb + nb.x);
+                *q0 = *q0 + d0;
+                volatile float* q1 = reinterpret_cast<volatile float*>(dtb + nb.y);
+                *q1 = *q1 + d1;
+                pk0[q * 8 + (j >> 1)] = pack_bf16(p0, p1);
+                dk0[q * 8 + (j >> 1)] = pack_bf16(d0, d1);
+              }
             }
           }
         } else if (__all_sync(0xffffffffu, k0 + 32 <= key_lo || k0 >= key_hi)) {
           // packed short sequences: this 32-key piece belongs to other sequences for every row of the warp
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[h * 16 + j] = dk[h * 16 + j] = 0u;
+          for (int j = 0; j < 16; ++j) pk0[j] = dk0[j] = 0u;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const int ka = k0 + j;
-            const float p0 = (ka >= key_lo && ka < key_hi) ? ex2_approx(__uint_as_float(s[j]) - lse_i) : 0.f;
-            const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? ex2_approx(__uint_as_float(s[j + 1]) - lse_i) : 0.f;
-            const float d0 = p0 * (__uint_as_float(dp[j]) - delta_i);
-            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta_i);
-            pk[h * 16 + (j >> 1)] = pack_bf16(p0, p1);
-            dk[h * 16 + (j >> 1)] = pack_bf16(d0, d1);
+          for (int q = 0; q < 2; ++q) {
+            const int kq = q ? k1 : k0;
+            const uint32_t* sq = q ? s1 : s0;
+            const uint32_t* dq_ = q ? dp1 : dp0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const int ka = kq + j;
+              const float p0 = (ka >= key_lo && ka < key_hi) ? ex2_approx(__uint_as_float(sq[j]) - lse_i) : 0.f;
+              const float p1 = (ka + 1 >= key_lo && ka + 1 < key_hi) ? ex2_approx(__uint_as_float(sq[j + 1]) - lse_i) : 0.f;
+              const float d0 = p0 * (__uint_as_float(dq_[j]) - delta_i);
+              const float d1 = p1 * (__uint_as_float(dq_[j + 1]) - delta_i);
+              pk0[q * 8 + (j >> 1)] = pack_bf16(p0, p1);
+              dk0[q * 8 + (j >> 1)] = pack_bf16(d0, d1);
+            }
           }
         }
       }
@@ -655,16 +690,19 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         mbar_wait(bars + 2, ph_m);
         ph_m ^= 1;
       }
-      // this thread's 2 x 32 columns of the P / dS tiles (K-major core matrices): half-chunk h, quarter `half`
+      // this thread's 4 x 16 columns of the P / dS tiles (K-major core matrices): half-chunk h, sub-piece q
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int cg = h * 8 + half * 4 + c8;   // 8-column group inside the 128-key chunk
-          *reinterpret_cast<uint4*>(sP + cm_off(rowt, cg, BKC)) =
-              make_uint4(pk[h * 16 + 4 * c8], pk[h * 16 + 4 * c8 + 1], pk[h * 16 + 4 * c8 + 2], pk[h * 16 + 4 * c8 + 3]);
-          *reinterpret_cast<uint4*>(sdS + cm_off(rowt, cg, BKC)) =
-              make_uint4(dk[h * 16 + 4 * c8], dk[h * 16 + 4 * c8 + 1], dk[h * 16 + 4 * c8 + 2], dk[h * 16 + 4 * c8 + 3]);
+        for (int q = 0; q < 2; ++q) {
+          const int colq = h * BKH + (has_bias ? q * 32 + half * 16 : half * 32 + q * 16);
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            const int cg = (colq >> 3) + c8;      // 8-column group inside the 128-key chunk
+            const int w = h * 16 + q * 8 + 4 * c8;
+            *reinterpret_cast<uint4*>(sP + cm_off(rowt, cg, BKC)) = make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
+            *reinterpret_cast<uint4*>(sdS + cm_off(rowt, cg, BKC)) = make_uint4(dk[w], dk[w + 1], dk[w + 2], dk[w + 3]);
+          }
         }
       fence_proxy_async_smem();
       tc_fence_before();

@@ -41,13 +41,14 @@ class LinearFunction(torch.autograd.Function):
     """y = x W^T (bias-free nn.Linear, ct_clip.py:549,564) on the tcgen05 GEMM; fp32 accumulate, fp32 out"""
 
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, x_bf16):
+    def forward(ctx, x, weight, w_bf16, x_bf16, direct=False):
         xb = x_bf16 if x_bf16 is not None else ops.cast_bf16(x.contiguous().float())
         M = xb.shape[0]
         y = torch.zeros((M, weight.shape[0]), device=x.device, dtype=torch.float32)
         ops.gemm(xb, w_bf16, out=y, accumulate=True, splits=0)  # skinny: split-K over the (long) reduction
         ctx.save_for_backward(xb, w_bf16)
         ctx.need = (x.requires_grad, weight.requires_grad)
+        ctx.weight = weight if direct else None
         return y
 
     @staticmethod
@@ -58,8 +59,14 @@ class LinearFunction(torch.autograd.Function):
         if ctx.need[0]:
             dx = ops.gemm(dyb, wb, b_t=True, out_dtype=torch.float32)               # [M, K]
         if ctx.need[1]:
-            dw = ops.gemm(dyb, xb, a_t=True, b_t=True, out_dtype=torch.float32)     # [N, K], reduction over the batch
-        return dx, dw, None, None
+            w = ctx.weight
+            if w is not None and w.grad is not None and w.grad.is_contiguous():
+                # direct mode: accumulate into the parameter's gradient buffer (no 600 MB temporary + add for the
+                # 294912 -> 512 projection); autograd gets None
+                ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, accumulate=True, splits=1)
+            else:
+                dw = ops.gemm(dyb, xb, a_t=True, b_t=True, out_dtype=torch.float32)  # [N, K], reduction over the batch
+        return dx, dw, None, None, None
 
 
 class ClipLossFunction(torch.autograd.Function):
@@ -161,6 +168,8 @@ class CTCLIP(nn.Module):
         self.text_autocast = True   # non-BERT text encoders: run the injected torch module under bf16 autocast
         self.native_text = True     # HF BertModel (what CT-CLIP injects): forward/backward on libctclip_sm100.so
         self._native_text = None
+        # set by CTClipTrainStep: kernels accumulate parameter gradients straight into the existing p.grad buffers
+        self.direct_grad = False
         self._sh_text, self._sh_vis = _Shadow(), _Shadow()
 
     def load(self, path):
@@ -177,6 +186,7 @@ class CTCLIP(nn.Module):
             if self._native_text is None and supports(self.text_transformer):
                 self._native_text = NativeBert(self.text_transformer)
             if self._native_text is not None:   # BERT on the sm_100a kernels (ct_clip.py:685-686)
+                self._native_text.direct_grad = self.direct_grad
                 training = self.training and self.text_transformer.training and torch.is_grad_enabled()
                 return encode(self._native_text, text.input_ids, text.attention_mask, training)
         # any other injected text encoder runs as the torch module it is (library kernels)
@@ -189,13 +199,14 @@ class CTCLIP(nn.Module):
 
     def text_latents_raw(self, enc_text):
         cls = enc_text[:, 0, :].float().contiguous()                                # ct_clip.py:762
-        return LinearFunction.apply(cls, self.to_text_latent.weight, self._sh_text.get(self.to_text_latent.weight), None)
+        return LinearFunction.apply(cls, self.to_text_latent.weight, self._sh_text.get(self.to_text_latent.weight), None,
+                                    self.direct_grad)
 
     def image_latents_raw(self, image):
         vit = self.visual_transformer
         pooled = vit.encode_pooled(image)                                           # ct_clip.py:715,724,740
         return LinearFunction.apply(pooled, self.to_visual_latent.weight, self._sh_vis.get(self.to_visual_latent.weight),
-                                    vit.last_pooled_bf16)
+                                    vit.last_pooled_bf16, self.direct_grad)
 
     # ---------------------------------------------------------------- forward (ct_clip.py:614-901)
     def forward(self, text, image, device=None, return_loss=False, return_encodings=False, return_latents=False,

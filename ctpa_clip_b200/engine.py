@@ -151,13 +151,37 @@ def vq_forward(W: EncoderWeights, tokens, stats=None):
 
 # ------------------------------------------------------------------------------------------------ backward
 class GradStore:
-    """fp32 accumulators in kernel layout, converted to reference parameter shapes at the end"""
+    """fp32 gradient accumulators. Default: fresh zero tensors in kernel layout, converted to reference parameter shapes
+    at the end and handed to autograd. Direct mode (CTClipTrainStep): when the kernel layout IS the parameter layout the
+    accumulator is the parameter's existing .grad (flat arena, zeroed by the optimiser kernel) and autograd gets None."""
 
-    def __init__(self, device):
+    def __init__(self, device, params=None, direct=False):
         self.device = device
         self.g = {}
+        self.params = params or {}
+        self.direct = direct
+
+    def direct_grad(self, name, shape=None):
+        """the parameter's own .grad if direct accumulation is possible for `name` (optionally: in this shape)"""
+        if not self.direct or name not in self.params:
+            return None
+        g = self.params[name].grad
+        if g is None or not g.is_contiguous() or g.dtype != torch.float32:
+            return None
+        if shape is not None and tuple(g.shape) != tuple(shape):
+            return None
+        return g
+
+    def fresh(self, name, shape):
+        """always a new zero tensor (for gradients that are also an INPUT of a later kernel of this backward)"""
+        t = torch.zeros(shape, device=self.device, dtype=torch.float32)
+        self.g[name] = t
+        return t
 
     def zeros(self, name, shape):
+        g = self.direct_grad(name, shape)
+        if g is not None:
+            return g
         t = torch.zeros(shape, device=self.device, dtype=torch.float32)
         self.g[name] = t
         return t
@@ -172,11 +196,17 @@ def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal,
         g_bf = ops.cast_bf16(g)
     # ---- feed-forward (attention.py:44-52)
     du = ops.gemm(g_bf, L.w2p, b_t=True)                                                     # [T, ffp]
-    dw2 = gs.zeros(prefix + "3.4.weight", (dim, L.ffp))
-    ops.gemm(g_bf, c.u, a_t=True, b_t=True, out=dw2, accumulate=True, splits=0)
+    dw2 = gs.direct_grad(prefix + "3.4.weight")
+    if dw2 is not None:   # un-padded [dim, ffi] parameter gradient: the GEMM simply stops at column ffi of u
+        ops.gemm(g_bf, c.u[:, : L.ffi], a_t=True, b_t=True, out=dw2, accumulate=True, splits=0)
+    else:
+        dw2 = gs.zeros(prefix + "3.4.weight", (dim, L.ffp))
+        ops.gemm(g_bf, c.u, a_t=True, b_t=True, out=dw2, accumulate=True, splits=0)
     dh1 = ops.geglu_bwd(c.h1, du)
     dxf = ops.gemm(dh1, L.w1p, b_t=True, out_dtype=torch.float32)                           # [T, dim]
-    dw1 = gs.zeros(prefix + "3.1.weight", (2 * L.ffp, dim))
+    # one GEMM over both padded halves [x rows | gate rows] (two half-size GEMMs into the parameter's own gradient would
+    # read xf twice and fill the SMs worse); un-padded and handed to autograd at the end
+    dw1 = gs.fresh(prefix + "3.1.weight", (2 * L.ffp, dim))
     ops.gemm(dh1, c.xf, a_t=True, b_t=True, out=dw1, accumulate=True, splits=0)
     dg = gs.zeros(prefix + "3.0.weight", (dim,))
     db = gs.zeros(prefix + "3.0.bias", (dim,))
@@ -210,7 +240,7 @@ def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
     """backward of encoder_forward; g_tokens = dL/d(tokens) fp32 [T, dim]. Returns {reference param name: grad}."""
     dim = W.dim
     dev = g_tokens.device
-    gs = GradStore(dev)
+    gs = GradStore(dev, params=dict(vit.named_parameters()), direct=getattr(vit, "direct_grad", False))
     grid = ctx.grid
     v = ""
     # temporal transformer
@@ -232,9 +262,9 @@ def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
     dg2 = gs.zeros("to_patch_emb.3.weight", (dim,))
     db2 = gs.zeros("to_patch_emb.3.bias", (dim,))
     dy0, dy0_bf = ops.layernorm_bwd(g, y0, W.pe_g2, dgamma=dg2, dbeta=db2, want_bf16=True)
-    dbias = gs.zeros("to_patch_emb.2.bias", (dim,))
+    dbias = gs.fresh("to_patch_emb.2.bias", (dim,))
     ops.colsum(dy0, dbias)
-    dwp = gs.zeros("to_patch_emb.2.weight", (dim, a.shape[1]))
+    dwp = gs.fresh("to_patch_emb.2.weight", (dim, a.shape[1]))   # this step's dW alone feeds patch_ln_param_grad below
     ops.gemm(dy0_bf, a, a_t=True, b_t=True, out=dwp, accumulate=True, splits=0)
     dg1 = gs.zeros("to_patch_emb.1.weight", (W.pdim,))
     db1 = gs.zeros("to_patch_emb.1.bias", (W.pdim,))

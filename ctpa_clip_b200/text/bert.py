@@ -48,6 +48,9 @@ class NativeBert:
         self.vocab = cfg.vocab_size
         self._key, self._layers = None, None
         self.calls = 0
+        # True (set by CTClipTrainStep): the kernels accumulate parameter gradients straight into the existing p.grad
+        # buffers (flat gradient arena, zeroed by the optimiser kernel) and autograd gets None for them
+        self.direct_grad = False
         # parameters in a fixed order (the autograd.Function takes them as inputs and returns their gradients)
         emb = module.embeddings
         self.names, self.params = [], []
@@ -164,17 +167,23 @@ class NativeBert:
         T = B * L
         dev = g_out.device
         grads = [None] * len(self.params)
+        direct = self.direct_grad
 
-        def put(name, g):
-            grads[self.index[name]] = g
+        def target(name):
+            """fp32 accumulator for the gradient of parameter `name`: p.grad itself in direct mode, else a fresh zero
+            tensor that is handed to autograd"""
+            i = self.index[name]
+            pg = self.params[i].grad
+            if direct and pg is not None and pg.is_contiguous() and pg.dtype == torch.float32:
+                return pg
+            t = torch.zeros(self.params[i].shape, device=dev, dtype=torch.float32)
+            grads[i] = t
+            return t
 
-        def zeros(*shape):
-            return torch.zeros(shape, device=dev, dtype=torch.float32)
-
-        def wgrad(dy_bf, x_bf, n_out, n_in):
-            dw = zeros(n_out, n_in)
-            ops.gemm(dy_bf, x_bf, a_t=True, b_t=True, out=dw, accumulate=True, splits=0, tag=f"bert_wgrad:{n_out}x{n_in}x{T}")
-            return dw
+        def wgrad(name, dy_bf, x_bf):
+            dw = target(name)
+            ops.gemm(dy_bf, x_bf, a_t=True, b_t=True, out=dw, accumulate=True, splits=0,
+                     tag=f"bert_wgrad:{dw.shape[0]}x{dw.shape[1]}x{T}")
 
         scale = 1.0 / math.sqrt(hd)
         g = g_out.reshape(T, D).contiguous().float()
@@ -184,43 +193,34 @@ class NativeBert:
             sd = c["sd"]
             pfx = f"encoder.layer.{li}."
             # ---- BertOutput: LayerNorm(dropout(dense(a)) + x1)
-            dg, db = zeros(D), zeros(D)
-            dpre2, dpre2_b = ops.layernorm_bwd(g, c["pre2"], w.g2, eps=self.eps, dgamma=dg, dbeta=db, want_bf16=(ph == 0))
-            put(pfx + "output.LayerNorm.weight", dg)
-            put(pfx + "output.LayerNorm.bias", db)
+            dpre2, dpre2_b = ops.layernorm_bwd(g, c["pre2"], w.g2, eps=self.eps, dgamma=target(pfx + "output.LayerNorm.weight"),
+                                               dbeta=target(pfx + "output.LayerNorm.bias"), want_bf16=(ph == 0))
             if ph > 0:
                 dy = ops.dropout_add(dpre2, None, ph, sd + 3)
                 dy_b = ops.cast_bf16(dy)
             else:
                 dy, dy_b = dpre2, dpre2_b
-            db2 = zeros(D)
-            ops.colsum(dy, db2)
-            put(pfx + "output.dense.bias", db2)
-            put(pfx + "output.dense.weight", wgrad(dy_b, c["a"], D, I))
+            ops.colsum(dy, target(pfx + "output.dense.bias"))
+            wgrad(pfx + "output.dense.weight", dy_b, c["a"])
             da = ops.gemm(dy_b, w.w2, b_t=True, tag=f"bert_dgrad:{T}x{I}x{D}")
             # ---- BertIntermediate: gelu(dense(x1))
             dh = ops.gelu_bwd(c["h"], da)
-            db1 = zeros(I)
-            ops.colsum_bf16(dh, db1)
-            put(pfx + "intermediate.dense.bias", db1)
-            put(pfx + "intermediate.dense.weight", wgrad(dh, c["x1b"], I, D))
+            ops.colsum_bf16(dh, target(pfx + "intermediate.dense.bias"))
+            wgrad(pfx + "intermediate.dense.weight", dh, c["x1b"])
             # x1 feeds the FFN and, as the residual, pre2: its gradient is the FFN data gradient + dpre2 (GEMM epilogue)
             dx1 = ops.gemm(dh, w.w1, b_t=True, out_dtype=torch.float32, resid=dpre2, tag=f"bert_dgrad:{T}x{D}x{I}")
             del dh, da
             # ---- BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)
-            dg, db = zeros(D), zeros(D)
-            dpre1, dpre1_b = ops.layernorm_bwd(dx1, c["pre1"], w.g1, eps=self.eps, dgamma=dg, dbeta=db, want_bf16=(ph == 0))
-            put(pfx + "attention.output.LayerNorm.weight", dg)
-            put(pfx + "attention.output.LayerNorm.bias", db)
+            dpre1, dpre1_b = ops.layernorm_bwd(dx1, c["pre1"], w.g1, eps=self.eps,
+                                               dgamma=target(pfx + "attention.output.LayerNorm.weight"),
+                                               dbeta=target(pfx + "attention.output.LayerNorm.bias"), want_bf16=(ph == 0))
             if ph > 0:
                 dao = ops.dropout_add(dpre1, None, ph, sd + 2)
                 dao_b = ops.cast_bf16(dao)
             else:
                 dao, dao_b = dpre1, dpre1_b
-            dbo = zeros(D)
-            ops.colsum(dao, dbo)
-            put(pfx + "attention.output.dense.bias", dbo)
-            put(pfx + "attention.output.dense.weight", wgrad(dao_b, c["cv"], D, D))
+            ops.colsum(dao, target(pfx + "attention.output.dense.bias"))
+            wgrad(pfx + "attention.output.dense.weight", dao_b, c["cv"])
             dcv = ops.gemm(dao_b, w.wo, b_t=True, tag=f"bert_dgrad:{T}x{D}x{D}")
             # ---- BertSelfAttention
             qkv, P, Pd = c["qkv"], c["P"], c["Pd"]
@@ -248,30 +248,21 @@ class NativeBert:
                                  dbase + 2 * D, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
             ops.run_gemm_desc(d, False, f"bert_dk:{B}x{H}x{L}x{hd}x{L}", fl)
             del dS
-            dbqkv = zeros(3 * D)
-            ops.colsum_bf16(dqkv, dbqkv)
-            dwqkv = wgrad(dqkv, c["xb"], 3 * D, D)
-            for j, nm in enumerate(("query", "key", "value")):
-                put(pfx + f"attention.self.{nm}.weight", dwqkv[j * D:(j + 1) * D])
-                put(pfx + f"attention.self.{nm}.bias", dbqkv[j * D:(j + 1) * D])
+            for j, nm in enumerate(("query", "key", "value")):   # the three projections are separate parameters
+                dslice = dqkv[:, j * D:(j + 1) * D]                # column slice of the packed gradient (row pitch 3D)
+                ops.colsum_bf16(dslice, target(pfx + f"attention.self.{nm}.bias"), dim=D, ld=3 * D)
+                wgrad(pfx + f"attention.self.{nm}.weight", dslice, c["xb"])
             g = ops.gemm(dqkv, w.wqkv, b_t=True, out_dtype=torch.float32, resid=dpre1, tag=f"bert_dgrad:{T}x{D}x{3 * D}")
             ctx["layers"][li] = None
         # ---- embeddings: LayerNorm(word + pos + type) (+ dropout)
         emb = self.m.embeddings
         if ph > 0:
             g = ops.dropout_add(g, None, ph, ctx["seed0"])
-        dg, db = zeros(D), zeros(D)
-        dpre0, _ = ops.layernorm_bwd(g, ctx["pre0"], emb.LayerNorm.weight.detach(), eps=self.eps, dgamma=dg, dbeta=db)
-        put("embeddings.LayerNorm.weight", dg)
-        put("embeddings.LayerNorm.bias", db)
-        dword = zeros(*emb.word_embeddings.weight.shape)
-        dpos = zeros(*emb.position_embeddings.weight.shape)
-        ops.bert_embed_bwd(ctx["ids"].reshape(-1), L, dpre0, dword, dpos, emb.word_embeddings.padding_idx)
-        dtype_ = zeros(*emb.token_type_embeddings.weight.shape)
-        ops.colsum(dpre0, dtype_[0])
-        put("embeddings.word_embeddings.weight", dword)
-        put("embeddings.position_embeddings.weight", dpos)
-        put("embeddings.token_type_embeddings.weight", dtype_)
+        dpre0, _ = ops.layernorm_bwd(g, ctx["pre0"], emb.LayerNorm.weight.detach(), eps=self.eps,
+                                     dgamma=target("embeddings.LayerNorm.weight"), dbeta=target("embeddings.LayerNorm.bias"))
+        ops.bert_embed_bwd(ctx["ids"].reshape(-1), L, dpre0, target("embeddings.word_embeddings.weight"),
+                           target("embeddings.position_embeddings.weight"), emb.word_embeddings.padding_idx)
+        ops.colsum(dpre0, target("embeddings.token_type_embeddings.weight")[0])
         return grads
 
 

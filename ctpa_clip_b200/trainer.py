@@ -54,6 +54,9 @@ class CTClipTrainStep:
         self.model = model
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
         self.arena = ParamArena(model)
+        # every trainable parameter now owns a zeroed .grad view of the flat arena: let the kernels accumulate into it
+        model.direct_grad = True
+        model.visual_transformer.direct_grad = True
         self.step_count = 0
         self.bucket = bucket_elems
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1

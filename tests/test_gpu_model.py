@@ -148,3 +148,28 @@ def test_zero_shot_scores_match_reference_calling_pattern():
         want = O.zero_shot_scores(tl, il, sdc["temperature"])
     assert got.shape == (4, 3)
     assert torch.allclose(got, want, atol=3e-2)
+
+
+def test_direct_gradient_accumulation_equals_autograd_accumulation():
+    """CTClipTrainStep lets the kernels accumulate parameter gradients straight into the flat arena (p.grad views) instead
+    of returning fresh tensors to autograd: both routes must give the same gradients (same kernels; only the order of the
+    fp32 atomics differs)."""
+    from ctpa_clip_b200.trainer import CTClipTrainStep, trainable_parameters
+    cfg = O.MID
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, 3, 5)
+    m1 = build(cfg, sd, O.make_text_encoder(cfg, 0))
+    tr = CTClipTrainStep(m1)
+    assert m1.direct_grad and m1.visual_transformer.direct_grad
+    tr.forward_backward(text_of(ids, mask), video.cuda())
+    m2 = build(cfg, sd, O.make_text_encoder(cfg, 0)).train()
+    m2(text_of(ids, mask), video.cuda(), return_loss=True).backward()
+    g2 = dict(trainable_parameters(m2))
+    checked = 0
+    for n, p in trainable_parameters(m1):
+        a, b = p.grad, g2[n].grad
+        assert b is not None, n
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 2e-3 * scale + 1e-7, n
+        checked += 1
+    assert checked > 100
