@@ -88,6 +88,21 @@ class NativeBert:
     def invalidate(self):
         self._key = None
 
+    def _packed_qkv_grad(self, pfx):
+        """([3D, D] weight-gradient view, [3D] bias-gradient view) when the q / k / v .grad buffers of this layer sit back
+        to back in memory (trainer.ParamArena lays them out that way), else None"""
+        D = self.D
+        ws = [self.params[self.index[pfx + f"attention.self.{m}.weight"]].grad for m in ("query", "key", "value")]
+        bs = [self.params[self.index[pfx + f"attention.self.{m}.bias"]].grad for m in ("query", "key", "value")]
+        if any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in ws + bs):
+            return None
+        if not (ws[1].data_ptr() == ws[0].data_ptr() + 4 * D * D and ws[2].data_ptr() == ws[1].data_ptr() + 4 * D * D and
+                bs[1].data_ptr() == bs[0].data_ptr() + 4 * D and bs[2].data_ptr() == bs[1].data_ptr() + 4 * D):
+            return None
+        if ws[0].untyped_storage().data_ptr() != ws[2].untyped_storage().data_ptr():
+            return None
+        return ws[0].as_strided((3 * D, D), (D, 1)), bs[0].as_strided((3 * D,), (1,))
+
     # ------------------------------------------------------------------------------------------ attention products
     def _scores(self, qkv, B, L):
         """S[b,h] = Q_bh K_bh^T  (fp32 [B,H,L,L])"""
@@ -248,10 +263,17 @@ class NativeBert:
                                  dbase + 2 * D, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
             ops.run_gemm_desc(d, False, f"bert_dk:{B}x{H}x{L}x{hd}x{L}", fl)
             del dS
-            for j, nm in enumerate(("query", "key", "value")):   # the three projections are separate parameters
-                dslice = dqkv[:, j * D:(j + 1) * D]                # column slice of the packed gradient (row pitch 3D)
-                ops.colsum_bf16(dslice, target(pfx + f"attention.self.{nm}.bias"), dim=D, ld=3 * D)
-                wgrad(pfx + f"attention.self.{nm}.weight", dslice, c["xb"])
+            packed = self._packed_qkv_grad(pfx) if direct else None
+            if packed is not None:   # q / k / v gradients are adjacent in the arena: one wgrad GEMM, one column sum
+                dw3, db3 = packed
+                ops.colsum_bf16(dqkv, db3)
+                ops.gemm(dqkv, c["xb"], a_t=True, b_t=True, out=dw3, accumulate=True, splits=0,
+                         tag=f"bert_wgrad:{3 * D}x{D}x{T}")
+            else:
+                for j, nm in enumerate(("query", "key", "value")):   # the three projections are separate parameters
+                    dslice = dqkv[:, j * D:(j + 1) * D]                # column slice of the packed gradient (row pitch 3D)
+                    ops.colsum_bf16(dslice, target(pfx + f"attention.self.{nm}.bias"), dim=D, ld=3 * D)
+                    wgrad(pfx + f"attention.self.{nm}.weight", dslice, c["xb"])
             g = ops.gemm(dqkv, w.wqkv, b_t=True, out_dtype=torch.float32, resid=dpre1, tag=f"bert_dgrad:{T}x{D}x{3 * D}")
             ctx["layers"][li] = None
         # ---- embeddings: LayerNorm(word + pos + type) (+ dropout)

@@ -23,9 +23,31 @@ def trainable_parameters(module):
             if p.requires_grad and p.numel() > 0 and not any(m in n for m in UNUSED_PARAM_MARKERS)]
 
 
+def _arena_order(named):
+    """parameter order inside the arena: as named_parameters(), except that the query / key / value projections of a BERT
+    self-attention are laid out back to back (weights, then biases), so that the packed [3*hidden, hidden] QKV weight
+    gradient of the native text tower is ONE contiguous view of the gradient arena"""
+    by_name = dict(named)
+    out, done = [], set()
+    for n, p in named:
+        if n in done:
+            continue
+        if n.endswith("attention.self.query.weight"):
+            base = n[: -len("query.weight")]
+            group = [base + f"{m}.{k}" for k in ("weight", "bias") for m in ("query", "key", "value")]
+            if all(g in by_name for g in group):
+                for g in group:
+                    out.append(by_name[g])
+                    done.add(g)
+                continue
+        out.append(p)
+        done.add(n)
+    return out
+
+
 class ParamArena:
     def __init__(self, module: torch.nn.Module):
-        params = [p for _, p in trainable_parameters(module)]
+        params = _arena_order(trainable_parameters(module))
         self.params = params
         dev = params[0].device
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]

@@ -62,6 +62,15 @@ gemm_case("ff1_dgrad_Tx512x2736", T, 512, 2736, b_t=True, f32=True)
 gemm_case("ff1_wgrad_2736x512xT", 2736, 512, T, a_t=True, b_t=True, accumulate=True)
 gemm_case("vq_scores_Tx8192x512", T, 8192, 512)
 gemm_case("square_8192", 8192, 8192, 8192)
+# memory-bound projections: fp32 output added in place to the fp32 residual stream (out-proj, attention.py:181 + :326)
+qo = torch.randn(T, 256, device=dev).bfloat16(); wo = torch.randn(512, 256, device=dev).bfloat16(); xr = torch.randn(T, 512, device=dev)
+ms = timeit(lambda: ops.gemm(qo, wo, out=xr, resid=xr), iters=20)
+byts = T * 256 * 2 + 2 * T * 512 * 4
+out["gemm_outproj_resid_Tx512x256"] = {"ms": ms, "algorithmic_GBps": byts / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+xk = torch.randn(T, 512, device=dev).bfloat16(); wk = torch.randn(512, 512, device=dev).bfloat16()
+ms = timeit(lambda: ops.gemm(xk, wk), iters=20)
+byts = 2 * T * 512 * 2
+out["gemm_kv_Tx512x512_bf16"] = {"ms": ms, "algorithmic_GBps": byts / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 x = torch.randn(T, 512, device=dev)
 w27 = torch.randn(27, 512, device=dev); bias = torch.randn(512, device=dev)
 ms = timeit(lambda: ops.peg_fwd(x, w27, bias, (8, 24, 24, 24), False))
@@ -73,6 +82,26 @@ vid = torch.rand(8, 1, 240, 480, 480, device=dev)
 g4, b4 = torch.ones(4000, device=dev), torch.zeros(4000, device=dev)
 ms = timeit(lambda: ops.patch_ln_fwd(vid, g4, b4, 10, 20), iters=5)
 out["patch_ln_fwd"] = {"ms": ms, "algorithmic_GBps": (vid.numel() * 4 + T * 4000 * 2) / (ms * 1e-3) / 1e9}
+# ---- config 5: zero-shot scoring, one GPU's share (32 of the 256 volumes) x 18 pathologies x 2 prompts
+del vid
+torch.cuda.empty_cache()
+sys.argv = sys.argv[:1]
+import bench
+from transformers import BatchEncoding
+from oracle import ctclip_oracle as O   # configs only
+cfg = O.CONFIGS["production"]
+model = bench.build_model(cfg, torch.device("cuda"), seed=0).eval()
+vols = torch.rand(32, 1, 240, 480, 480, device=dev) * 2 - 1
+gq = torch.Generator().manual_seed(5)
+pid = torch.randint(1, 30522, (36, 512), generator=gq); pmask = torch.ones(36, 512, dtype=torch.long)
+pid[:, 32:] = 0; pmask[:, 32:] = 0
+prompts = BatchEncoding({"input_ids": pid.to(dev), "attention_mask": pmask.to(dev)})
+def zs():
+    outs = [model.zero_shot_scores(prompts, vols[i:i + 8]) for i in range(0, 32, 8)]
+    return torch.cat(outs)
+ms = timeit(zs, iters=3, warm=1)
+out["zero_shot_32vol_x_18path"] = {"ms": ms, "volumes_per_s": 32 / (ms * 1e-3), "scores_shape": list(zs().shape),
+                                   "note": "image encoder once per volume (reference: 18x), text latents recomputed per 8-volume chunk"}
 for k, v in out.items():
     print(k, json.dumps(v))
 json.dump(out, open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/components.json", "w"), indent=1)
