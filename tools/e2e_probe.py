@@ -27,9 +27,11 @@ def run(copies, sync, steps=6):
             copy_stream.wait_event(consumed[i % 2])
             bufs[i % 2].copy_(host[i % 2], non_blocking=True)
             ready[i % 2].record(copy_stream)
-    def step(i):
+    k = [0]
+    if copies: prefetch(0)
+    def step(_):
+        i = k[0]; k[0] += 1
         if copies:
-            if i == 0: prefetch(0)
             prefetch(i + 1)
             torch.cuda.current_stream().wait_event(ready[i % 2])
             loss = tr.step(text, bufs[i % 2])
