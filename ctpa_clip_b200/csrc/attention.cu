@@ -88,6 +88,23 @@ __device__ __forceinline__ float load_head_row(const __nv_bfloat16* src, float (
   return 1.f / fmaxf(sqrtf(ss), 1e-12f);
 }
 
+// unpack a raw 32-wide bf16 head row held in registers, return fp32 values and the inverse l2 norm
+__device__ __forceinline__ float unpack_head_row(const uint4 (&raw)[4], float (&v)[DH]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[8 * j + 2 * k] = bf16_lo(w[k]);
+      v[8 * j + 2 * k + 1] = bf16_hi(w[k]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DH; ++j) ss = fmaf(v[j], v[j], ss);
+  return 1.f / fmaxf(sqrtf(ss), 1e-12f);
+}
+
 __device__ __forceinline__ void store_row_cm(uint8_t* tile, int r, const float (&v)[DH]) {
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
@@ -170,8 +187,24 @@ attn_fwd_kernel(const AttnParams p) {
   constexpr uint32_t idesc_o = make_idesc_bf16(QT, DH, false, true);
   uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
 
+  // raw Q row of a tile (half 0 threads), loaded one tile ahead so that its global latency hides behind the key loop
+  uint4 qraw[4];
+  bool qvalid = false;
+  long long qtok = 0;
+  auto load_q_row = [&](int blk_, int tile_) {
+    const int r_ = tile_ * QT + rowt;
+    qvalid = false;
+    qtok = (r_ < R) ? row_token(p, blk_, r_, qvalid) : 0;
+    if (half == 0 && qvalid) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.q + qtok * p.ldq + head * DH);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qraw[j] = src[j];
+    }
+  };
+
   // persistent over the sequence blocks of this head: tables, barriers and TMEM are set up once per CTA
   for (int blk = blockIdx.x / p.heads; blk < p.num_blocks; blk += gridDim.x / p.heads) {
+  load_q_row(blk, 0);   // in flight together with the K / V rows below
   // ---- K^ and V for the whole block (every MMA of the previous block has retired: its last tile waited bars + 2)
   for (int r = tid; r < kv_rows; r += blockDim.x) {
     bool valid = false;
@@ -196,12 +229,12 @@ attn_fwd_kernel(const AttnParams p) {
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int r = tile * QT + rowt;
-    bool valid = false;
-    const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
+    const bool valid = qvalid;
+    const long long tok = qtok;
     if (half == 0) {
       if (valid) {
         float v[DH];
-        const float inv = load_head_row(p.q + tok * p.ldq + head * DH, v);
+        const float inv = unpack_head_row(qraw, v);
 #pragma unroll
         for (int d = 0; d < DH; ++d) v[d] *= inv * sScale[d];
         store_row_cm(sQ, rowt, v);
@@ -209,6 +242,7 @@ attn_fwd_kernel(const AttnParams p) {
         store_zero_row_cm(sQ, rowt);
       }
     }
+    if (tile + 1 < ntiles) load_q_row(blk, tile + 1);   // next tile's row: consumed after this tile's key loop
     const int my_seq = r / p.nst;
     const int my_pos = r - my_seq * p.nst;
     const int key_lo = my_seq * p.nst, key_hi = min(R, key_lo + p.n);   // keys of this row's own sequence
