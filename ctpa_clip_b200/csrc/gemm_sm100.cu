@@ -17,6 +17,7 @@
 // Tile 128 x BN x 64, SWIZZLE_128B operand tiles, 2 accumulator buffers (2*BN TMEM columns).
 #include "ptx.cuh"
 #include "ctclip_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -27,11 +28,11 @@ constexpr int BK = 64;
 constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
 constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant, each owning half of the tile's columns
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && !PAIR) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA of a pair stages half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStageOut = kStages * kStageBytes;             // epilogue warps x 32 rows x 128 B staging
   static constexpr int kBarOffset = kStageOut + kEpiWarps * 32 * 128;
@@ -249,11 +250,16 @@ __device__ __forceinline__ void epi_store_f32x32(const GemmKernelParams& p, uint
 }
 
 // ---------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN>
+// PAIR: two CTAs of a cluster (same TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2 — CTA r owns rows
+// [128 r, 128 r + 128) of A and of the accumulator and stages HALF of the B tile (rows [BN/2 r, ...)), which cuts the
+// shared-memory fill per k-block from 48 KB to 32 KB (6 stages instead of 4). Only the leader issues MMAs; both CTAs' TMA
+// loads are counted on the leader's full barriers, MMA completion is multicast to both CTAs' empty / accumulator-full
+// barriers, and both epilogues release the accumulator on the leader's barrier.
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -265,7 +271,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_work = p.m_tiles * p.n_tiles * p.splits * (p.z_n > 1 ? p.z_n : 1);
+  // work units: (problem | split, m unit, n tile), n fastest. In PAIR mode an m unit is two m tiles (one per CTA) and the
+  // two CTAs of a cluster walk the same unit sequence.
+  const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int num_work = m_units * p.n_tiles * p.splits * (p.z_n > 1 ? p.z_n : 1);
+  const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m = [&](int w) { const int mu = (w / p.n_tiles) % m_units; return PAIR ? 2 * mu + cta_rank : mu; };
+  auto tile_zs = [&](int w) { return w / (p.n_tiles * m_units); };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -278,16 +292,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, kEpiWarps);
+      mbar_init(tmem_empty + a, PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogues release on the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, 2 * BN);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -296,24 +315,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = w_first; w < num_work; w += w_stride) {
         const int n_t = w % p.n_tiles;
-        const int m_t = (w / p.n_tiles) % p.m_tiles;
-        const int zs = w / (p.n_tiles * p.m_tiles);      // split index, or problem index in batched mode
+        const int m_t = tile_m(w);
+        const int zs = tile_zs(w);                        // split index, or problem index in batched mode
         const int sp = p.z_n > 1 ? 0 : zs;
         const int zh = p.z_n > 1 ? zs % p.zh_n : 0, zb = p.z_n > 1 ? zs / p.zh_n : 0;
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         // operand tiles: coordinates (contiguous, row) plus the (head, batch) pair of the problem
         auto load = [&](uint8_t* dst, const CUtensorMap* m, int hpos, int c0, int crow) {
-          if (hpos == 1) tma_load_4d(dst, m, full_bar + stage, c0, zh, crow, zb);
-          else tma_load_4d(dst, m, full_bar + stage, c0, crow, zh, zb);
+          if constexpr (PAIR) {   // bytes are counted on the leader's full barrier
+            if (hpos == 1) tma_load_4d_pair(dst, m, full_bar + stage, c0, zh, crow, zb);
+            else tma_load_4d_pair(dst, m, full_bar + stage, c0, crow, zh, zb);
+          } else {
+            if (hpos == 1) tma_load_4d(dst, m, full_bar + stage, c0, zh, crow, zb);
+            else tma_load_4d(dst, m, full_bar + stage, c0, crow, zh, zb);
+          }
         };
+        constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows this CTA stages
+        const int b_row0 = n_t * BN + (PAIR ? cta_rank * kBRows : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(full_bar + stage, L::kStageBytes);
+          if constexpr (PAIR) {
+            if (cta_rank == 0) mbar_expect_tx(full_bar + stage, 2 * L::kStageBytes);   // leader: both CTAs' bytes
+          } else {
+            mbar_expect_tx(full_bar + stage, L::kStageBytes);
+          }
           if constexpr (!A_MN) {
             load(sa, &tmap_a, p.a_hpos, kb * BK, m_t * BM);
           } else {
@@ -321,25 +351,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmap_a, p.a_hpos, m_t * BM + j * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            load(sb, &tmap_b, p.b_hpos, kb * BK, n_t * BN);
+            load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) load(sb + j * (BK * 128), &tmap_b, p.b_hpos, n_t * BN + j * 64, kb * BK);
+            for (int j = 0; j < kBRows / 64; ++j) load(sb + j * (BK * 128), &tmap_b, p.b_hpos, b_row0 + j * 64, kb * BK);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int sp = p.z_n > 1 ? 0 : w / (p.n_tiles * p.m_tiles);
+      for (int w = w_first; w < num_work; w += w_stride) {
+        const int sp = p.z_n > 1 ? 0 : tile_zs(w);
         const int kb0 = sp * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -359,12 +389,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                      : make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) mma_f16_ss_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else mma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) mma_commit_pair(empty_bar + stage); else mma_commit(empty_bar + stage);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(tmem_full + acc);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue(s)
+        if constexpr (PAIR) mma_commit_pair(tmem_full + acc); else mma_commit(tmem_full + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -376,7 +409,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       auto prefetch_tile = [&](int wn) {
         if (wn >= num_work) return;
         const int n_t = wn % p.n_tiles;
-        const int m_t = (wn / p.n_tiles) % p.m_tiles;
+        const int m_t = tile_m(wn);
         const int cols = min(BN, p.N - n_t * BN);
         const int lines = (cols * 4 + 127) / 128;            // 128-byte lines per tile row
         for (int i = lane; i < BM * lines; i += 32) {
@@ -387,10 +420,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       };
       int acc = 0;
       uint32_t acc_phase = 0;
-      prefetch_tile(blockIdx.x);
-      prefetch_tile(blockIdx.x + gridDim.x);
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        prefetch_tile(w + 2 * gridDim.x);        // two tiles of lead: a short-K tile is over in ~1 us
+      prefetch_tile(w_first);
+      prefetch_tile(w_first + w_stride);
+      for (int w = w_first; w < num_work; w += w_stride) {
+        prefetch_tile(w + 2 * w_stride);        // two tiles of lead: a short-K tile is over in ~1 us
         mbar_wait_bounded(tmem_full + acc, acc_phase, 1u << 16);   // observe only: the epilogue warps own the hand-shake
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -414,11 +447,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     GemmKernelParams pz = p;   // per-problem view: C shifted to the (head, batch) slice in batched mode
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = w_first; w < num_work; w += w_stride) {
       const int n_t = w % p.n_tiles;
-      const int m_t = (w / p.n_tiles) % p.m_tiles;
+      const int m_t = tile_m(w);
       if (p.z_n > 1) {
-        const int zs = w / (p.n_tiles * p.m_tiles);
+        const int zs = tile_zs(w);
         const long long off = (long long)(zs % p.zh_n) * p.c_stride_h + (long long)(zs / p.zh_n) * p.c_stride_b;
         pz.C = p.c_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.C) + off)
                           : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
@@ -505,16 +538,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(tmem_empty + acc); else mbar_arrive(tmem_empty + acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem / TMEM stay alive until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -548,20 +583,45 @@ int encode_operand_map(CUtensorMap* map, int* hpos, const void* ptr, bool mn_maj
                              estr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 int launch(const ctclip_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta, const CUtensorMap& tb,
            int grid, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  using L = SmemLayout<BN, PAIR>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, PAIR>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, kp);
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, kp);
+    if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "gemm (CTA pair) launch: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, kp);
+  }
   (void)d;
   return ctclip::check_launch("gemm launch");
+}
+
+// CTA-pair mode is used for the wide (BN = 256) tiles unless CTCLIP_GEMM_PAIR=0
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CTCLIP_GEMM_PAIR");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -628,26 +688,42 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
     if ((d->a_stride_h % 8) || (d->a_stride_b % 8) || (d->b_stride_h % 8) || (d->b_stride_b % 8))
       return ctclip::fail(CTCLIP_E_ALIGN, "gemm: batch strides must be multiples of 8 elements");
   }
+  // CTA pairs pay off where the tensor pipe is the limit: deep enough K, enough tiles to fill every pair, plain epilogues
+  const bool pair = BN == 256 && pair_enabled() && kp.m_tiles >= 2 && d->K >= 512 &&
+                    (long long)tiles * kp.splits * kp.z_n >= sms && kp.top2 == nullptr;
   CUtensorMap ta, tb;
   rc = encode_operand_map(&ta, &kp.a_hpos, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM, zh_n, zb_n, d->a_stride_h,
                           d->a_stride_b);
   if (rc) return rc;
-  rc = encode_operand_map(&tb, &kp.b_hpos, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, BN, zh_n, zb_n, d->b_stride_h,
-                          d->b_stride_b);
+  rc = encode_operand_map(&tb, &kp.b_hpos, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, pair ? BN / 2 : BN, zh_n, zb_n,
+                          d->b_stride_h, d->b_stride_b);
   if (rc) return rc;
 
+  if (pair) {
+    const int units = ((kp.m_tiles + 1) / 2) * kp.n_tiles * kp.splits * kp.z_n;
+    int clusters = sms / 2;
+    if (clusters > units) clusters = units;
+    const int grid = 2 * clusters;
+    const int sel = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+    switch (sel) {
+      case 0: return launch<256, false, false, true>(d, kp, ta, tb, grid, stream);
+      case 1: return launch<256, false, true, true>(d, kp, ta, tb, grid, stream);
+      case 2: return launch<256, true, false, true>(d, kp, ta, tb, grid, stream);
+      default: return launch<256, true, true, true>(d, kp, ta, tb, grid, stream);
+    }
+  }
   const int num_work = tiles * kp.splits * kp.z_n;
   const int grid = num_work < sms ? num_work : sms;
   const int sel = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   switch (sel) {
-    case 0: return launch<128, false, false>(d, kp, ta, tb, grid, stream);
-    case 1: return launch<128, false, true>(d, kp, ta, tb, grid, stream);
-    case 2: return launch<128, true, false>(d, kp, ta, tb, grid, stream);
-    case 3: return launch<128, true, true>(d, kp, ta, tb, grid, stream);
-    case 4: return launch<256, false, false>(d, kp, ta, tb, grid, stream);
-    case 5: return launch<256, false, true>(d, kp, ta, tb, grid, stream);
-    case 6: return launch<256, true, false>(d, kp, ta, tb, grid, stream);
-    default: return launch<256, true, true>(d, kp, ta, tb, grid, stream);
+    case 0: return launch<128, false, false, false>(d, kp, ta, tb, grid, stream);
+    case 1: return launch<128, false, true, false>(d, kp, ta, tb, grid, stream);
+    case 2: return launch<128, true, false, false>(d, kp, ta, tb, grid, stream);
+    case 3: return launch<128, true, true, false>(d, kp, ta, tb, grid, stream);
+    case 4: return launch<256, false, false, false>(d, kp, ta, tb, grid, stream);
+    case 5: return launch<256, false, true, false>(d, kp, ta, tb, grid, stream);
+    case 6: return launch<256, true, false, false>(d, kp, ta, tb, grid, stream);
+    default: return launch<256, true, true, false>(d, kp, ta, tb, grid, stream);
   }
 }
 
