@@ -64,6 +64,28 @@ def test_gemm_epilogues_and_split_k(ops):
     close(out, dy.float().t() @ xx.float() + 1, 1e-4)
 
 
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+@pytest.mark.parametrize("shape", [(3104, 1544, 576), (3208, 1304, 640)])
+def test_gemm_cta_pair_layouts(ops, a_t, b_t, shape):
+    """shapes that take the tcgen05.mma.cta_group::2 path (K >= 512, >= 148 tiles): odd number of m tiles (the second CTA
+    of the last pair owns a phantom tile), ragged last m tile (8 valid rows) and ragged n tile; every operand layout;
+    fp32 + bias + residual, bf16 and split-K atomic epilogues"""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t()
+    a_op, b_op = (A.t().contiguous() if a_t else A), (B.t().contiguous() if b_t else B)
+    close(ops.gemm(a_op, b_op, a_t=a_t, b_t=b_t, out_dtype=torch.float32, bias=bias, resid=resid), ref + bias + resid, 2e-5)
+    close(ops.gemm(a_op, b_op, a_t=a_t, b_t=b_t), ref, 1e-2)
+    out = torch.ones(M, N, device="cuda")
+    ops.gemm(a_op, b_op, a_t=a_t, b_t=b_t, out=out, accumulate=True, splits=3)
+    close(out, ref + 1, 1e-4)
+
+
 def test_gemm_rejects_bad_alignment(ops):
     from ctpa_clip_b200._lib import CtclipError
     A = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
