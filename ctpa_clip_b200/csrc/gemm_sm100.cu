@@ -25,7 +25,7 @@ using namespace ptx;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle (keeps the epilogue warps quadrant-aligned), warps 4-11: epilogue
 constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant, each owning half of the tile's columns
 
 template <int BN, bool PAIR = false>
@@ -398,33 +398,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         // accumulator ready for the epilogue(s)
         if constexpr (PAIR) mma_commit_pair(tmem_full + acc); else mma_commit(tmem_full + acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== residual prefetcher =====================
-    // The fp32 residual tile the epilogue adds is read with ordinary loads; this otherwise idle warp pulls the NEXT
-    // tile's residual into L2 while the current tile is being multiplied, pacing itself on the accumulator barrier.
-    if (p.resid != nullptr && p.z_n <= 1) {
-      auto prefetch_tile = [&](int wn) {
-        if (wn >= num_work) return;
-        const int n_t = wn % p.n_tiles;
-        const int m_t = tile_m(wn);
-        const int cols = min(BN, p.N - n_t * BN);
-        const int lines = (cols * 4 + 127) / 128;            // 128-byte lines per tile row
-        for (int i = lane; i < BM * lines; i += 32) {
-          const int r = m_t * BM + i / lines;
-          if (r < p.M)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + n_t * BN + (i % lines) * 32));
-        }
-      };
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      prefetch_tile(w_first);
-      prefetch_tile(w_first + w_stride);
-      for (int w = w_first; w < num_work; w += w_stride) {
-        prefetch_tile(w + 2 * w_stride);        // two tiles of lead: a short-K tile is over in ~1 us
-        mbar_wait_bounded(tmem_full + acc, acc_phase, 1u << 16);   // observe only: the epilogue warps own the hand-shake
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
