@@ -434,30 +434,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = m_t * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
       if (p.top2 != nullptr) {
-        // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column); one warp per
-        // lane quadrant scans the whole tile so that a row's result stays in one thread
-        if (ch == 0) {
-          float v1 = -INFINITY, v2 = -INFINITY;
-          int i1 = -1, i2 = -1;
+        // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column). The two warps of
+        // a lane quadrant scan one half of the columns each; the upper half hands its pair to the lower one through the
+        // staging tile (named barrier of the two warps), which merges and writes one float4 per row.
+        float v1 = -INFINITY, v2 = -INFINITY;
+        int i1 = -1, i2 = -1;
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
-            if (n_t * BN + c >= p.N) break;
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c, r);
-            tmem_wait_ld();
+        for (int c = ch * kHalf; c < (ch + 1) * kHalf; c += 32) {
+          if (n_t * BN + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n_t * BN + c + j;
-              const float x = __uint_as_float(r[j]);
-              if (col < p.N) {
-                if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = col; }
-                else if (x > v2) { v2 = x; i2 = col; }
-              }
+          for (int j = 0; j < 32; ++j) {
+            const int col = n_t * BN + c + j;
+            const float x = __uint_as_float(r[j]);
+            if (col < p.N) {
+              if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = col; }
+              else if (x > v2) { v2 = x; i2 = col; }
             }
           }
-          if (row < p.M)
-            p.top2[(long long)row * p.n_tiles + n_t] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
         }
+        float4* xch = reinterpret_cast<float4*>(smem + L::kStageOut + (4 + ew) * (32 * 128));   // upper-half warp's tile
+        if (ch == 1) xch[lane] = make_float4(v1, __int_as_float(i1), v2, __int_as_float(i2));
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");
+        if (ch == 0) {
+          const float4 u = xch[lane];
+          const float b1 = u.x, b2 = u.z;
+          const int bi1 = __float_as_int(u.y), bi2 = __float_as_int(u.w);
+          float t1, t2; int j1, j2;
+          if (b1 > v1) {          // upper columns win only when strictly larger
+            t1 = b1; j1 = bi1;
+            if (b2 > v1) { t2 = b2; j2 = bi2; } else { t2 = v1; j2 = i1; }
+          } else {
+            t1 = v1; j1 = i1;
+            if (b1 > v2) { t2 = b1; j2 = bi1; } else { t2 = v2; j2 = i2; }
+          }
+          if (row < p.M)
+            p.top2[(long long)row * p.n_tiles + n_t] = make_float4(t1, __int_as_float(j1), t2, __int_as_float(j2));
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");   // the pair's tile is free for the next work unit
       } else if (fast_mode == 1 && n_t * BN + (ch + 1) * kHalf <= p.N) {
         // bf16 plain: 64 columns per round; the next round's TMEM loads fly while this round is stored
         const int cbase = n_t * BN + ch * kHalf;
@@ -661,9 +677,9 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
     if ((d->a_stride_h % 8) || (d->a_stride_b % 8) || (d->b_stride_h % 8) || (d->b_stride_b % 8))
       return ctclip::fail(CTCLIP_E_ALIGN, "gemm: batch strides must be multiples of 8 elements");
   }
-  // CTA pairs pay off where the tensor pipe is the limit: deep enough K, enough tiles to fill every pair, plain epilogues
+  // CTA pairs pay off where the tensor pipe is the limit: deep enough K, enough tiles to fill every pair
   const bool pair = BN == 256 && pair_enabled() && kp.m_tiles >= 2 && d->K >= 512 &&
-                    (long long)tiles * kp.splits * kp.z_n >= sms && kp.top2 == nullptr;
+                    (long long)tiles * kp.splits * kp.z_n >= sms;
   CUtensorMap ta, tb;
   rc = encode_operand_map(&ta, &kp.a_hpos, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM, zh_n, zb_n, d->a_stride_h,
                           d->a_stride_b);

@@ -83,9 +83,9 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int dim, const
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx_out = (add_in ? add_in : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy  (fp32 atomics, one per column per block)
-template <int kMaxVec>
+template <int kMaxVec, bool DY_BF16>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long rows, int dim,
+layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x, long long rows, int dim,
                      const float* __restrict__ gamma, float eps, const float* __restrict__ add_in,
                      float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
@@ -103,7 +103,6 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
-    const float4* dr = reinterpret_cast<const float4*>(dy + row * dim);
     float4 v[kMaxVec], d[kMaxVec];
     float s = 0.f;
 #pragma unroll
@@ -111,7 +110,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       const int i = lane + 32 * j;
       if (i < nvec) {
         v[j] = xr[i];
-        d[j] = dr[i];
+        if (DY_BF16) {   // upstream gradient straight from a bf16 GEMM epilogue
+          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_v) + row * dim)[i];
+          d[j] = make_float4(ptx::bf16_lo(u.x), ptx::bf16_hi(u.x), ptx::bf16_lo(u.y), ptx::bf16_hi(u.y));
+        } else {
+          d[j] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_v) + row * dim)[i];
+        }
         s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
     }
@@ -278,9 +282,9 @@ extern "C" int ctclip_layernorm_fwd(const float* x, long long rows, int dim, con
   return ctclip::check_launch("layernorm_fwd");
 }
 
-extern "C" int ctclip_layernorm_bwd(const float* dy, const float* x, long long rows, int dim, const float* gamma,
-                                    float eps, const float* add_in, float* dx_out, void* dx_bf16, float* dgamma,
-                                    float* dbeta, void* stream) {
+extern "C" int ctclip_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, long long rows, int dim,
+                                    const float* gamma, float eps, const float* add_in, float* dx_out, void* dx_bf16,
+                                    float* dgamma, float* dbeta, void* stream) {
   if (rows <= 0) return CTCLIP_OK;
   if (dim % 4 || dim > kMaxVecAll * 128 || dim <= 0)
     return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: dim must be a multiple of 4 and <= %d", kMaxVecAll * 128);
@@ -294,10 +298,18 @@ extern "C" int ctclip_layernorm_bwd(const float* dy, const float* x, long long r
   const size_t sm = 2 * dim * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
-  if (nv <= 1) layernorm_bwd_kernel<1><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
-  else if (nv <= 2) layernorm_bwd_kernel<2><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
-  else if (nv <= 4) layernorm_bwd_kernel<4><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
-  else layernorm_bwd_kernel<8><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);
+#define LN_BWD(V)                                                                                                      \
+  do {                                                                                                                 \
+    if (dy_is_bf16)                                                                                                    \
+      layernorm_bwd_kernel<V, true><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);  \
+    else                                                                                                               \
+      layernorm_bwd_kernel<V, false><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta); \
+  } while (0)
+  if (nv <= 1) LN_BWD(1);
+  else if (nv <= 2) LN_BWD(2);
+  else if (nv <= 4) LN_BWD(4);
+  else LN_BWD(8);
+#undef LN_BWD
   return ctclip::check_launch("layernorm_bwd");
 }
 

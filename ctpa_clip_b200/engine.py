@@ -203,7 +203,7 @@ def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal,
         dw2 = gs.zeros(prefix + "3.4.weight", (dim, L.ffp))
         ops.gemm(g_bf, c.u, a_t=True, b_t=True, out=dw2, accumulate=True, splits=0)
     dh1 = ops.geglu_bwd(c.h1, du)
-    dxf = ops.gemm(dh1, L.w1p, b_t=True, out_dtype=torch.float32)                           # [T, dim]
+    dxf = ops.gemm(dh1, L.w1p, b_t=True)                  # [T, dim] bf16: only LayerNorm's backward reads it
     # one GEMM over both padded halves [x rows | gate rows] (two half-size GEMMs into the parameter's own gradient would
     # read xf twice and fill the SMs worse); un-padded and handed to autograd at the end
     dw1 = gs.fresh(prefix + "3.1.weight", (2 * L.ffp, dim))
@@ -220,7 +220,7 @@ def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal,
     dks = gs.zeros(prefix + "1.k_scale", (32,))
     dq, dkv = ops.attn_bwd(c.q, c.kv, c.o, c.lse, d_o, grid, heads, temporal, L.q_scale, L.k_scale, dqs, dks, tab, rowmax,
                            dtab)
-    dxn = ops.gemm(dq, L.wq, b_t=True, out_dtype=torch.float32)
+    dxn = ops.gemm(dq, L.wq, b_t=True)                    # bf16, consumed by the LayerNorm backward below
     dwq = gs.zeros(prefix + "1.to_q.weight", (inner, dim))
     ops.gemm(dq, c.xn, a_t=True, b_t=True, out=dwq, accumulate=True, splits=0)
     dwkv = gs.zeros(prefix + "1.to_kv.weight", (2 * inner, dim))

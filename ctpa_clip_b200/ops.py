@@ -145,14 +145,15 @@ def layernorm_fwd(x, gamma, beta=None, *, eps=1e-5, want_bf16=True, want_raw_bf1
 
 def layernorm_bwd(dy, x, gamma, *, eps=1e-5, add_in=None, dgamma=None, dbeta=None, want_bf16=False, out=None):
     """returns (dx fp32, dx_bf16 | None); dgamma / dbeta are accumulated in place"""
-    _req(dy, torch.float32, "layernorm_bwd.dy")
+    if dy.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.CtclipError("layernorm_bwd.dy: expected fp32 or bf16")
     _req(x, torch.float32, "layernorm_bwd.x")
     rows, dim = x.shape
-    assert dy.is_contiguous() and x.is_contiguous()
+    assert dy.is_cuda and dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape
     dx = out if out is not None else torch.empty_like(x)
     dxb = torch.empty((rows, dim), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    _call("ctclip_layernorm_bwd", _ptr(dy), _ptr(x), _ll(rows), dim, _ptr(gamma), _f(eps), _ptr(add_in), _ptr(dx),
-          _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _stream())
+    _call("ctclip_layernorm_bwd", _ptr(dy), int(dy.dtype == torch.bfloat16), _ptr(x), _ll(rows), dim, _ptr(gamma), _f(eps),
+          _ptr(add_in), _ptr(dx), _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _stream())
     return dx, dxb
 
 

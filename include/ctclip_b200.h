@@ -74,8 +74,9 @@ int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream);
  * geglu: attention.py:39-42 on a [rows][2*ld_half] bf16 buffer laid out [x | gate]. */
 int ctclip_layernorm_fwd(const float* x, long long rows, int dim, const float* gamma, const float* beta, float eps,
                          void* y_bf16, void* raw_bf16, float* y_f32, void* stream);
-int ctclip_layernorm_bwd(const float* dy, const float* x, long long rows, int dim, const float* gamma, float eps,
-                         const float* add_in, float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+int ctclip_layernorm_bwd(const void* dy /* fp32, or bf16 when dy_is_bf16 (straight from a GEMM epilogue) */, int dy_is_bf16,
+                         const float* x, long long rows, int dim, const float* gamma, float eps, const float* add_in,
+                         float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_half, void* stream);
 int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, int ld_half, void* stream);
 int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream);

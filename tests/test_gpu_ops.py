@@ -112,6 +112,13 @@ def test_layernorm_fwd_bwd(ops, rows, dim):
     dg, db = torch.zeros(dim, device="cuda"), torch.zeros(dim, device="cuda")
     dx, dxb = ops.layernorm_bwd(dy, x, gam, add_in=add, dgamma=dg, dbeta=db, want_bf16=True)
     close(dx, xr.grad + add, 1e-4); close(dxb, xr.grad + add, 1e-2); close(dg, gr.grad, 1e-4); close(db, br.grad, 1e-4)
+    # upstream gradient handed over in bf16 (as the dgrad GEMM epilogue writes it): exact for the bf16-rounded dy
+    dyb = dy.bfloat16()
+    xr2, gr2, br2 = x.clone().requires_grad_(), gam.clone().requires_grad_(), bet.clone().requires_grad_()
+    F.layer_norm(xr2, (dim,), gr2, br2).backward(dyb.float())
+    dg2, db2 = torch.zeros(dim, device="cuda"), torch.zeros(dim, device="cuda")
+    dx2, _ = ops.layernorm_bwd(dyb, x, gam, dgamma=dg2, dbeta=db2)
+    close(dx2, xr2.grad, 1e-4); close(dg2, gr2.grad, 1e-4); close(db2, br2.grad, 1e-4)
 
 
 def test_constant_rows_give_beta(ops):
