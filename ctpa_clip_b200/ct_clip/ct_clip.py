@@ -63,7 +63,8 @@ class LinearFunction(torch.autograd.Function):
             if w is not None and w.grad is not None and w.grad.is_contiguous():
                 # direct mode: accumulate into the parameter's gradient buffer (no 600 MB temporary + add for the
                 # 294912 -> 512 projection); autograd gets None
-                ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, accumulate=True, splits=1)
+                # (in-place "+=" through the residual epilogue: plain 128-bit loads / stores instead of 151 M atomics)
+                ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, resid=w.grad)
             else:
                 dw = ops.gemm(dyb, xb, a_t=True, b_t=True, out_dtype=torch.float32)  # [N, K], reduction over the batch
         return dx, dw, None, None, None
