@@ -41,7 +41,7 @@ class LinearFunction(torch.autograd.Function):
     """y = x W^T (bias-free nn.Linear, ct_clip.py:549,564) on the tcgen05 GEMM; fp32 accumulate, fp32 out"""
 
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, x_bf16, direct=False):
+    def forward(ctx, x, weight, w_bf16, x_bf16, direct=False, ready=None):
         xb = x_bf16 if x_bf16 is not None else ops.cast_bf16(x.contiguous().float())
         M = xb.shape[0]
         y = torch.zeros((M, weight.shape[0]), device=x.device, dtype=torch.float32)
@@ -49,6 +49,7 @@ class LinearFunction(torch.autograd.Function):
         ctx.save_for_backward(xb, w_bf16)
         ctx.need = (x.requires_grad, weight.requires_grad)
         ctx.weight = weight if direct else None
+        ctx.ready = ready
         return y
 
     @staticmethod
@@ -65,9 +66,11 @@ class LinearFunction(torch.autograd.Function):
                 # 294912 -> 512 projection); autograd gets None
                 # (in-place "+=" through the residual epilogue: plain 128-bit loads / stores instead of 151 M atomics)
                 ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, resid=w.grad)
+                if ctx.ready is not None:
+                    ctx.ready([w])       # this gradient is final: the trainer may start its all-reduce now
             else:
                 dw = ops.gemm(dyb, xb, a_t=True, b_t=True, out_dtype=torch.float32)  # [N, K], reduction over the batch
-        return dx, dw, None, None, None
+        return dx, dw, None, None, None, None
 
 
 class ClipLossFunction(torch.autograd.Function):
@@ -171,6 +174,7 @@ class CTCLIP(nn.Module):
         self._native_text = None
         # set by CTClipTrainStep: kernels accumulate parameter gradients straight into the existing p.grad buffers
         self.direct_grad = False
+        self.grad_ready = None      # optional callable(list of parameters): their .grad is final (direct mode only)
         self._sh_text, self._sh_vis = _Shadow(), _Shadow()
 
     def load(self, path):
@@ -188,6 +192,7 @@ class CTCLIP(nn.Module):
                 self._native_text = NativeBert(self.text_transformer)
             if self._native_text is not None:   # BERT on the sm_100a kernels (ct_clip.py:685-686)
                 self._native_text.direct_grad = self.direct_grad
+                self._native_text.grad_ready = self.grad_ready
                 training = self.training and self.text_transformer.training and torch.is_grad_enabled()
                 return encode(self._native_text, text.input_ids, text.attention_mask, training)
         # any other injected text encoder runs as the torch module it is (library kernels)
@@ -201,13 +206,13 @@ class CTCLIP(nn.Module):
     def text_latents_raw(self, enc_text):
         cls = enc_text[:, 0, :].float().contiguous()                                # ct_clip.py:762
         return LinearFunction.apply(cls, self.to_text_latent.weight, self._sh_text.get(self.to_text_latent.weight), None,
-                                    self.direct_grad)
+                                    self.direct_grad, self.grad_ready)
 
     def image_latents_raw(self, image):
         vit = self.visual_transformer
         pooled = vit.encode_pooled(image)                                           # ct_clip.py:715,724,740
         return LinearFunction.apply(pooled, self.to_visual_latent.weight, self._sh_vis.get(self.to_visual_latent.weight),
-                                    vit.last_pooled_bf16, self.direct_grad)
+                                    vit.last_pooled_bf16, self.direct_grad, self.grad_ready)
 
     # ---------------------------------------------------------------- forward (ct_clip.py:614-901)
     def forward(self, text, image, device=None, return_loss=False, return_encodings=False, return_latents=False,

@@ -51,6 +51,7 @@ class NativeBert:
         # True (set by CTClipTrainStep): the kernels accumulate parameter gradients straight into the existing p.grad
         # buffers (flat gradient arena, zeroed by the optimiser kernel) and autograd gets None for them
         self.direct_grad = False
+        self.grad_ready = None      # optional callable(list of parameters), called at the end of a direct-mode backward
         # parameters in a fixed order (the autograd.Function takes them as inputs and returns their gradients)
         emb = module.embeddings
         self.names, self.params = [], []
@@ -285,6 +286,8 @@ class NativeBert:
         ops.bert_embed_bwd(ctx["ids"].reshape(-1), L, dpre0, target("embeddings.word_embeddings.weight"),
                            target("embeddings.position_embeddings.weight"), emb.word_embeddings.padding_idx)
         ops.colsum(dpre0, target("embeddings.token_type_embeddings.weight")[0])
+        if direct and self.grad_ready is not None and all(g is None for g in grads):
+            self.grad_ready(self.params)   # every gradient went straight into p.grad and is final
         return grads
 
 
