@@ -93,4 +93,5 @@ class PrepDesc(C.Structure):
         ("pad_value", C.c_float),
         ("lut_workspace", C.c_void_p),
         ("force_generic", C.c_int),
+        ("pre_op", C.c_int), ("post_op", C.c_int),
     ]

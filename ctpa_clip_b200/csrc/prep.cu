@@ -27,6 +27,8 @@ struct PrepParams {
   int tD, tH, tW;                      // destination volume
   long long obatch;
   int kn_max, jn_max;                  // shared tile extents (input depth / width span of one output tile)
+  int pre_op, post_op;                 // fp32 input: DataLoader-side arithmetic around the resample (see ctclip_prep_desc)
+  float slope32, icpt32;
 };
 
 __device__ __forceinline__ void taps(int in, int out, int o, int& i0, int& i1, float& w0, float& w1) {
@@ -54,6 +56,19 @@ __device__ __forceinline__ float load_norm(const PrepParams& p, long long off) {
     return (float)__ddiv_rn(v, 1000.0);
   }
   return reinterpret_cast<const float*>(p.in)[off];
+}
+
+// fp32 input, value arithmetic of the two DataLoaders (one rounding per numpy operation, no contraction):
+//   pre_op 2: data_inference.py:81-85   fl(fl(clip(fl(x*1000), -1000, 200) + 400) / 600)
+//   pre_op 3: data.py:138               fl(fl(slope*x) + intercept)
+__device__ __forceinline__ float pre_f32(const PrepParams& p, float v) {
+  if (p.pre_op == 2) {
+    v = __fmul_rn(v, 1000.f);
+    v = fminf(fmaxf(v, -1000.f), 200.f);
+    return __fdiv_rn(__fadd_rn(v, 400.f), 600.f);
+  }
+  if (p.pre_op == 3) return __fadd_rn(__fmul_rn(p.slope32, v), p.icpt32);
+  return v;
 }
 
 // exact HU normalisation table: lut[v - lut_lo] = float(clip(slope*v + intercept, -1000, 1000) / 1000) for raw values v in
@@ -119,7 +134,7 @@ prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_
             const int raw = reinterpret_cast<const short*>(p.in)[off + k];
             v = use_lut ? s_lut[min(max(raw, lut_lo), lut_lo + lut_n - 1) - lut_lo] : load_norm(p, off + k);
           } else {
-            v = reinterpret_cast<const float*>(p.in)[off + k];
+            v = pre_f32(p, reinterpret_cast<const float*>(p.in)[off + k]);
           }
           dst[k * jn_pad + j] = v;
         }
@@ -133,7 +148,7 @@ prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_
             const int raw = reinterpret_cast<const short*>(p.in)[off + (long long)j * p.sw];
             v = use_lut ? s_lut[min(max(raw, lut_lo), lut_lo + lut_n - 1) - lut_lo] : load_norm(p, off + (long long)j * p.sw);
           } else {
-            v = reinterpret_cast<const float*>(p.in)[off + (long long)j * p.sw];
+            v = pre_f32(p, reinterpret_cast<const float*>(p.in)[off + (long long)j * p.sw]);
           }
           dst[k * jn_pad + j] = v;
         }
@@ -165,7 +180,8 @@ prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_
       const float d = combine(r1[kb + ja], wa, r1[kb + jb], wb);   // d1, h1
       const float ab = combine(a, wh0, b, wh1);
       const float cd = combine(c, wh0, d, wh1);
-      const float v = combine(ab, s_wd0[z], cd, s_wd1[z]);
+      float v = combine(ab, s_wd0[z], cd, s_wd1[z]);
+      if (p.post_op == 1) v = __fdiv_rn(fminf(fmaxf(v, -1000.f), 1000.f), 1000.f);   // data.py:150-152
       const int dd = od_base + z - p.wd0 + p.pd0;
       const int dw = ow_base + x - p.ww0 + p.pw0;
       out_b[((long long)dd * p.tH + dh) * p.tW + dw] = v;
@@ -432,6 +448,11 @@ extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
   p.D = d->D; p.H = d->H; p.W = d->W;
   p.sd = d->stride_d; p.sh = d->stride_h; p.sw = d->stride_w; p.sbatch = d->stride_batch;
   p.oD = d->oD; p.oH = d->oH; p.oW = d->oW;
+  if (d->in_is_i16 && (d->pre_op || d->post_op))
+    return ctclip::fail(CTCLIP_E_SHAPE, "prep_resample: pre_op / post_op apply to fp32 input only");
+  if ((d->pre_op != 0 && d->pre_op != 2 && d->pre_op != 3) || (d->post_op != 0 && d->post_op != 1))
+    return ctclip::fail(CTCLIP_E_SHAPE, "prep_resample: unknown pre_op %d / post_op %d", d->pre_op, d->post_op);
+  p.pre_op = d->pre_op; p.post_op = d->post_op; p.slope32 = (float)d->slope; p.icpt32 = (float)d->intercept;
   p.tD = d->tD > 0 ? d->tD : d->oD; p.tH = d->tH > 0 ? d->tH : d->oH; p.tW = d->tW > 0 ? d->tW : d->oW;
   // centre crop / pad split exactly as data.py:155-189 (python floor division)
   const int o[3] = {p.oD, p.oH, p.oW}, t[3] = {p.tD, p.tH, p.tW};

@@ -40,3 +40,30 @@ def to_training_volume(vol_dhw, target_shape=TARGET_SHAPE, pad_value=-1.0):
     """centre crop / pad(-1) of an already normalised (b, D, H, W) fp32 volume to (b, 1, 240, 480, 480) (data.py:155-190)"""
     out = ops.prep_resample(vol_dhw.contiguous(), vol_dhw.shape[1:], layout="dhw", target=target_shape, pad_value=pad_value)
     return out[:, None]
+
+
+def _as_f32_cuda(arr):
+    t = torch.from_numpy(arr) if isinstance(arr, np.ndarray) else arr
+    if t.dtype != torch.float32 or t.dim() != 3:
+        raise ValueError("loader volumes are 3-D float32 arrays (the .npz files preprocess_train.py writes)")
+    return t.to("cuda", non_blocking=True).contiguous()
+
+
+def training_loader_volume(ct_scan, slope, intercept, xy_spacing, z_spacing, target_shape=TARGET_SHAPE):
+    """CTReportDataset.npz_img_to_tensor (ct_clip/data.py:114-192) after the file / CSV reads, in ONE kernel:
+    ct_scan is the float32 (H, W, N) array of the .npz; slope * x + intercept (float32), resize_array to spacing
+    (1.5, 0.75, 0.75), clip [-1000, 1000] / 1000, centre crop / pad(-1) to (480, 480, 240), permute.
+    Returns the (1, 240, 480, 480) CUDA tensor the Dataset yields, bit-identical to the reference's."""
+    x = _as_f32_cuda(ct_scan)
+    H, W, N = x.shape
+    new_shape = resize_shape((N, H, W), (z_spacing, xy_spacing, xy_spacing), TARGET_SPACING)
+    return ops.prep_resample(x[None], new_shape, hu=(slope, intercept), layout="hwn", target=target_shape, pad_value=-1.0,
+                             pre_op="affine", post_op="clip_div")
+
+
+def inference_loader_volume(img_data, target_shape=TARGET_SHAPE):
+    """CTReportDatasetinfer.nii_img_to_tensor (ct_clip/data_inference.py:78-122) after np.load: img_data is the float32
+    (D, H, W) array of the .npz; (clip(x * 1000, -1000, 200) + 400) / 600, centre crop / pad(-1), no resample.
+    Returns (1, 240, 480, 480)."""
+    x = _as_f32_cuda(img_data)
+    return ops.prep_resample(x[None], x.shape, layout="dhw", target=target_shape, pad_value=-1.0, pre_op="infer_window")

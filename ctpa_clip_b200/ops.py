@@ -390,11 +390,18 @@ def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max
           _f(beta2), _f(eps), step, _ptr(norm_sq), _f(max_norm), int(zero_grad), _stream())
 
 
-def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0, force_generic=False):
+PREP_PRE_OPS = {None: 0, "infer_window": 2, "affine": 3}
+PREP_POST_OPS = {None: 0, "clip_div": 1}
+
+
+def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0, force_generic=False,
+                  pre_op=None, post_op=None):
     """Trilinear resample (align_corners=False) of a batch of volumes on the GPU.
     layout "dhw": inp is [b, D, H, W] (fp32, or int16 with hu=(slope, intercept));
     layout "hwn": inp is [b, H, W, N] as stored in a NIfTI array (depth contiguous).
-    out_grid = (oD, oH, oW) resampled size; target = (tD, tH, tW) -> centre crop / pad(pad_value) window."""
+    out_grid = (oD, oH, oW) resampled size; target = (tD, tH, tW) -> centre crop / pad(pad_value) window.
+    fp32 input: pre_op "affine" (with hu=(slope, intercept), data.py:138) or "infer_window" (data_inference.py:81-85) is applied
+    to every voxel before, post_op "clip_div" (data.py:150-152) after the resample — the DataLoaders' float32 arithmetic."""
     assert inp.is_cuda and inp.is_contiguous() and inp.dim() == 4
     d = _lib.PrepDesc()
     b = inp.shape[0]
@@ -410,8 +417,12 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
         if hu is None:
             raise _lib.CtclipError("prep_resample: int16 input needs hu=(slope, intercept)")
         d.in_is_i16, d.slope, d.intercept = 1, float(hu[0]), float(hu[1])
+        d.pre_op, d.post_op = PREP_PRE_OPS[pre_op], PREP_POST_OPS[post_op]    # rejected by the library for int16
     elif inp.dtype == torch.float32:
         d.in_is_i16 = 0
+        d.pre_op, d.post_op = PREP_PRE_OPS[pre_op], PREP_POST_OPS[post_op]
+        if pre_op == "affine":
+            d.slope, d.intercept = float(hu[0]), float(hu[1])
     else:
         raise _lib.CtclipError("prep_resample: input must be int16 or float32")
     tgt = tuple(target) if target is not None else tuple(out_grid)

@@ -207,6 +207,12 @@ typedef struct ctclip_prep_desc {
   float pad_value;
   float* lut_workspace; /* device scratch of >= 8192 floats for the exact HU table (int16 input); NULL -> per-voxel fp64 */
   int force_generic;    /* 1: skip the depth-marching fast path for int16 (H,W,N) scans (test hook; results are identical) */
+  /* fp32 input only — the value arithmetic of the two DataLoaders, fused around the resample (float32, one rounding per
+   * numpy operation):
+   *   pre_op 2: CTReportDatasetinfer.nii_img_to_tensor, ct_clip/data_inference.py:81-85: (clip(x*1000, -1000, 200) + 400) / 600
+   *   pre_op 3: CTReportDataset.npz_img_to_tensor, ct_clip/data.py:138: (float)slope * x + (float)intercept
+   *   post_op 1: ct_clip/data.py:150-152, after the resample: clip(v, -1000, 1000) / 1000 */
+  int pre_op, post_op;
 } ctclip_prep_desc;
 int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream);
 

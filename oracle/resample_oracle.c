@@ -100,3 +100,32 @@ void ctclip_oracle_crop_pad(const float* in, int D, int H, int W, float* out, in
         out[((size_t)d * tH + h) * tW + w] = v;
       }
 }
+
+/* ---- DataLoader-side arithmetic (the two loaders that feed CT-CLIP) ------------------------------------------------
+ * All float32, one rounding per numpy operation (NEP 50: the python scalars act as float32 against a float32 array).
+ *   affine_f32   : CTPA_CLIP/ct_clip/data.py:138   img = slope * ct_scan + intercept           (before the resample)
+ *   clip_div_f32 : CTPA_CLIP/ct_clip/data.py:150-152  clip(img, -1000, 1000) / 1000             (after the resample)
+ *   window_infer : CTPA_CLIP/ct_clip/data_inference.py:81-85  clip(img * 1000, -1000, 200); (img + 400) / 600 */
+void ctclip_oracle_affine_f32(const float* in, size_t n, float slope, float intercept, float* out) {
+  for (size_t i = 0; i < n; ++i) {
+    float v = slope * in[i];
+    out[i] = v + intercept;
+  }
+}
+void ctclip_oracle_clip_div_f32(const float* in, size_t n, float* out) {
+  for (size_t i = 0; i < n; ++i) {
+    float v = in[i];
+    if (v < -1000.f) v = -1000.f;
+    if (v > 1000.f) v = 1000.f;
+    out[i] = v / 1000.f;
+  }
+}
+void ctclip_oracle_window_infer(const float* in, size_t n, float* out) {
+  for (size_t i = 0; i < n; ++i) {
+    float v = in[i] * 1000.f;
+    if (v < -1000.f) v = -1000.f;
+    if (v > 200.f) v = 200.f;
+    v = v + 400.f;
+    out[i] = v / 600.f;
+  }
+}

@@ -69,3 +69,32 @@ def preprocess_volume(raw_hwn: np.ndarray, slope: float, intercept: float, xy_sp
     vol = hu_normalise(raw_hwn, slope, intercept)
     new_shape = resize_shape(vol.shape, (z_spacing, xy_spacing, xy_spacing), target)
     return trilinear(vol, new_shape)
+
+
+def _unary(fn, x: np.ndarray, *args) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    getattr(lib(), fn)(x.ctypes.data_as(C.c_void_p), C.c_size_t(x.size), *args, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def training_loader_volume(arr: np.ndarray, slope: float, intercept: float, xy_spacing: float, z_spacing: float,
+                           target=(240, 480, 480)) -> np.ndarray:
+    """CTReportDataset.npz_img_to_tensor, CTPA_CLIP/ct_clip/data.py:138-192, on the float32 array of an .npz:
+    slope*x+intercept (float32) -> transpose(2,0,1) -> resize_array to spacing (1.5, 0.75, 0.75) -> clip[-1000,1000]/1000 ->
+    centre crop / pad(-1) to (480,480,240) in (h,w,d) order -> permute to (1, 240, 480, 480)."""
+    assert arr.dtype == np.float32 and arr.ndim == 3
+    img = _unary("ctclip_oracle_affine_f32", arr, C.c_float(slope), C.c_float(intercept))
+    img = np.ascontiguousarray(img.transpose(2, 0, 1))                                   # data.py:139
+    new_shape = resize_shape(img.shape, (z_spacing, xy_spacing, xy_spacing), (1.5, 0.75, 0.75))
+    img = trilinear(img, new_shape)                                                      # data.py:142-146
+    img = _unary("ctclip_oracle_clip_div_f32", img)                                      # data.py:150-152
+    return crop_pad(img, target, -1.0)[None]                                             # data.py:155-190
+
+
+def inference_loader_volume(arr: np.ndarray, target=(240, 480, 480)) -> np.ndarray:
+    """CTReportDatasetinfer.nii_img_to_tensor, CTPA_CLIP/ct_clip/data_inference.py:78-122: x*1000 -> clip[-1000,200] ->
+    (x+400)/600 (float32) -> centre crop / pad(-1) to (480,480,240) -> (1, 240, 480, 480). No resample."""
+    assert arr.dtype == np.float32 and arr.ndim == 3
+    img = _unary("ctclip_oracle_window_infer", arr)
+    return crop_pad(img, target, -1.0)[None]

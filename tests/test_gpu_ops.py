@@ -387,3 +387,46 @@ def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spaci
         got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
         assert got.shape == want.shape
         assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force}"
+
+
+# ---- DataLoader conversions on the GPU ---------------------------------------------------------------
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_inference_loader_volume_equals_reference_golden(ops, i):
+    """data_inference.py:78-122 fused into the resample kernel; golden = the reference loader's own output"""
+    from ctpa_clip_b200.data_prep import inference_loader_volume
+    g = np.load("tests/golden/loaders.npz")
+    arr = g[f"infer{i}_q"].astype(np.float32) / np.float32(1024)
+    got = inference_loader_volume(arr).cpu().numpy()
+    assert got.shape == (1, 240, 480, 480)
+    assert _sha(got) == g[f"infer{i}_sha256"].tobytes()
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_training_loader_volume_equals_reference_golden(ops, i):
+    """data.py:114-192 (affine -> resize_array -> clip / 1000 -> crop / pad(-1) -> permute) in one kernel, bit-exact"""
+    from ctpa_clip_b200.data_prep import training_loader_volume
+    g = np.load("tests/golden/loaders.npz")
+    s, ic, xy, z = (float(v) for v in g[f"train{i}_params"])
+    got = training_loader_volume(g[f"train{i}_in"], s, ic, xy, z).cpu().numpy()
+    assert got.shape == (1, 240, 480, 480)
+    assert _sha(got) == g[f"train{i}_sha256"].tobytes()
+
+
+def test_training_loader_volume_full_size_equals_oracle(ops):
+    """a CT-RATE sized float32 scan (512 x 512 x 160, spacing 0.82 / 2.0: crop in h / w, pad in depth) against the C oracle"""
+    from ctpa_clip_b200.data_prep import training_loader_volume
+    rng = np.random.default_rng(3)
+    arr = (rng.random((512, 512, 160), dtype=np.float32) * 3000 - 1400).astype(np.float32)
+    want = R.training_loader_volume(arr, 1.0, -8.25, 0.82, 2.0)
+    got = training_loader_volume(arr, 1.0, -8.25, 0.82, 2.0).cpu().numpy()
+    assert (got.view(np.int32) == want.view(np.int32)).all()
+
+
+def test_loader_ops_reject_int16_input(ops):
+    with pytest.raises(Exception):
+        ops.prep_resample(torch.zeros(1, 8, 8, 8, dtype=torch.int16, device="cuda"), (8, 8, 8), hu=(1.0, 0.0), post_op="clip_div")

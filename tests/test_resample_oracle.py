@@ -106,3 +106,35 @@ def test_fp32_newton_division_equals_numpy_double_path_for_all_integer_hu():
         q0 = rnd32(F(c) * r)
         q1 = rnd32(rnd32(-q0 * 1000 + c) * r + q0)
         assert float(q1) == float(want), c
+
+
+# ---- DataLoader conversions: oracle restatement pinned against the reference's own loaders ------------
+def _loader_golden():
+    return np.load("tests/golden/loaders.npz")
+
+
+def _check_volume(out, g, key):
+    import hashlib
+    assert out.shape == (1, 240, 480, 480) and out.dtype == np.float32
+    assert hashlib.sha256(out.tobytes()).digest() == g[key + "_sha256"].tobytes()
+    if key + "_win" in g:
+        lo, hi = g[key + "_box"][:3], g[key + "_box"][3:]
+        assert np.array_equal(out[0, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]], g[key + "_win"])
+        assert out[0, 0, 0, 0] == -1.0                           # pad value, data.py:186 / data_inference.py:115
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_inference_loader_oracle_matches_reference(i):
+    """golden = CTReportDatasetinfer.nii_img_to_tensor run verbatim (tools/make_golden.py loaders); case 1 crops depth"""
+    g = _loader_golden()
+    arr = g[f"infer{i}_q"].astype(np.float32) / np.float32(1024)
+    _check_volume(R.inference_loader_volume(arr), g, f"infer{i}")
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_training_loader_oracle_matches_reference(i):
+    """golden = CTReportDataset.npz_img_to_tensor run verbatim; case 2 has a slope / intercept that float32 cannot
+    represent (pins the float32 weak-scalar arithmetic of data.py:138) and up-samples depth 2x"""
+    g = _loader_golden()
+    s, ic, xy, z = (float(v) for v in g[f"train{i}_params"])
+    _check_volume(R.training_loader_volume(g[f"train{i}_in"], s, ic, xy, z), g, f"train{i}")

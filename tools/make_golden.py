@@ -1,7 +1,7 @@
 """Writes tests/golden/*.pt / *.npz by running the UNMODIFIED reference (/root/reference, authoring container only)
 through oracle/ref_shim.py on the seeded synthetic weights / inputs of oracle/ctclip_oracle.py.
 
-    python tools/make_golden.py [tiny mid production resample]
+    python tools/make_golden.py [tiny mid production resample loaders]
 
 The fixtures pin (i) the oracle restatement against the real reference modules, (ii) the data_prep index/weight rule and
 value arithmetic against the reference's own resize_array. They travel to the GPU box; /root/reference does not.
@@ -122,11 +122,65 @@ def resample_fixture():
     print("resample ->", (GOLD / "resample.npz").stat().st_size // 1024, "KiB")
 
 
+def loaders_fixture():
+    """the reference's two DataLoader conversions run verbatim on small synthetic .npz arrays (outputs are the fixed
+    (1,240,480,480) training volume: stored as sha256 + the non-padding window)"""
+    import os, tempfile, types
+    import pandas as pd
+    sys.path.insert(0, str(ref_shim.REFERENCE_ROOT))
+    import ct_clip.data as rdata
+    import ct_clip.data_inference as rinf
+    rng = np.random.default_rng(7)
+    out = {}
+
+    def window_of(t):  # (1,240,480,480) -> bounding box of the values that are not the -1 padding
+        a = t[0].numpy()
+        nz = np.argwhere(a != -1.0)
+        lo, hi = nz.min(0), nz.max(0) + 1
+        return np.concatenate([lo, hi]), np.ascontiguousarray(a[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]])
+
+    with tempfile.TemporaryDirectory() as td:
+        # ---- inference loader (data_inference.py:78-122)
+        for i, shape in enumerate([(20, 36, 30), (484, 4, 244)]):
+            q = rng.integers(-1126, 512, size=shape, dtype=np.int16)     # stored as int16: arr = q / 1024 exactly
+            arr = q.astype(np.float32) / np.float32(1024)
+            path = os.path.join(td, f"inf{i}.npz")
+            np.savez(path, arr)
+            t = rinf.CTReportDatasetinfer.nii_img_to_tensor(types.SimpleNamespace(), path, None)
+            box, win = window_of(t)
+            out[f"infer{i}_q"], out[f"infer{i}_box"] = q, box
+            if win.size < 100000:                                        # the crop case is pinned by its sha256 only
+                out[f"infer{i}_win"] = win
+            out[f"infer{i}_sha256"] = np.frombuffer(hashlib.sha256(t.numpy().tobytes()).digest(), dtype=np.uint8)
+        # ---- training loader (data.py:114-192): metadata CSV row patched in
+        cases = [((24, 30, 18), 1.0, 0.0, 0.9, 2.0), ((40, 26, 33), 1.0, -24.0, 0.6, 1.2), ((16, 20, 12), 1.0007, -10.3, 1.1, 3.0)]
+        for i, (shape, slope, intercept, xy, z) in enumerate(cases):
+            arr = (rng.random(shape, dtype=np.float32) * 2600 - 1300).astype(np.float32)
+            path = os.path.join(td, f"train{i}.npz")
+            np.savez(path, arr)
+            df = pd.DataFrame({"VolumeName": [f"train{i}.nii"], "RescaleSlope": [slope], "RescaleIntercept": [intercept],
+                               "XYSpacing": [f"[{xy}, {xy}]"], "ZSpacing": [z]})
+            real = pd.read_csv
+            pd.read_csv = lambda *a, **k: df
+            try:
+                t = rdata.CTReportDataset.npz_img_to_tensor(types.SimpleNamespace(split="train"), path, None)
+            finally:
+                pd.read_csv = real
+            box, win = window_of(t)
+            out[f"train{i}_in"], out[f"train{i}_params"] = arr, np.array([slope, intercept, xy, z])
+            out[f"train{i}_box"], out[f"train{i}_win"] = box, win
+            out[f"train{i}_sha256"] = np.frombuffer(hashlib.sha256(t.numpy().tobytes()).digest(), dtype=np.uint8)
+    np.savez_compressed(GOLD / "loaders.npz", **out)
+    print("loaders ->", (GOLD / "loaders.npz").stat().st_size // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["tiny", "mid", "production", "resample"]
+    what = sys.argv[1:] or ["tiny", "mid", "production", "resample", "loaders"]
     assert ref_shim.available(), "needs /root/reference"
     for w in what:
         if w == "resample":
             resample_fixture()
+        elif w == "loaders":
+            loaders_fixture()
         else:
             model_fixture(w)
