@@ -872,6 +872,402 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   }
 }
 
+
+// =============================================================================================== short sequences
+// Sequences of n <= 32 tokens without an additive bias (the temporal attention of CTViT: n = t = 24, 4608 x 8
+// (sequence, head) problems of 24 x 24 x 32 per volume batch). A 128-row tcgen05 tile would be > 80 % padding and the
+// whole problem fits the registers of one warp, so here ONE WARP owns one (sequence, head): Q^, K^, V (dO, O) rows go
+// straight from global memory into mma.sync m16n8k16 fragment images (bf16 operands, fp32 accumulators — the same operand
+// rounding as the tcgen05 kernels), S / P / dS never leave registers and the transposed operands (V^T, K^T, P^T, dS^T,
+// dO^T, Q^T) come from movmatrix. Same math as above: s = (8 log2e q^).k^, p = exp2(s - lse).
+//
+// Fragment images: thread (g = lane / 4, c = lane % 4) holds, for row block a (rows g + 8a), ONE 16-byte group = the eight
+// head-dim columns 8c .. 8c+7 (a single coalesced load / store per row). The tensor-core k / n index of a head-dim column
+// is therefore a fixed permutation of the real one — harmless, every operand uses the same permutation and the output
+// fragments (columns 2c + 8 nt + e in MMA space) land on the thread's own eight real columns 8c + 2 nt + e.
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {  // 8x8 bf16 block image -> image of its transpose
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ uint32_t comp(const uint4& u, int b) { return b == 0 ? u.x : b == 1 ? u.y : b == 2 ? u.z : u.w; }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+  v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+}
+// l2-normalise one head row spread over the four threads of a quad, scale per column, pack to bf16; returns 1 / |row|
+__device__ __forceinline__ float norm_row(const uint4& raw, const float (&sc)[8], uint4& img) {
+  float v[8];
+  unpack8(raw, v);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+  ss = quad_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  img.x = pack_bf16(v[0] * inv * sc[0], v[1] * inv * sc[1]);
+  img.y = pack_bf16(v[2] * inv * sc[2], v[3] * inv * sc[3]);
+  img.z = pack_bf16(v[4] * inv * sc[4], v[5] * inv * sc[5]);
+  img.w = pack_bf16(v[6] * inv * sc[6], v[7] * inv * sc[7]);
+  return inv;
+}
+// token of row r of sequence `seq`: spatial sequences are contiguous, temporal ones have stride h*w
+__device__ __forceinline__ void seq_origin(const AttnParams& p, long long seq, long long& tok0, long long& tstride) {
+  if (p.mode == 0) { tok0 = seq * p.n; tstride = 1; return; }
+  const int hw = p.gh * p.gw;
+  const long long b = seq / hw;
+  tok0 = b * p.gt * hw + (seq - b * hw);
+  tstride = hw;
+}
+
+// NB = number of 8-row blocks (ceil(n / 8)); rows / keys beyond n are zero images and masked probabilities
+template <int NB>
+__global__ void __launch_bounds__(256)
+attn_short_fwd_kernel(const AttnParams p) {
+  constexpr int MT = (NB + 1) / 2, NA = 2 * MT;
+  __shared__ float sScale[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  if (tid < DH) {
+    sScale[tid] = p.q_scale[tid] * (kScale * kLog2e);
+    sScale[DH + tid] = p.k_scale[tid];
+  }
+  __syncthreads();
+  float qs[8], ks[8], cmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { qs[i] = sScale[8 * c + i]; ks[i] = sScale[DH + 8 * c + i]; }
+  for (int d = 0; d < DH; ++d) cmax = fmaxf(cmax, fabsf(sScale[d] * sScale[DH + d]));
+  const long long pairs = (long long)p.num_seqs * p.heads;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (long long pair = (long long)blockIdx.x * 8 + warp; pair < pairs; pair += (long long)gridDim.x * 8) {
+    const int head = (int)(pair % p.heads);
+    long long tok0, tstride;
+    seq_origin(p, pair / p.heads, tok0, tstride);
+    uint4 qi[NA], ki[NA], vi[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = g + 8 * a;
+      qi[a] = ki[a] = vi[a] = zero4;
+      if (a < NB && r < p.n) {
+        const long long tok = tok0 + r * tstride;
+        qi[a] = __ldg(reinterpret_cast<const uint4*>(p.q + tok * p.ldq + head * DH + 8 * c));
+        ki[a] = __ldg(reinterpret_cast<const uint4*>(p.kv + tok * p.ldkv + head * DH + 8 * c));
+        vi[a] = __ldg(reinterpret_cast<const uint4*>(p.kv + tok * p.ldkv + p.inner + head * DH + 8 * c));
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      norm_row(qi[a], qs, qi[a]);
+      norm_row(ki[a], ks, ki[a]);
+    }
+    // S = Q~ K^T
+    float sacc[MT][NA][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NA; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[mt][nt][e] = 0.f;
+        if (nt < NB) {
+#pragma unroll
+          for (int kd = 0; kd < 2; ++kd)
+            mma_16816(sacc[mt][nt], comp(qi[2 * mt], 2 * kd), comp(qi[2 * mt + 1], 2 * kd), comp(qi[2 * mt], 2 * kd + 1),
+                      comp(qi[2 * mt + 1], 2 * kd + 1), comp(ki[nt], 2 * kd), comp(ki[nt], 2 * kd + 1));
+        }
+      }
+    // p = exp2(s - cmax) (never overflows: |s| <= cmax), masked beyond the sequence; row sums over the quad
+    uint32_t pimg[NA][NA];
+    float l[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) l[a] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NA; ++nt) {
+        const int j0 = 8 * nt + 2 * c;
+        const bool v0 = (nt < NB) && (j0 < p.n), v1 = (nt < NB) && (j0 + 1 < p.n);
+        const float e0 = v0 ? ex2_approx(sacc[mt][nt][0] - cmax) : 0.f;
+        const float e1 = v1 ? ex2_approx(sacc[mt][nt][1] - cmax) : 0.f;
+        const float e2 = v0 ? ex2_approx(sacc[mt][nt][2] - cmax) : 0.f;
+        const float e3 = v1 ? ex2_approx(sacc[mt][nt][3] - cmax) : 0.f;
+        l[2 * mt] += e0 + e1;
+        l[2 * mt + 1] += e2 + e3;
+        pimg[2 * mt][nt] = pack_bf16(e0, e1);
+        pimg[2 * mt + 1][nt] = pack_bf16(e2, e3);
+      }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) l[a] = quad_sum(l[a]);
+    // O = P V  (B operand = V^T blocks)
+    float oacc[MT][4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      uint32_t vt[NA];
+#pragma unroll
+      for (int jb = 0; jb < NA; ++jb) vt[jb] = movm_t(comp(vi[jb], nd));
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[mt][nd][e] = 0.f;
+#pragma unroll
+        for (int kj = 0; kj < MT; ++kj)
+          mma_16816(oacc[mt][nd], pimg[2 * mt][2 * kj], pimg[2 * mt + 1][2 * kj], pimg[2 * mt][2 * kj + 1],
+                    pimg[2 * mt + 1][2 * kj + 1], vt[2 * kj], vt[2 * kj + 1]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = g + 8 * a;
+      if (a < NB && r < p.n) {
+        const long long tok = tok0 + r * tstride;
+        const float il = 1.f / l[a];
+        const int mt = a >> 1, h2 = (a & 1) * 2;
+        uint4 u;
+        u.x = pack_bf16(oacc[mt][0][h2] * il, oacc[mt][0][h2 + 1] * il);
+        u.y = pack_bf16(oacc[mt][1][h2] * il, oacc[mt][1][h2 + 1] * il);
+        u.z = pack_bf16(oacc[mt][2][h2] * il, oacc[mt][2][h2 + 1] * il);
+        u.w = pack_bf16(oacc[mt][3][h2] * il, oacc[mt][3][h2 + 1] * il);
+        *reinterpret_cast<uint4*>(p.o + tok * p.ldo + head * DH + 8 * c) = u;
+        if (c == 0 && p.lse != nullptr) p.lse[tok * p.heads + head] = cmax + log2f(l[a]);
+      }
+    }
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256, 1)
+attn_short_bwd_kernel(const AttnBwdParams bp) {
+  const AttnParams& p = bp.f;
+  constexpr int MT = (NB + 1) / 2, NA = 2 * MT;
+  __shared__ float sScale[64];
+  __shared__ float sRed[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  if (tid < DH) {
+    sScale[tid] = p.q_scale[tid];
+    sScale[DH + tid] = p.k_scale[tid];
+  }
+  if (tid < 64) sRed[tid] = 0.f;
+  __syncthreads();
+  float qsr[8], ksr[8], qs[8];   // raw scales, and the folded 8 log2e q_scale of Q~
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    qsr[i] = sScale[8 * c + i];
+    ksr[i] = sScale[DH + 8 * c + i];
+    qs[i] = qsr[i] * (kScale * kLog2e);
+  }
+  float accq[8], acck[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) accq[i] = acck[i] = 0.f;
+  const long long pairs = (long long)p.num_seqs * p.heads;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (long long pair = (long long)blockIdx.x * 8 + warp; pair < pairs; pair += (long long)gridDim.x * 8) {
+    const int head = (int)(pair % p.heads);
+    long long tok0, tstride;
+    seq_origin(p, pair / p.heads, tok0, tstride);
+    uint4 qr[NA], kr[NA], vi[NA], gi[NA], qi[NA], ki[NA];   // raw q / k rows, V, dO, Q~, K^ images
+    float delta[NA], lse[NA], qinv[NA], kinv[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = g + 8 * a;
+      qr[a] = kr[a] = vi[a] = gi[a] = zero4;
+      delta[a] = 0.f;
+      lse[a] = INFINITY;   // exp2(s - inf) = 0 for rows beyond the sequence
+      if (a < NB && r < p.n) {
+        const long long tok = tok0 + r * tstride;
+        qr[a] = __ldg(reinterpret_cast<const uint4*>(p.q + tok * p.ldq + head * DH + 8 * c));
+        kr[a] = __ldg(reinterpret_cast<const uint4*>(p.kv + tok * p.ldkv + head * DH + 8 * c));
+        vi[a] = __ldg(reinterpret_cast<const uint4*>(p.kv + tok * p.ldkv + p.inner + head * DH + 8 * c));
+        gi[a] = __ldg(reinterpret_cast<const uint4*>(bp.d_o + tok * p.ldo + head * DH + 8 * c));
+        const uint4 ou = __ldg(reinterpret_cast<const uint4*>(p.o + tok * p.ldo + head * DH + 8 * c));
+        lse[a] = p.lse[tok * p.heads + head];
+        float go[8], oo[8];
+        unpack8(gi[a], go);
+        unpack8(ou, oo);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) delta[a] = fmaf(go[i], oo[i], delta[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      delta[a] = quad_sum(delta[a]);
+      qinv[a] = norm_row(qr[a], qs, qi[a]);
+      kinv[a] = norm_row(kr[a], ksr, ki[a]);
+    }
+    // S = Q~ K^T and dP = dO V^T, then p = exp2(s - lse), dz = p (dP - delta) packed as A-operand images
+    uint32_t pimg[NA][NA], dimg[NA][NA];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NA; ++nt) {
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
+        if (nt < NB) {
+#pragma unroll
+          for (int kd = 0; kd < 2; ++kd) {
+            mma_16816(sa, comp(qi[2 * mt], 2 * kd), comp(qi[2 * mt + 1], 2 * kd), comp(qi[2 * mt], 2 * kd + 1),
+                      comp(qi[2 * mt + 1], 2 * kd + 1), comp(ki[nt], 2 * kd), comp(ki[nt], 2 * kd + 1));
+            mma_16816(da, comp(gi[2 * mt], 2 * kd), comp(gi[2 * mt + 1], 2 * kd), comp(gi[2 * mt], 2 * kd + 1),
+                      comp(gi[2 * mt + 1], 2 * kd + 1), comp(vi[nt], 2 * kd), comp(vi[nt], 2 * kd + 1));
+          }
+        }
+        const int j0 = 8 * nt + 2 * c;
+        const bool v0 = (nt < NB) && (j0 < p.n), v1 = (nt < NB) && (j0 + 1 < p.n);
+        const float p0 = v0 ? ex2_approx(sa[0] - lse[2 * mt]) : 0.f;
+        const float p1 = v1 ? ex2_approx(sa[1] - lse[2 * mt]) : 0.f;
+        const float p2 = v0 ? ex2_approx(sa[2] - lse[2 * mt + 1]) : 0.f;
+        const float p3 = v1 ? ex2_approx(sa[3] - lse[2 * mt + 1]) : 0.f;
+        pimg[2 * mt][nt] = pack_bf16(p0, p1);
+        pimg[2 * mt + 1][nt] = pack_bf16(p2, p3);
+        dimg[2 * mt][nt] = pack_bf16(p0 * (da[0] - delta[2 * mt]), p1 * (da[1] - delta[2 * mt]));
+        dimg[2 * mt + 1][nt] = pack_bf16(p2 * (da[2] - delta[2 * mt + 1]), p3 * (da[3] - delta[2 * mt + 1]));
+      }
+    // ---- dQ^ = dS K^   (B operand = K^T blocks), then the l2norm / scale backward of q
+    {
+      float acc[MT][4][4];
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        uint32_t kt[NA];
+#pragma unroll
+        for (int jb = 0; jb < NA; ++jb) kt[jb] = movm_t(comp(ki[jb], nd));
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nd][e] = 0.f;
+#pragma unroll
+          for (int kj = 0; kj < MT; ++kj)
+            mma_16816(acc[mt][nd], dimg[2 * mt][2 * kj], dimg[2 * mt + 1][2 * kj], dimg[2 * mt][2 * kj + 1],
+                      dimg[2 * mt + 1][2 * kj + 1], kt[2 * kj], kt[2 * kj + 1]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int r = g + 8 * a;
+        const int mt = a >> 1, h2 = (a & 1) * 2;
+        float raw[8], gg[8], dot = 0.f;
+        unpack8(qr[a], raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dqh = acc[mt][i >> 1][h2 + (i & 1)] * kScale;   // d/dq^ = 8 dz K^
+          const float qbar = raw[i] * qinv[a];
+          accq[i] = fmaf(dqh, qbar, accq[i]);
+          gg[i] = dqh * qsr[i];
+          dot = fmaf(gg[i], qbar, dot);
+        }
+        dot = quad_sum(dot);
+        if (a < NB && r < p.n) {
+          const long long tok = tok0 + r * tstride;
+          float o8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = (gg[i] - raw[i] * qinv[a] * dot) * qinv[a];
+          *reinterpret_cast<uint4*>(bp.dq + tok * p.ldq + head * DH + 8 * c) =
+              make_uint4(pack_bf16(o8[0], o8[1]), pack_bf16(o8[2], o8[3]), pack_bf16(o8[4], o8[5]), pack_bf16(o8[6], o8[7]));
+        }
+      }
+    }
+    // ---- dV = P^T dO and dK^ = dS^T Q~   (A operands = transposed P / dS blocks, B operands = dO^T / Q~^T blocks)
+    {
+      uint32_t pt[NA][NA], dt[NA][NA];   // [key block][query block]
+#pragma unroll
+      for (int jb = 0; jb < NA; ++jb)
+#pragma unroll
+        for (int ib = 0; ib < NA; ++ib) {
+          pt[jb][ib] = movm_t(pimg[ib][jb]);
+          dt[jb][ib] = movm_t(dimg[ib][jb]);
+        }
+      float av[MT][4][4], ak[MT][4][4];
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        uint32_t gt[NA], qt[NA];
+#pragma unroll
+        for (int ib = 0; ib < NA; ++ib) {
+          gt[ib] = movm_t(comp(gi[ib], nd));
+          qt[ib] = movm_t(comp(qi[ib], nd));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) av[mt][nd][e] = ak[mt][nd][e] = 0.f;
+#pragma unroll
+          for (int kq = 0; kq < MT; ++kq) {
+            mma_16816(av[mt][nd], pt[2 * mt][2 * kq], pt[2 * mt + 1][2 * kq], pt[2 * mt][2 * kq + 1],
+                      pt[2 * mt + 1][2 * kq + 1], gt[2 * kq], gt[2 * kq + 1]);
+            mma_16816(ak[mt][nd], dt[2 * mt][2 * kq], dt[2 * mt + 1][2 * kq], dt[2 * mt][2 * kq + 1],
+                      dt[2 * mt + 1][2 * kq + 1], qt[2 * kq], qt[2 * kq + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int r = g + 8 * a;
+        const int mt = a >> 1, h2 = (a & 1) * 2;
+        // k^ = ks * k / |k| : dk = (g - kbar (kbar.g)) / |k|, g = ks * dk^ ; dks += dk^ * kbar
+        float raw[8], gg[8], dot = 0.f;
+        unpack8(kr[a], raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dkh = ak[mt][i >> 1][h2 + (i & 1)] * (1.f / kLog2e);
+          const float kbar = raw[i] * kinv[a];
+          acck[i] = fmaf(dkh, kbar, acck[i]);
+          gg[i] = dkh * ksr[i];
+          dot = fmaf(gg[i], kbar, dot);
+        }
+        dot = quad_sum(dot);
+        if (a < NB && r < p.n) {
+          const long long tok = tok0 + r * tstride;
+          float o8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = (gg[i] - raw[i] * kinv[a] * dot) * kinv[a];
+          *reinterpret_cast<uint4*>(bp.dkv + tok * p.ldkv + head * DH + 8 * c) =
+              make_uint4(pack_bf16(o8[0], o8[1]), pack_bf16(o8[2], o8[3]), pack_bf16(o8[4], o8[5]), pack_bf16(o8[6], o8[7]));
+          *reinterpret_cast<uint4*>(bp.dkv + tok * p.ldkv + p.inner + head * DH + 8 * c) =
+              make_uint4(pack_bf16(av[mt][0][h2], av[mt][0][h2 + 1]), pack_bf16(av[mt][1][h2], av[mt][1][h2 + 1]),
+                         pack_bf16(av[mt][2][h2], av[mt][2][h2 + 1]), pack_bf16(av[mt][3][h2], av[mt][3][h2 + 1]));
+        }
+      }
+    }
+  }
+  // scale gradients: sum over the eight row groups of the warp, then over the warps of the CTA, one atomic per column
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {
+      accq[i] += __shfl_xor_sync(0xffffffffu, accq[i], m);
+      acck[i] += __shfl_xor_sync(0xffffffffu, acck[i], m);
+    }
+    if (g == 0) {
+      atomicAdd(&sRed[8 * c + i], accq[i]);
+      atomicAdd(&sRed[DH + 8 * c + i], acck[i]);
+    }
+  }
+  __syncthreads();
+  if (tid < DH) {
+    if (bp.dq_scale != nullptr) atomicAdd(bp.dq_scale + tid, sRed[tid]);
+    if (bp.dk_scale != nullptr) atomicAdd(bp.dk_scale + tid, sRed[DH + tid]);
+  }
+}
+
+// the short-sequence kernels apply to bias-free attention with n <= 32 (CTCLIP_ATTN_SHORT=0 forces the tcgen05 kernels)
+bool use_short(const AttnParams& p) {
+  const char* e = getenv("CTCLIP_ATTN_SHORT");   // read per call: the tests compare both paths in one process
+  return !(e != nullptr && e[0] == '0') && p.bias_table == nullptr && p.n <= 32;
+}
+unsigned short_grid(const AttnParams& p, int ctas_per_sm) {
+  const long long pairs = (long long)p.num_seqs * p.heads;
+  long long ctas = (pairs + 7) / 8;
+  const long long cap = (long long)ctclip::sm_count() * ctas_per_sm;
+  return (unsigned)(ctas < cap ? ctas : cap);
+}
+
 size_t bwd_smem_bytes(const AttnParams& p) {
   const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
   return (size_t)QT * DH * 2 * 6 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
@@ -923,6 +1319,16 @@ extern "C" int ctclip_attn_fwd(const ctclip_attn_desc* d, void* stream) {
   if (rc) return rc;
   p.q = (const __nv_bfloat16*)d->q; p.kv = (const __nv_bfloat16*)d->kv; p.o = (__nv_bfloat16*)d->o; p.lse = d->lse;
   if (!p.q || !p.kv || !p.o) return ctclip::fail(CTCLIP_E_SHAPE, "attn_fwd: null pointer");
+  if (use_short(p)) {
+    const unsigned grid = short_grid(p, 2);
+    switch ((p.n + 7) / 8) {
+      case 1: attn_short_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p); break;
+      case 2: attn_short_fwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(p); break;
+      case 3: attn_short_fwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(p); break;
+      default: attn_short_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(p); break;
+    }
+    return ctclip::check_launch("attn_fwd(short)");
+  }
   const size_t smem = fwd_smem_bytes(p);
   if (smem > 227 * 1024) return ctclip::fail(CTCLIP_E_SHAPE, "attn_fwd: sequence too long for shared memory (%zu B)", smem);
   static size_t configured = 0;
@@ -951,6 +1357,16 @@ extern "C" int ctclip_attn_bwd(const ctclip_attn_desc* d, void* stream) {
   bp.dq_scale = d->dq_scale; bp.dk_scale = d->dk_scale; bp.dbias_table = d->dbias_table;
   if (!p.q || !p.kv || !p.o || !p.lse || !bp.d_o || !bp.dq || !bp.dkv)
     return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: null pointer");
+  if (use_short(p)) {
+    const unsigned grid = short_grid(p, 1);
+    switch ((p.n + 7) / 8) {
+      case 1: attn_short_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(bp); break;
+      case 2: attn_short_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(bp); break;
+      case 3: attn_short_bwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(bp); break;
+      default: attn_short_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(bp); break;
+    }
+    return ctclip::check_launch("attn_bwd(short)");
+  }
   if (p.r_pad / QT > 6) return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: sequences longer than 768 tokens are not supported");
   const size_t smem = bwd_smem_bytes(p);
   if (smem > 227 * 1024) return ctclip::fail(CTCLIP_E_SHAPE, "attn_bwd: sequence too long for shared memory (%zu B)", smem);

@@ -69,6 +69,11 @@ __device__ __forceinline__ void store_row_chunk(const GemmKernelParams& p, int r
   if (p.c_is_f32) {
     float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
     if (p.atomic) {
+      if (ncols == 32 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red_add_v4(c + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < ncols) atomicAdd(c + j, v[j]);
@@ -156,7 +161,7 @@ __device__ __forceinline__ void store_chunk_coalesced(const GemmKernelParams& p,
       if (grow < p.M) {
         float* c = reinterpret_cast<float*>(p.C) + (long long)grow * p.ldc + col0 + c8 * 4;
         if (p.atomic) {
-          atomicAdd(c + 0, x.x); atomicAdd(c + 1, x.y); atomicAdd(c + 2, x.z); atomicAdd(c + 3, x.w);
+          red_add_v4(c, x.x, x.y, x.z, x.w);
         } else {
           *reinterpret_cast<float4*>(c) = x;
         }
@@ -638,20 +643,16 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   if (splits <= 0) {  // auto: only when the caller allows atomic accumulation
     splits = 1;
     if (d->atomic) {
-      // fill whole waves of SMs: the smallest split count whose last wave is (nearly) as full as the best one; each
-      // split keeps >= 8 k-blocks so that the fp32 atomic epilogue stays a small fraction of its work
-      int max_splits = kp.kb_total / 8 > 0 ? kp.kb_total / 8 : 1;
-      if (max_splits > 64) max_splits = 64;
-      double best = 0.0;
+      // cost model in k-block units: the persistent CTAs take ceil(units / SMs) work units each; a unit is its share of the
+      // k-blocks plus a fixed cost (pipeline fill + the vector-RED epilogue of a 128 x BN fp32 tile ~ 8 k-blocks of MMA time)
+      int max_splits = kp.kb_total < 128 ? kp.kb_total : 128;
+      const long long kFixed = 8;
+      long long best_cost = -1;
       for (int sp = 1; sp <= max_splits; ++sp) {
         const long long units = (long long)tiles * sp;
-        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
-        if (eff > best) best = eff;
-      }
-      for (int sp = 1; sp <= max_splits; ++sp) {
-        const long long units = (long long)tiles * sp;
-        const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
-        if (eff >= 0.97 * best) { splits = sp; break; }
+        const long long waves = (units + sms - 1) / sms;
+        const long long cost = waves * ((kp.kb_total + sp - 1) / sp + kFixed);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
       }
     }
   }

@@ -40,6 +40,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 // 2^x on the MUFU pipe, flush-to-zero: one instruction (exp2f() adds a denormal-range fix-up around it)
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): one L2 operation per four fp32 atomic adds
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

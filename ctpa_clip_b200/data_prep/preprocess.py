@@ -67,3 +67,17 @@ def inference_loader_volume(img_data, target_shape=TARGET_SHAPE):
     Returns (1, 240, 480, 480)."""
     x = _as_f32_cuda(img_data)
     return ops.prep_resample(x[None], x.shape, layout="dhw", target=target_shape, pad_value=-1.0, pre_op="infer_window")
+
+
+def resample_to_target(image_tensor, target_depth=240, target_size=480):
+    """The report generator's direct-to-target resample (ctpa_report/vqa_meditron.py:165-175, ct_scan_inference.py:50-55,
+    data_utils.py:54-59): F.interpolate((C, D, H, W)[None], size=(240, 480, 480), mode='trilinear', align_corners=False)[0]
+    on the GPU; a volume already at the target size is returned unchanged, like the reference."""
+    if image_tensor.dim() == 3:
+        image_tensor = image_tensor[None]
+    C, D, H, W = image_tensor.shape
+    tgt = (target_depth, target_size, target_size)
+    x = image_tensor.to(device="cuda", dtype=torch.float32).contiguous()
+    if (D, H, W) == tgt:
+        return x
+    return ops.prep_resample(x, tgt, layout="dhw")

@@ -200,7 +200,8 @@ def _attn_ref(q, kv, grid, heads, temporal, qs, ks, bias):
     return out.reshape(-1, inner)
 
 
-@pytest.mark.parametrize("grid,heads", [((2, 5, 4, 4), 2), ((2, 6, 6, 6), 4), ((1, 24, 24, 24), 8), ((2, 3, 13, 11), 1)])
+@pytest.mark.parametrize("grid,heads", [((2, 5, 4, 4), 2), ((2, 6, 6, 6), 4), ((1, 24, 24, 24), 8), ((2, 3, 13, 11), 1),
+                                        ((1, 12, 5, 5), 2), ((1, 30, 3, 4), 3), ((1, 40, 3, 3), 2)])
 @pytest.mark.parametrize("temporal", [False, True])
 def test_attention_fwd_bwd(ops, grid, heads, temporal):
     b, t, h, w = grid
@@ -221,6 +222,24 @@ def test_attention_fwd_bwd(ops, grid, heads, temporal):
     if not temporal:
         ref_dtab = torch.zeros_like(tab).index_add_(1, idx.reshape(-1), fullr.grad.reshape(heads, -1))
         close(dtab, ref_dtab, 2e-2)
+
+
+@pytest.mark.parametrize("t", [3, 12, 24, 31])
+def test_short_sequence_attention_equals_tcgen05_path(ops, t, monkeypatch):
+    """temporal attention (n <= 32, no bias) runs on the one-warp-per-(sequence, head) mma.sync kernels; the tcgen05 kernels
+    (CTCLIP_ATTN_SHORT=0) compute the same function with the same bf16 operand rounding"""
+    grid, heads = (2, t, 5, 3), 4
+    q, kv, qs, ks, tab, idx = _attn_inputs(grid, heads, 40 + t)
+    d_o = torch.randn(q.shape[0], heads * 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).bfloat16()
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("CTCLIP_ATTN_SHORT", flag)
+        o, lse = ops.attn_fwd(q, kv, grid, heads, True, qs, ks, None, None)
+        dqs, dks = torch.zeros(32, device="cuda"), torch.zeros(32, device="cuda")
+        dq, dkv = ops.attn_bwd(q, kv, o, lse, d_o, grid, heads, True, qs, ks, dqs, dks, None, None, None)
+        res.append((o, lse, dq, dkv, dqs, dks))
+    for a, b2, tol in zip(res[0], res[1], (1e-2, 1e-3, 1.5e-2, 1.5e-2, 1e-2, 1e-2)):
+        close(a, b2, tol)
 
 
 def test_attention_large_bias_spread_does_not_underflow(ops):
@@ -430,3 +449,15 @@ def test_training_loader_volume_full_size_equals_oracle(ops):
 def test_loader_ops_reject_int16_input(ops):
     with pytest.raises(Exception):
         ops.prep_resample(torch.zeros(1, 8, 8, 8, dtype=torch.int16, device="cuda"), (8, 8, 8), hu=(1.0, 0.0), post_op="clip_div")
+
+
+def test_resample_to_target_equals_oracle(ops):
+    """a15: direct (C, D, H, W) -> (C, 240, 480, 480) trilinear resample of the report generator, two channels, mixed up / down"""
+    from ctpa_clip_b200.data_prep import resample_to_target
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 150, 300, 512), dtype=np.float32)
+    got = resample_to_target(torch.from_numpy(x)).cpu().numpy()
+    assert got.shape == (2, 240, 480, 480)
+    for c in range(2):
+        want = R.trilinear(x[c], (240, 480, 480))
+        assert (got[c].view(np.int32) == want.view(np.int32)).all()
