@@ -203,10 +203,9 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ GELU (erf)
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_df(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
+__device__ __forceinline__ float gelu_f(float x) { return gelu_fast(x); }
+__device__ __forceinline__ float gelu_df(float x) { return gelu_grad_fast(x); }
+
 __global__ void __launch_bounds__(256)
 gelu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long nvec) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {

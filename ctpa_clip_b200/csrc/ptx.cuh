@@ -40,6 +40,33 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 // 2^x on the MUFU pipe, flush-to-zero: one instruction (exp2f() adds a denormal-range fix-up around it)
+// exact-erf GELU (F.gelu default) and its derivative from ONE exponential: erf(x) = 1 - poly(t) e^{-x^2}, t = 1 / (1 + p x)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 absolute — three orders below the bf16 resolution of the outputs), and
+// e^{-x^2} with x = |g| / sqrt(2) is also the Gaussian of the derivative. ~14 instructions, 2 MUFU, no branches.
+__device__ __forceinline__ void gelu_parts(float g, float& cdf, float& pdf_g) {
+  const float x = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-x * x * 1.4426950408889634f));   // exp(-g^2 / 2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_tail = 0.5f * poly * t * ex;            // 0.5 * (1 - erf(|x|))
+  cdf = g >= 0.f ? 1.f - half_tail : half_tail;            // Phi(g) = 0.5 (1 + erf(g / sqrt 2))
+  pdf_g = g * 0.3989422804014327f * ex;                    // g * phi(g)
+}
+__device__ __forceinline__ float gelu_fast(float g) {
+  float cdf, pg;
+  gelu_parts(g, cdf, pg);
+  return g * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float g) {
+  float cdf, pg;
+  gelu_parts(g, cdf, pg);
+  return cdf + pg;
+}
+
 // 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): one L2 operation per four fp32 atomic adds
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -83,8 +83,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int dim, const
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx_out = (add_in ? add_in : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy  (fp32 atomics, one per column per block)
-template <int kMaxVec, bool DY_BF16>
-__global__ void __launch_bounds__(256)
+template <int kMaxVec, bool DY_BF16, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x, long long rows, int dim,
                      const float* __restrict__ gamma, float eps, const float* __restrict__ add_in,
                      float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
@@ -104,7 +104,6 @@ layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x,
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
     float4 v[kMaxVec], d[kMaxVec];
-    float s = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
       const int i = lane + 32 * j;
@@ -116,47 +115,54 @@ layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x,
         } else {
           d[j] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_v) + row * dim)[i];
         }
-        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
     }
-    const float mean = warp_sum(s) / dim;
-    float q = 0.f;
+    // ONE reduction round for the four row sums. The statistics are taken about x0 = the row's first element (a sample of
+    // the row, so |mean - x0| ~ std): sum(x - x0), sum((x - x0)^2) give mean and variance without cancellation, and
+    // sum(g xhat) = rstd (sum(g (x - x0)) - (mean - x0) sum(g)),  g = dy * gamma.
+    const float x0 = __shfl_sync(0xffffffffu, v[0].x, 0);
+    float s1 = 0.f, s2 = 0.f, sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
       const int i = lane + 32 * j;
       if (i < nvec) {
-        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
-        q += (a * a + b * b) + (c * c + e * e);
+        v[j].x -= x0; v[j].y -= x0; v[j].z -= x0; v[j].w -= x0;
+        s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        s2 += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        const float gx = d[j].x * gm.x, gy = d[j].y * gm.y, gz = d[j].z * gm.z, gw = d[j].w * gm.w;
+        sg += (gx + gy) + (gz + gw);
+        sgx += (gx * v[j].x + gy * v[j].y) + (gz * v[j].z + gw * v[j].w);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
-    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+      sg += __shfl_xor_sync(0xffffffffu, sg, m);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, m);
+    }
+    asm volatile("" ::: "memory");   // gamma is re-read (L1) below instead of living in 16 registers across the reduction
+    const float inv_dim = 1.f / dim;
+    const float m0 = s1 * inv_dim;                                     // mean - x0
+    const float rstd = rsqrtf(fmaxf(s2 * inv_dim - m0 * m0, 0.f) + eps);
+    const float mg = sg * inv_dim, mgx = rstd * (sgx - m0 * sg) * inv_dim;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
       const int i = lane + 32 * j;
       if (i < nvec) {
-        const float4 g = reinterpret_cast<const float4*>(gamma)[i];
-        // v <- xhat ; d stays dy ; accumulate parameter grads
-        v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd;
-        v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
+        // v <- xhat ; accumulate parameter grads ; dx
+        v[j].x = (v[j].x - m0) * rstd; v[j].y = (v[j].y - m0) * rstd;
+        v[j].z = (v[j].z - m0) * rstd; v[j].w = (v[j].w - m0) * rstd;
         acc_g[j].x += d[j].x * v[j].x; acc_g[j].y += d[j].y * v[j].y;
         acc_g[j].z += d[j].z * v[j].z; acc_g[j].w += d[j].w * v[j].w;
         acc_b[j].x += d[j].x; acc_b[j].y += d[j].y; acc_b[j].z += d[j].z; acc_b[j].w += d[j].w;
-        d[j].x *= g.x; d[j].y *= g.y; d[j].z *= g.z; d[j].w *= g.w;  // g = dy * gamma
-        sg += (d[j].x + d[j].y) + (d[j].z + d[j].w);
-        sgx += (d[j].x * v[j].x + d[j].y * v[j].y) + (d[j].z * v[j].z + d[j].w * v[j].w);
-      }
-    }
-    const float mg = warp_sum(sg) / dim, mgx = warp_sum(sgx) / dim;
-#pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
         float4 o;
-        o.x = rstd * (d[j].x - mg - v[j].x * mgx);
-        o.y = rstd * (d[j].y - mg - v[j].y * mgx);
-        o.z = rstd * (d[j].z - mg - v[j].z * mgx);
-        o.w = rstd * (d[j].w - mg - v[j].w * mgx);
+        o.x = rstd * (d[j].x * gm.x - mg - v[j].x * mgx);
+        o.y = rstd * (d[j].y * gm.y - mg - v[j].y * mgx);
+        o.z = rstd * (d[j].z * gm.z - mg - v[j].z * mgx);
+        o.w = rstd * (d[j].w * gm.w - mg - v[j].w * mgx);
         if (add_in != nullptr) {
           const float4 a = reinterpret_cast<const float4*>(add_in + row * dim)[i];
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -190,27 +196,23 @@ layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------------------------------ GEGLU
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float g) {
-  return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
-}
-
 // h: [rows][2*ld_half] bf16 = [x | gate];  u: [rows][ld_half] bf16 = x * gelu(gate)
 __global__ void __launch_bounds__(256)
 geglu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ u, long long rows, int half_vec /* ld_half/8 */) {
-  const long long total = rows * half_vec;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / half_vec;
-    const int c = (int)(idx - row * half_vec);
-    const uint4 xv = h[row * 2 * half_vec + c];
-    const uint4 gv = h[row * 2 * half_vec + half_vec + c];
+  // 32-bit index arithmetic (the host checks rows * half_vec < 2^31): a 64-bit division per vector costs more than the GELUs
+  const unsigned total = (unsigned)(rows * half_vec), hv = (unsigned)half_vec;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned row = idx / hv;
+    const unsigned c = idx - row * hv;
+    const uint4* hr = h + (size_t)row * 2 * hv + c;
+    const uint4 xv = hr[0];
+    const uint4 gv = hr[hv];
     const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      o[k] = ptx::pack_bf16(ptx::bf16_lo(xs[k]) * gelu_erf(ptx::bf16_lo(gs[k])),
-                            ptx::bf16_hi(xs[k]) * gelu_erf(ptx::bf16_hi(gs[k])));
+      o[k] = ptx::pack_bf16(ptx::bf16_lo(xs[k]) * ptx::gelu_fast(ptx::bf16_lo(gs[k])),
+                            ptx::bf16_hi(xs[k]) * ptx::gelu_fast(ptx::bf16_hi(gs[k])));
     u[idx] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -219,13 +221,13 @@ geglu_fwd_kernel(const uint4* __restrict__ h, uint4* __restrict__ u, long long r
 __global__ void __launch_bounds__(256)
 geglu_bwd_kernel(const uint4* __restrict__ h, const uint4* __restrict__ du, uint4* __restrict__ dh, long long rows,
                  int half_vec) {
-  const long long total = rows * half_vec;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / half_vec;
-    const int c = (int)(idx - row * half_vec);
-    const uint4 xv = h[row * 2 * half_vec + c];
-    const uint4 gv = h[row * 2 * half_vec + half_vec + c];
+  const unsigned total = (unsigned)(rows * half_vec), hv = (unsigned)half_vec;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned row = idx / hv;
+    const unsigned c = idx - row * hv;
+    const uint4* hr = h + (size_t)row * 2 * hv + c;
+    const uint4 xv = hr[0];
+    const uint4 gv = hr[hv];
     const uint4 dv = du[idx];
     const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w},
                    ds[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -235,11 +237,15 @@ geglu_bwd_kernel(const uint4* __restrict__ h, const uint4* __restrict__ du, uint
       const float x0 = ptx::bf16_lo(xs[k]), x1 = ptx::bf16_hi(xs[k]);
       const float g0 = ptx::bf16_lo(gs[k]), g1 = ptx::bf16_hi(gs[k]);
       const float d0 = ptx::bf16_lo(ds[k]), d1 = ptx::bf16_hi(ds[k]);
-      ox[k] = ptx::pack_bf16(d0 * gelu_erf(g0), d1 * gelu_erf(g1));
-      og[k] = ptx::pack_bf16(d0 * x0 * gelu_erf_grad(g0), d1 * x1 * gelu_erf_grad(g1));
+      float c0, p0, c1, p1;
+      ptx::gelu_parts(g0, c0, p0);
+      ptx::gelu_parts(g1, c1, p1);
+      ox[k] = ptx::pack_bf16(d0 * (g0 * c0), d1 * (g1 * c1));
+      og[k] = ptx::pack_bf16(d0 * x0 * (c0 + p0), d1 * x1 * (c1 + p1));
     }
-    dh[row * 2 * half_vec + c] = make_uint4(ox[0], ox[1], ox[2], ox[3]);
-    dh[row * 2 * half_vec + half_vec + c] = make_uint4(og[0], og[1], og[2], og[3]);
+    uint4* dr = dh + (size_t)row * 2 * hv + c;
+    dr[0] = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+    dr[hv] = make_uint4(og[0], og[1], og[2], og[3]);
   }
 }
 
@@ -292,23 +298,24 @@ extern "C" int ctclip_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
   int rc = ctclip::require_sm100();
   if (rc) return rc;
   long long blocks = (rows + 63) / 64;  // each warp walks >= 8 rows so the column reductions amortise
-  const long long cap = (long long)ctclip::sm_count() * 8;
+  // one resident wave (3 CTAs / SM at <= 80 registers for dim <= 512): the column-sum flush happens once per CTA
+  const long long cap = (long long)ctclip::sm_count() * 3;
   if (blocks > cap) blocks = cap;
   const int nv = (dim + 127) / 128;
   const size_t sm = 2 * dim * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
-#define LN_BWD(V)                                                                                                      \
+#define LN_BWD(V, MB)                                                                                                      \
   do {                                                                                                                 \
     if (dy_is_bf16)                                                                                                    \
-      layernorm_bwd_kernel<V, true><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);  \
+      layernorm_bwd_kernel<V, true, MB><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta);  \
     else                                                                                                               \
-      layernorm_bwd_kernel<V, false><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta); \
+      layernorm_bwd_kernel<V, false, MB><<<(int)blocks, 256, sm, s>>>(dy, x, rows, dim, gamma, eps, add_in, dx_out, db, dgamma, dbeta); \
   } while (0)
-  if (nv <= 1) LN_BWD(1);
-  else if (nv <= 2) LN_BWD(2);
-  else if (nv <= 4) LN_BWD(4);
-  else LN_BWD(8);
+  if (nv <= 1) LN_BWD(1, 3);
+  else if (nv <= 2) LN_BWD(2, 3);
+  else if (nv <= 4) LN_BWD(4, 3);
+  else LN_BWD(8, 1);
 #undef LN_BWD
   return ctclip::check_launch("layernorm_bwd");
 }
@@ -318,6 +325,7 @@ extern "C" int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_h
   if (ld_half % 8 || ld_half <= 0) return ctclip::fail(CTCLIP_E_ALIGN, "geglu_fwd: ld_half must be a multiple of 8");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
+  if (rows * (ld_half / 8) >= (1LL << 31)) return ctclip::fail(CTCLIP_E_SHAPE, "geglu_fwd: more than 2^31 vectors");
   geglu_fwd_kernel<<<grid_for(rows * (ld_half / 8), 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)h, (uint4*)u, rows, ld_half / 8);
   return ctclip::check_launch("geglu_fwd");
@@ -328,6 +336,7 @@ extern "C" int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long lo
   if (ld_half % 8 || ld_half <= 0) return ctclip::fail(CTCLIP_E_ALIGN, "geglu_bwd: ld_half must be a multiple of 8");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
+  if (rows * (ld_half / 8) >= (1LL << 31)) return ctclip::fail(CTCLIP_E_SHAPE, "geglu_bwd: more than 2^31 vectors");
   geglu_bwd_kernel<<<grid_for(rows * (ld_half / 8), 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)h, (const uint4*)du, (uint4*)dh, rows, ld_half / 8);
   return ctclip::check_launch("geglu_bwd");
