@@ -434,6 +434,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         pz.C = p.c_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.C) + off)
                           : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
       }
+      if (fast_mode == 3 || fast_mode == 5) {
+        // The residual rows of the NEXT work unit start their way from HBM into L2 now (no registers held): one tile
+        // epilogue later the loads below are L2 hits, so the few loads a warp keeps in flight no longer bound the bandwidth
+        auto prefetch_resid = [&](int wq) {
+          const int prow = tile_m(wq) * BM + ew * 32 + lane;
+          const int pcol = (wq % p.n_tiles) * BN + ch * kHalf;
+          if (prow < p.M) {
+            const char* base = reinterpret_cast<const char*>(p.resid + (long long)prow * p.ldr + pcol);
+#pragma unroll
+            for (int k = 0; k < kHalf / 32; ++k)
+              if (pcol + k * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + k * 128));
+          }
+        };
+        if (w == w_first) prefetch_resid(w);
+        if (w + w_stride < num_work) prefetch_resid(w + w_stride);
+      }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const int row = m_t * BM + ew * 32 + lane;
