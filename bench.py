@@ -266,6 +266,16 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # DRAM bytes per GEMM launch: NOT measured in this run (a profiler is never attached to a bench run) — the committed ncu
+    # metrics pass over one identical training step (tools/step_traffic.py -> profiles/r01_step_traffic.json)
+    traffic, traffic_note = None, "profiles/r01_step_traffic.json not found"
+    tpath = Path(__file__).resolve().parent / "profiles" / "r01_step_traffic.json"
+    if tpath.exists():
+        tj = json.loads(tpath.read_text())["gemm"]
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = (f"bytes per launch: dram__bytes_read+write summed over the {tj['launches']} gemm_bf16_kernel launches of one "
+                        f"step / launches, from the committed ncu pass profiles/r01_step_traffic.json "
+                        f"(GEMM share of that serialised step: {tj['share_of_step']:.3f})")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,7 +292,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "achieved_tflops_step": world * B * TRAIN_GF_PER_VOLUME / (ms_step * 1e-3) / 1e3 / world,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": achieved / tf_peak if tf_peak else None, "traffic": None,
+                     "frac": achieved / tf_peak if tf_peak else None, "traffic": traffic, "traffic_note": traffic_note,
                      "kernel": "gemm_bf16_kernel (tcgen05): all launches of one step, algorithmic (un-padded) FLOPs / "
                                "summed CUDA-event durations", "peak_source": peak_src,
                      "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None},
