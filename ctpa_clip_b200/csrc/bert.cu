@@ -269,6 +269,12 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int dim,
   }
 }
 
+__global__ void __launch_bounds__(256)
+colsum_bf16_tile_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int dim, long long ld, float* __restrict__ out,
+                        int rows_per_block) {
+  colsum_tile<__nv_bfloat16>(x, rows, dim, ld, out, rows_per_block);
+}
+
 int grid_for(long long n, int per_block) {
   long long b = (n + per_block - 1) / per_block;
   const long long cap = (long long)ctclip::sm_count() * 16;
@@ -370,6 +376,14 @@ extern "C" int ctclip_colsum_bf16(const void* x, long long rows, int dim, long l
   if ((dim % 2) || (ld % 2)) return ctclip::fail(CTCLIP_E_ALIGN, "colsum_bf16: dim and ld must be even");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
+  if (dim % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int bx = (dim / 8 + 255) / 256;
+    long long rpb8 = rows * bx / (2LL * ctclip::sm_count());   // about two CTAs per SM
+    rpb8 = rpb8 < 8 ? 8 : (rpb8 > 64 ? 64 : rpb8 / 8 * 8);
+    dim3 grid((unsigned)bx, (unsigned)((rows + rpb8 - 1) / rpb8));
+    colsum_bf16_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, dim, ld, out, (int)rpb8);
+    return ctclip::check_launch("colsum_bf16");
+  }
   int rpb = 8;   // rows per block: enough blocks to fill the chip even for a few thousand rows
   long long blocks = (rows + rpb - 1) / rpb;
   const long long cap = (long long)ctclip::sm_count() * 16;

@@ -71,6 +71,43 @@ __device__ __forceinline__ float gelu_grad_fast(float g) {
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// out[c] += sum over a chunk of rows of x[row][c]: 16-byte loads along the row (4 fp32 / 8 bf16 columns per thread), eight
+// independent loads in flight per thread, one 16-byte RED per thread at the end. grid = (column tiles of 256 threads, row chunks)
+template <typename T>
+__device__ __forceinline__ void colsum_tile(const T* __restrict__ x, long long rows, int dim, long long ld,
+                                            float* __restrict__ out, int rows_per_block) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (c0 >= dim) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (long long r = r0; r < r1; r += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (r + k < r1) ? __ldg(reinterpret_cast<const uint4*>(x + (r + k) * ld + c0)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (sizeof(T) == 4) {
+        acc[0] += __uint_as_float(v[k].x); acc[1] += __uint_as_float(v[k].y);
+        acc[2] += __uint_as_float(v[k].z); acc[3] += __uint_as_float(v[k].w);
+      } else {
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[(2 * e) % VEC] += __uint_as_float(w[e] << 16);
+          acc[(2 * e + 1) % VEC] += __uint_as_float(w[e] & 0xFFFF0000u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; i += 4) red_add_v4(out + c0 + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -363,12 +363,24 @@ colsum_kernel(const float* __restrict__ x, long long rows, int dim, float* __res
     atomicAdd(out + c, s);
   }
 }
+__global__ void __launch_bounds__(256)
+colsum_tile_kernel(const float* __restrict__ x, long long rows, int dim, float* __restrict__ out, int rows_per_block) {
+  ptx::colsum_tile<float>(x, rows, dim, dim, out, rows_per_block);
+}
 }  // namespace
 
 extern "C" int ctclip_colsum(const float* x, long long rows, int dim, float* out, void* stream) {
   if (rows <= 0 || dim <= 0) return CTCLIP_OK;
   int rc = ctclip::require_sm100();
   if (rc) return rc;
+  if (dim % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int bx = (dim / 4 + 255) / 256;
+    long long rpb8 = rows * bx / (2LL * ctclip::sm_count());   // about two CTAs per SM
+    rpb8 = rpb8 < 8 ? 8 : (rpb8 > 64 ? 64 : rpb8 / 8 * 8);
+    dim3 grid((unsigned)bx, (unsigned)((rows + rpb8 - 1) / rpb8));
+    colsum_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, out, (int)rpb8);
+    return ctclip::check_launch("colsum");
+  }
   int rpb = 64;
   long long blocks = (rows + rpb - 1) / rpb;
   const long long cap = (long long)ctclip::sm_count() * 8;

@@ -461,3 +461,22 @@ def test_resample_to_target_equals_oracle(ops):
     for c in range(2):
         want = R.trilinear(x[c], (240, 480, 480))
         assert (got[c].view(np.int32) == want.view(np.int32)).all()
+
+
+@pytest.mark.parametrize("rows,dim", [(4096, 768), (4096, 3072), (1000, 512), (37, 20), (5, 6)])
+def test_column_sums(ops, rows, dim):
+    """bias-gradient column sums (fp32 and bf16 inputs, tiled 16-byte path and the scalar fallback), accumulated in place"""
+    g = torch.Generator(device="cuda").manual_seed(rows + dim)
+    x = torch.randn(rows, dim, device="cuda", generator=g)
+    out = torch.ones(dim, device="cuda")
+    ops.colsum(x, out)
+    close(out, 1 + x.double().sum(0).float(), 2e-5)
+    xb = x.bfloat16()
+    outb = torch.zeros(dim, device="cuda")
+    ops.colsum_bf16(xb, outb)
+    close(outb, xb.double().sum(0).float(), 2e-5)
+    if dim % 3 == 0:                                  # a column slice of a packed [rows, 3 * d] matrix (BERT q / k / v biases)
+        d = dim // 3
+        outs = torch.zeros(d, device="cuda")
+        ops.colsum_bf16(xb[:, d:2 * d], outs, dim=d, ld=dim)
+        close(outs, xb[:, d:2 * d].double().sum(0).float(), 2e-5)
