@@ -64,6 +64,29 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo, uint3
   return d;
 }
 
+// The same descriptor as two 32-bit words: only the low word depends on the address, so the MMA-issuing thread derives
+// every descriptor of a step from a few base words with one 32-bit add each (byte offset >> 4; shared memory addresses
+// stay below 2^18, no carry out of the 14-bit field) instead of rebuilding 64-bit descriptors per instruction.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) {
+  return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // byte offset of the 16-byte group (row r, column group c8) in a core-matrix tile with `cols` columns
 __device__ __forceinline__ uint32_t cm_off(int r, int c8, int cols) {
   return (uint32_t)((r >> 3) * (cols >> 3) * 128 + c8 * 128 + (r & 7) * 16);
@@ -256,18 +279,18 @@ attn_fwd_kernel(const AttnParams p) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k)
-        mma_f16_ss(tS, desc_nosw(smem_u32(sQ) + k * 256, 128, 512), desc_nosw(smem_u32(sK) + k * 256, 128, 512),
-                   idesc_s, k > 0);
+        mma_lohi(tS, desc_lo(smem_u32(sQ), 128) + k * 16, desc_hi(512), desc_lo(smem_u32(sK), 128) + k * 16, desc_hi(512),
+                 idesc_s, k > 0);
       mma_commit(bars + 0);
     }
     for (int c = 0; c < nchunks; ++c) {
       // S of the NEXT chunk is issued before this chunk is processed (its TMEM buffer was drained one chunk ago)
       if (tid == 0 && c + 1 < nchunks) {
         const uint32_t tSn = tS + ((c + 1) & 1) * KC;
+        const uint32_t kn_lo = desc_lo(smem_u32(sK) + (c + 1) * KC * (DH * 2), 128);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          mma_f16_ss(tSn, desc_nosw(smem_u32(sQ) + k * 256, 128, 512),
-                     desc_nosw(smem_u32(sK) + (c + 1) * KC * (DH * 2) + k * 256, 128, 512), idesc_s, k > 0);
+          mma_lohi(tSn, desc_lo(smem_u32(sQ), 128) + k * 16, desc_hi(512), kn_lo + k * 16, desc_hi(512), idesc_s, k > 0);
         mma_commit(bars + ((c + 1) & 1));
       }
       if (c & 1) { mbar_wait(bars + 1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bars + 0, ph_s0); ph_s0 ^= 1; }
@@ -333,10 +356,11 @@ attn_fwd_kernel(const AttnParams p) {
       if (tid == 0) {
         tc_fence_after();
         // O += P V_c     A: P [128 x 64] K-major ; B: V_c [N=32][K=64] MN-major (rows = keys)
+        const uint32_t pv_lo = desc_lo(smem_u32(sP), 128), vv_lo = desc_lo(smem_u32(sV) + c * KC * (DH * 2), 512);
+        const uint32_t acc_o = (c > 0) ? 1u : 0u;
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k)
-          mma_f16_ss(tO, desc_nosw(smem_u32(sP) + k * 256, 128, (KC / 8) * 128),
-                     desc_nosw(smem_u32(sV) + (c * KC + k * 16) * (DH * 2), 512, 128), idesc_o, (c > 0 || k > 0));
+          mma_lohi(tO, pv_lo + k * 16, desc_hi((KC / 8) * 128), vv_lo + k * 64, desc_hi(128), idesc_o, k > 0 ? 1u : acc_o);
         mma_commit(bars + 2);
       }
     }
@@ -438,7 +462,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   if (tid == 0) {
     mbar_init(bars + 0, 1);  // S_A / dP_A of the current step ready
     mbar_init(bars + 1, 1);  // S_B / dP_B of the current step ready
-    mbar_init(bars + 2, 1);  // dV / dK / dQ MMAs of the current step retired (P, dS tiles and old tile buffers free)
+    mbar_init(bars + 2, 3);  // dV / dK / dQ MMAs of the current step retired (one commit per issuing thread): P, dS tiles free
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -541,13 +565,12 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   };
   // S_h = Q~ K^_h^T and dP_h = dO V_h^T for the 64-key half h of the chunk (thread 0 only)
   auto issue_s = [&](int buf, int h) {
-    const uint32_t q0 = smem_u32(sQt) + buf * TILE_B, o0 = smem_u32(sdOt) + buf * TILE_B;
+    const uint32_t q_lo = desc_lo(smem_u32(sQt) + buf * TILE_B, 128), o_lo = desc_lo(smem_u32(sdOt) + buf * TILE_B, 128);
+    const uint32_t k_lo = desc_lo(smem_u32(sK) + h * KH_B, 128), v_lo = desc_lo(smem_u32(sV) + h * KH_B, 128);
 #pragma unroll
     for (int k = 0; k < DH / 16; ++k) {
-      mma_f16_ss(tS + h * BKH, desc_nosw(q0 + k * 256, 128, 512), desc_nosw(smem_u32(sK) + h * KH_B + k * 256, 128, 512),
-                 idesc_s, k > 0);
-      mma_f16_ss(tdP + h * BKH, desc_nosw(o0 + k * 256, 128, 512), desc_nosw(smem_u32(sV) + h * KH_B + k * 256, 128, 512),
-                 idesc_s, k > 0);
+      mma_lohi(tS + h * BKH, q_lo + k * 16, desc_hi(512), k_lo + k * 16, desc_hi(512), idesc_s, k > 0);
+      mma_lohi(tdP + h * BKH, o_lo + k * 16, desc_hi(512), v_lo + k * 16, desc_hi(512), idesc_s, k > 0);
     }
     mma_commit(bars + h);
   };
@@ -741,21 +764,36 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
+      // The MMAs of this step are issued by four threads of four different warps (= four schedulers): the issue code of
+      // one thread (descriptor arithmetic + 28 tcgen05.mma) would otherwise make its warp the straggler of every barrier.
+      // The three gradient products use separate accumulators, so their relative order does not matter; each issuing thread
+      // commits its own MMAs to bars[2] (3 arrivals per phase).
       if (tid == 0) {
         tc_fence_after();
-        if (i + 1 < ntiles) issue_s(nbuf, 1);   // S_B / dP_B of the next tile go first: they are short
-        const uint32_t qb = smem_u32(sQt) + buf * TILE_B, ob = smem_u32(sdOt) + buf * TILE_B;
+        if (i + 1 < ntiles) issue_s(nbuf, 1);   // S_B / dP_B of the next tile
+      } else if (tid == 32) {                   // dV_c += P^T dO_i   (A: P^T MN-major, B: dO_i MN-major)
+        tc_fence_after();
+        const uint32_t ob_lo = desc_lo(smem_u32(sdOt) + buf * TILE_B, 512), pt_lo = desc_lo(smem_u32(sP), P_RS);
+        const uint32_t acc_kv = (i > 0) ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < QT / 16; ++k) {  // reduction over the 128 queries of this tile
-          const uint64_t dPt = desc_nosw(smem_u32(sP) + k * 2 * P_RS, P_RS, 128);     // P^T  (MN-major A)
-          const uint64_t dSt = desc_nosw(smem_u32(sdS) + k * 2 * P_RS, P_RS, 128);    // dS^T (MN-major A)
-          mma_f16_ss(tdV, dPt, desc_nosw(ob + k * 1024, 512, 128), idesc_kv, (i > 0 || k > 0));   // dO_i (MN-major B)
-          mma_f16_ss(tdK, dSt, desc_nosw(qb + k * 1024, 512, 128), idesc_kv, (i > 0 || k > 0));   // Q~_i
-        }
+        for (int k = 0; k < QT / 16; ++k)      // reduction over the 128 queries of this tile
+          mma_lohi(tdV, pt_lo + k * (2 * P_RS / 16), desc_hi(128), ob_lo + k * 64, desc_hi(128), idesc_kv, k > 0 ? 1u : acc_kv);
+        mma_commit(bars + 2);
+      } else if (tid == 64) {                   // dK^_c += dS^T Q~_i
+        tc_fence_after();
+        const uint32_t qb_lo = desc_lo(smem_u32(sQt) + buf * TILE_B, 512), st_lo = desc_lo(smem_u32(sdS), P_RS);
+        const uint32_t acc_kv = (i > 0) ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < BKC / 16; ++k)  // reduction over the 128 keys of this chunk
-          mma_f16_ss(tdQ + i * DH, desc_nosw(smem_u32(sdS) + k * 256, 128, P_RS),
-                     desc_nosw(smem_u32(sK) + k * 1024, 512, 128), idesc_q, (c > 0 || k > 0));
+        for (int k = 0; k < QT / 16; ++k)
+          mma_lohi(tdK, st_lo + k * (2 * P_RS / 16), desc_hi(128), qb_lo + k * 64, desc_hi(128), idesc_kv, k > 0 ? 1u : acc_kv);
+        mma_commit(bars + 2);
+      } else if (tid == 96) {                   // dQ_i += dS K^_c
+        tc_fence_after();
+        const uint32_t sq_lo = desc_lo(smem_u32(sdS), 128), kq_lo = desc_lo(smem_u32(sK), 512);
+        const uint32_t acc_q = (c > 0) ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < BKC / 16; ++k)     // reduction over the 128 keys of this chunk
+          mma_lohi(tdQ + i * DH, sq_lo + k * 16, desc_hi(P_RS), kq_lo + k * 64, desc_hi(128), idesc_q, k > 0 ? 1u : acc_q);
         mma_commit(bars + 2);
       }
       mma_pending = true;
