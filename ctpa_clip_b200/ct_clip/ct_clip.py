@@ -23,6 +23,9 @@ def exists(val):
     return val is not None
 
 
+from ..shadow import bf16_of
+
+
 class _Shadow:
     """bf16 operand copy of an fp32 weight, refreshed when the parameter changes"""
 
@@ -32,7 +35,7 @@ class _Shadow:
     def get(self, w):
         key = (w.data_ptr(), w._version)
         if key != self.key:
-            self.val = w.detach().to(torch.bfloat16).contiguous()
+            self.val = bf16_of(w)          # a view of the optimiser's bf16 mirror when there is one, else a cast
             self.key = key
         return self.val
 

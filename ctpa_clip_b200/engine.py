@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .shadow import bf16_of
 
 
 def ff_pad(n: int) -> int:
@@ -21,29 +22,34 @@ def ff_pad(n: int) -> int:
 class LayerWeights:
     """bf16 / re-laid-out operand copies of one transformer layer (derived caches, never saved)."""
 
-    def __init__(self, peg, attn, ff, dim):
+    def __init__(self, peg, attn, ff, dim, keep=None):
+        """keep: dict owned by the caller that outlives this object — holds the zero-padded operand buffers, so that a
+        rebuild after an optimiser step only re-copies the payload (and nothing at all for the plain casts, which are views
+        of the optimiser's bf16 mirror when there is one)"""
         inner2, _ = ff[1].weight.shape
         self.ffi = inner2 // 2
         self.ffp = ff_pad(self.ffi)
         dev = ff[1].weight.device
+        keep = keep if keep is not None else {}
         self.w27 = peg.dsconv.weight.detach().reshape(dim, 27).t().contiguous()           # [27, dim] fp32
         self.peg_bias = peg.dsconv.bias.detach()
         self.gamma = attn.norm.gamma.detach()
-        self.wq = attn.to_q.weight.detach().to(torch.bfloat16).contiguous()              # [inner, dim]
-        self.wkv = attn.to_kv.weight.detach().to(torch.bfloat16).contiguous()            # [2 inner, dim]
-        self.wout = attn.to_out.weight.detach().to(torch.bfloat16).contiguous()          # [dim, inner]
+        self.wq = bf16_of(attn.to_q.weight)                                              # [inner, dim]
+        self.wkv = bf16_of(attn.to_kv.weight)                                            # [2 inner, dim]
+        self.wout = bf16_of(attn.to_out.weight)                                          # [dim, inner]
         self.q_scale = attn.q_scale.detach()
         self.k_scale = attn.k_scale.detach()
         self.ff_g = ff[0].weight.detach()
         self.ff_b = ff[0].bias.detach()
-        w1 = ff[1].weight.detach()
-        w1p = torch.zeros(2 * self.ffp, dim, device=dev, dtype=torch.bfloat16)           # [x rows | gate rows], zero padded
+        w1 = bf16_of(ff[1].weight)
+        if "w1p" not in keep:
+            keep["w1p"] = torch.zeros(2 * self.ffp, dim, device=dev, dtype=torch.bfloat16)  # [x rows | gate rows], zero padded
+            keep["w2p"] = torch.zeros(dim, self.ffp, device=dev, dtype=torch.bfloat16)
+        w1p, w2p = keep["w1p"], keep["w2p"]
         w1p[: self.ffi] = w1[: self.ffi]
         w1p[self.ffp: self.ffp + self.ffi] = w1[self.ffi:]
-        self.w1p = w1p
-        w2p = torch.zeros(dim, self.ffp, device=dev, dtype=torch.bfloat16)
-        w2p[:, : self.ffi] = ff[4].weight.detach()
-        self.w2p = w2p
+        w2p[:, : self.ffi] = bf16_of(ff[4].weight)
+        self.w1p, self.w2p = w1p, w2p
 
 
 class EncoderWeights:
@@ -56,13 +62,20 @@ class EncoderWeights:
         self.pdim = pe[1].weight.numel()
         self.pe_g, self.pe_b = pe[1].weight.detach(), pe[1].bias.detach()
         kp = ff_pad(self.pdim)
-        w = torch.zeros(dim, kp, device=pe[2].weight.device, dtype=torch.bfloat16)
-        w[:, : self.pdim] = pe[2].weight.detach()
-        self.pe_w = w
+        keep = vit.__dict__.setdefault("_operand_buffers", {})
+        if kp == self.pdim:
+            self.pe_w = bf16_of(pe[2].weight)
+        else:
+            if "pe_w" not in keep:
+                keep["pe_w"] = torch.zeros(dim, kp, device=pe[2].weight.device, dtype=torch.bfloat16)
+            keep["pe_w"][:, : self.pdim] = bf16_of(pe[2].weight)
+            self.pe_w = keep["pe_w"]
         self.pe_bias = pe[2].bias.detach()
         self.pe_g2, self.pe_b2 = pe[3].weight.detach(), pe[3].bias.detach()
-        self.spatial = [LayerWeights(l[0], l[1], l[3], dim) for l in vit.enc_spatial_transformer.layers]
-        self.temporal = [LayerWeights(l[0], l[1], l[3], dim) for l in vit.enc_temporal_transformer.layers]
+        self.spatial = [LayerWeights(l[0], l[1], l[3], dim, keep.setdefault(("s", i), {}))
+                        for i, l in enumerate(vit.enc_spatial_transformer.layers)]
+        self.temporal = [LayerWeights(l[0], l[1], l[3], dim, keep.setdefault(("t", i), {}))
+                         for i, l in enumerate(vit.enc_temporal_transformer.layers)]
         self.s_out = vit.enc_spatial_transformer.norm_out.gamma.detach()
         self.t_out = vit.enc_temporal_transformer.norm_out.gamma.detach()
         embed = vit.vq._codebook.embed.detach()[0]

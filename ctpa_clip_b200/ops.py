@@ -176,10 +176,11 @@ def geglu_bwd(h, du):
     return dh
 
 
-def cast_bf16(x):
+def cast_bf16(x, out=None):
     _req(x, torch.float32, "cast_bf16.x")
     assert x.is_contiguous()
-    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    y = out if out is not None else torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    assert y.dtype == torch.bfloat16 and y.numel() == x.numel() and y.is_contiguous()
     _call("ctclip_cast_f32_bf16", _ptr(x), _ptr(y), _ll(x.numel()), _stream())
     return y
 

@@ -17,6 +17,7 @@ import math
 import torch
 
 from .. import ops
+from ..shadow import bf16_of, bf16_rows_of, f32_cat_of
 
 
 def supports(module) -> bool:
@@ -72,14 +73,14 @@ class NativeBert:
         for layer in self.m.encoder.layer:
             a, w = layer.attention, _LayerW()
             s = a.self
-            w.wqkv = torch.cat((s.query.weight, s.key.weight, s.value.weight), 0).detach().to(torch.bfloat16).contiguous()
-            w.bqkv = torch.cat((s.query.bias, s.key.bias, s.value.bias), 0).detach().float().contiguous()
-            w.wo = a.output.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.wqkv = bf16_rows_of((s.query.weight, s.key.weight, s.value.weight))
+            w.bqkv = f32_cat_of((s.query.bias, s.key.bias, s.value.bias))
+            w.wo = bf16_of(a.output.dense.weight)
             w.bo = a.output.dense.bias.detach()
             w.g1, w.b1n = a.output.LayerNorm.weight.detach(), a.output.LayerNorm.bias.detach()
-            w.w1 = layer.intermediate.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.w1 = bf16_of(layer.intermediate.dense.weight)
             w.b1 = layer.intermediate.dense.bias.detach()
-            w.w2 = layer.output.dense.weight.detach().to(torch.bfloat16).contiguous()
+            w.w2 = bf16_of(layer.output.dense.weight)
             w.b2 = layer.output.dense.bias.detach()
             w.g2, w.b2n = layer.output.LayerNorm.weight.detach(), layer.output.LayerNorm.bias.detach()
             out.append(w)

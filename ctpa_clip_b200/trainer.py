@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, shadow
 
 
 # parameters that exist in the reference's state_dict but never receive a gradient on the CLIP path (SURVEY.md a16;
@@ -50,7 +50,7 @@ class ParamArena:
         params = _arena_order(trainable_parameters(module))
         self.params = params
         dev = params[0].device
-        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        sizes = [(p.numel() + 7) // 8 * 8 for p in params]   # 32-byte fp32 slots: the bf16 mirror views stay 16-byte aligned (TMA)
         total = sum(sizes)
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -68,6 +68,21 @@ class ParamArena:
                 off += s
         self.norm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.total = total
+        # bf16 mirror of the parameters (same offsets): written by the Adam kernel, read by the tensor-core GEMMs as
+        # zero-copy views (shadow.bf16_of). `versions` pins the torch-side version of each parameter the mirror matches.
+        self.bf16 = None
+        self.versions = {}
+        if dev.type == "cuda":
+            self.bf16 = torch.empty(total, device=dev, dtype=torch.bfloat16)
+            self.sync_shadow()
+            shadow.register(self)
+
+    def sync_shadow(self):
+        """re-derive the whole mirror from the fp32 parameters (construction, or after torch-side writes such as load_state_dict)"""
+        if self.bf16 is None:
+            return
+        ops.cast_bf16(self.flat, out=self.bf16)
+        self.versions = {p.data_ptr(): p._version for p in self.params}
 
 
 class CTClipTrainStep:
@@ -137,7 +152,7 @@ class CTClipTrainStep:
         self.step_count += 1
         a.norm_sq.zero_()
         ops.sumsq(a.grad, a.norm_sq)
-        ops.adam_step(a.flat, a.grad, a.m, a.v, None, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+        ops.adam_step(a.flat, a.grad, a.m, a.v, a.bf16, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                       norm_sq=a.norm_sq, max_norm=self.max_grad_norm, zero_grad=True)
         # parameters changed in place behind autograd's back: drop the derived operand caches
         self.model.visual_transformer.invalidate_weights()
