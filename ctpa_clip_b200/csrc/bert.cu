@@ -23,13 +23,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// keep-probability test of element i under `seed`: uniform in [0,1) from a murmur3-style finaliser
-__device__ __forceinline__ bool keep_elem(unsigned long long i, unsigned seed, float p_drop) {
-  uint32_t h = (uint32_t)i * 0x9E3779B1u ^ seed ^ ((uint32_t)(i >> 32) * 0x7FEB352Du);
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p_drop;
-}
-
 // ------------------------------------------------------------------------------------------ embeddings
 // x[t] = word[ids[t]] + pos[t % L] + type[0]      (BertEmbeddings.forward; token_type_ids default to 0)
 __global__ void __launch_bounds__(256)

@@ -40,6 +40,14 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 // 2^x on the MUFU pipe, flush-to-zero: one instruction (exp2f() adds a denormal-range fix-up around it)
+// keep-probability test of element i under `seed`: uniform in [0,1) from a murmur3-style finaliser (stateless dropout: the
+// forward and backward kernels regenerate the same mask from the element index)
+__device__ __forceinline__ bool keep_elem(unsigned long long i, unsigned seed, float p_drop) {
+  uint32_t h = (uint32_t)i * 0x9E3779B1u ^ seed ^ ((uint32_t)(i >> 32) * 0x7FEB352Du);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p_drop;
+}
+
 // exact-erf GELU (F.gelu default) and its derivative from ONE exponential: erf(x) = 1 - poly(t) e^{-x^2}, t = 1 / (1 + p x)
 // (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 absolute — three orders below the bf16 resolution of the outputs), and
 // e^{-x^2} with x = |g| / sqrt(2) is also the Gaussian of the derivative. ~14 instructions, 2 MUFU, no branches.

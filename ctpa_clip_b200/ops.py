@@ -523,3 +523,25 @@ def colsum_bf16(x, out, dim=None, ld=None):
     rows = x.shape[0]
     _call("ctclip_colsum_bf16", _ptr(x), _ll(rows), dim if dim is not None else x.shape[1],
           _ll(ld if ld is not None else x.stride(0)), _ptr(out), _stream())
+
+
+def bert_attn_fwd(qkv, mask, B, H, L, D, p_drop=0.0, seed=0):
+    """fused BertSelfAttention core (head dim 64): returns (context bf16 [B*L, D], lse fp32 [B*H, L])"""
+    _req(qkv, torch.bfloat16, "bert_attn_fwd.qkv")
+    assert qkv.is_contiguous() and qkv.shape == (B * L, 3 * D) and mask.dtype == torch.long and mask.is_contiguous()
+    out = torch.empty((B * L, D), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((B * H, L), device=qkv.device, dtype=torch.float32)
+    _call("ctclip_bert_attn_fwd", _ptr(qkv), _ptr(mask), B, H, L, D, _ptr(out), _ptr(lse), _f(p_drop),
+          C.c_uint(seed & 0xFFFFFFFF), _stream())
+    return out, lse
+
+
+def bert_attn_bwd(qkv, mask, out, lse, dout, B, H, L, D, p_drop=0.0, seed=0):
+    """returns the packed gradient dQKV bf16 [B*L, 3*D]"""
+    _req(dout, torch.bfloat16, "bert_attn_bwd.dout")
+    assert dout.is_contiguous() and out.is_contiguous() and lse.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty((B * H, L), device=qkv.device, dtype=torch.float32)
+    _call("ctclip_bert_attn_bwd", _ptr(qkv), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout), B, H, L, D, _ptr(dqkv), _ptr(ws),
+          _f(p_drop), C.c_uint(seed & 0xFFFFFFFF), _stream())
+    return dqkv

@@ -13,6 +13,7 @@ keeps the HF module (a library path) for them.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -49,6 +50,8 @@ class NativeBert:
         self.vocab = cfg.vocab_size
         self._key, self._layers = None, None
         self.calls = 0
+        # fused attention core (csrc/bert_attn.cu) for head dim 64; CTCLIP_BERT_FUSED_ATTN=0 selects the GEMM + softmax path
+        self.fused_attention = self.hd == 64 and os.environ.get("CTCLIP_BERT_FUSED_ATTN", "1") != "0"
         # True (set by CTClipTrainStep): the kernels accumulate parameter gradients straight into the existing p.grad
         # buffers (flat gradient arena, zeroed by the optimiser kernel) and autograd gets None for them
         self.direct_grad = False
@@ -125,6 +128,34 @@ class NativeBert:
         ops.run_gemm_desc(d, False, f"bert_pv:{B}x{H}x{L}x{hd}x{L}", 2.0 * B * H * L * L * hd)
         return ctx
 
+    def _attention_backward_unfused(self, qkv, P, Pd, dcv, B, L, scale, pa, sd, dev):
+        """BertSelfAttention backward as batched tcgen05 GEMMs + the softmax-backward kernel (any head dim)"""
+        D, H, hd = self.D, self.H, self.hd
+        Pop = Pd if Pd is not None else P
+        base = qkv.data_ptr()
+        dqkv = torch.empty_like(qkv)
+        dbase = dqkv.data_ptr()
+        fl = 2.0 * B * H * L * L * hd
+        # dP = dctx V^T   (fp32 [B,H,L,L])
+        dP = torch.empty((B * H, L, L), device=dev, dtype=torch.float32)
+        d = ops.gemm_batched(dcv.data_ptr(), D, False, hd, L * D, base + 2 * (2 * D), 3 * D, False, hd, L * 3 * D,
+                             dP, L, L * L, H * L * L, L, L, hd, H, B)
+        ops.run_gemm_desc(d, True, f"bert_dp:{B}x{H}x{L}x{L}x{hd}", fl)
+        # dV = P^T dctx  -> v slice of dqkv
+        d = ops.gemm_batched(Pop.data_ptr(), L, True, L * L, H * L * L, dcv.data_ptr(), D, True, hd, L * D,
+                             dbase + 2 * (2 * D), 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+        ops.run_gemm_desc(d, False, f"bert_dv:{B}x{H}x{L}x{hd}x{L}", fl)
+        dS = ops.bert_softmax_bwd(P, dP, B, H, L, scale, pa, sd + 1)
+        del dP
+        # dQ = dS K -> q slice ; dK = dS^T Q -> k slice
+        d = ops.gemm_batched(dS.data_ptr(), L, False, L * L, H * L * L, base + 2 * D, 3 * D, True, hd, L * 3 * D,
+                             dbase, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+        ops.run_gemm_desc(d, False, f"bert_dq:{B}x{H}x{L}x{hd}x{L}", fl)
+        d = ops.gemm_batched(dS.data_ptr(), L, True, L * L, H * L * L, base, 3 * D, True, hd, L * 3 * D,
+                             dbase + 2 * D, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
+        ops.run_gemm_desc(d, False, f"bert_dk:{B}x{H}x{L}x{hd}x{L}", fl)
+        return dqkv
+
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, ids, mask, training: bool):
         B, L = ids.shape
@@ -152,10 +183,14 @@ class NativeBert:
             c = {}
             sd = seed0 + 101 * (li + 1)
             qkv = ops.gemm(xb, w.wqkv, bias=w.bqkv, tag=f"bert_qkv:{T}x{3 * D}x{D}")
-            S = self._scores(qkv, B, L)
-            P, Pd = ops.bert_softmax_fwd(S, mask, B, H, L, scale, pa, sd + 1)
-            del S
-            cv = self._pv(Pd if Pd is not None else P, qkv, B, L)
+            if self.fused_attention:    # scores / probabilities stay in registers (csrc/bert_attn.cu)
+                cv, P = ops.bert_attn_fwd(qkv, mask, B, H, L, D, pa, sd + 1)     # "P" slot holds lse
+                Pd = None
+            else:
+                S = self._scores(qkv, B, L)
+                P, Pd = ops.bert_softmax_fwd(S, mask, B, H, L, scale, pa, sd + 1)
+                del S
+                cv = self._pv(Pd if Pd is not None else P, qkv, B, L)
             if ph > 0:
                 ao = ops.gemm(cv, w.wo, out_dtype=torch.float32, bias=w.bo, tag=f"bert_out:{T}x{D}x{D}")
                 pre1 = ops.dropout_add(ao, x, ph, sd + 2)
@@ -241,30 +276,10 @@ class NativeBert:
             dcv = ops.gemm(dao_b, w.wo, b_t=True, tag=f"bert_dgrad:{T}x{D}x{D}")
             # ---- BertSelfAttention
             qkv, P, Pd = c["qkv"], c["P"], c["Pd"]
-            Pop = Pd if Pd is not None else P
-            base = qkv.data_ptr()
-            dqkv = torch.empty_like(qkv)
-            dbase = dqkv.data_ptr()
-            fl = 2.0 * B * H * L * L * hd
-            # dP = dctx V^T   (fp32 [B,H,L,L])
-            dP = torch.empty((B * H, L, L), device=dev, dtype=torch.float32)
-            d = ops.gemm_batched(dcv.data_ptr(), D, False, hd, L * D, base + 2 * (2 * D), 3 * D, False, hd, L * 3 * D,
-                                 dP, L, L * L, H * L * L, L, L, hd, H, B)
-            ops.run_gemm_desc(d, True, f"bert_dp:{B}x{H}x{L}x{L}x{hd}", fl)
-            # dV = P^T dctx  -> v slice of dqkv
-            d = ops.gemm_batched(Pop.data_ptr(), L, True, L * L, H * L * L, dcv.data_ptr(), D, True, hd, L * D,
-                                 dbase + 2 * (2 * D), 3 * D, hd, L * 3 * D, L, hd, L, H, B)
-            ops.run_gemm_desc(d, False, f"bert_dv:{B}x{H}x{L}x{hd}x{L}", fl)
-            dS = ops.bert_softmax_bwd(P, dP, B, H, L, scale, pa, sd + 1)
-            del dP
-            # dQ = dS K -> q slice ; dK = dS^T Q -> k slice
-            d = ops.gemm_batched(dS.data_ptr(), L, False, L * L, H * L * L, base + 2 * D, 3 * D, True, hd, L * 3 * D,
-                                 dbase, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
-            ops.run_gemm_desc(d, False, f"bert_dq:{B}x{H}x{L}x{hd}x{L}", fl)
-            d = ops.gemm_batched(dS.data_ptr(), L, True, L * L, H * L * L, base, 3 * D, True, hd, L * 3 * D,
-                                 dbase + 2 * D, 3 * D, hd, L * 3 * D, L, hd, L, H, B)
-            ops.run_gemm_desc(d, False, f"bert_dk:{B}x{H}x{L}x{hd}x{L}", fl)
-            del dS
+            if self.fused_attention:
+                dqkv = ops.bert_attn_bwd(qkv, ctx["mask"], c["cv"], P, dcv, B, H, L, D, pa, sd + 1)
+            else:
+                dqkv = self._attention_backward_unfused(qkv, P, Pd, dcv, B, L, scale, pa, sd, dev)
             packed = self._packed_qkv_grad(pfx) if direct else None
             if packed is not None:   # q / k / v gradients are adjacent in the arena: one wgrad GEMM, one column sum
                 dw3, db3 = packed

@@ -104,6 +104,15 @@ int ctclip_bert_softmax_fwd(const float* scores, const long long* mask, int batc
                             void* probs, void* probs_dropped, float p_drop, unsigned seed, void* stream);
 int ctclip_bert_softmax_bwd(const void* probs, const float* dprobs_dropped, int batch, int heads, int seq_len, float scale,
                             void* dscores, float p_drop, unsigned seed, void* stream);
+/* Fused BertSelfAttention core for head dim 64 (HF modeling_bert.py BertSelfAttention.forward: Q K^T / sqrt(d) + key mask ->
+ * softmax -> attention-probs dropout -> P V) on the packed [tokens, 3 * hidden] bf16 QKV projection; the scores stay in
+ * registers. fwd writes the context [tokens, hidden] bf16 and lse [batch * heads, seq_len] (log2 domain); bwd writes the
+ * packed dQKV and needs a [batch * heads, seq_len] fp32 workspace for rowsum(dO * O). */
+int ctclip_bert_attn_fwd(const void* qkv, const long long* mask, int batch, int heads, int seq_len, int hidden, void* out,
+                         float* lse, float p_drop, unsigned seed, void* stream);
+int ctclip_bert_attn_bwd(const void* qkv, const long long* mask, const void* out, const float* lse, const void* dout, int batch,
+                         int heads, int seq_len, int hidden, void* dqkv, float* delta_ws, float p_drop, unsigned seed,
+                         void* stream);
 int ctclip_gelu_fwd(const void* h, void* out, long long n, void* stream);
 int ctclip_gelu_bwd(const void* h, const void* dy, void* dh, long long n, void* stream);
 int ctclip_dropout_add(const float* y, const float* resid, float* out, long long n, float p_drop, unsigned seed,

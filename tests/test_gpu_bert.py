@@ -21,6 +21,7 @@ def _bert(hidden, heads, inter, layers, max_pos, vocab=500, seed=0):
     (64, 2, 128, 2, 3, 16, 8),      # tiny config of the test models: head dim 32, sequence shorter than one tile
     (256, 4, 512, 2, 2, 128, 40),   # head dim 64 (BERT-base), one full 128-row tile, ragged mask
     (128, 2, 256, 1, 2, 200, 0),    # sequence not a multiple of 64 / 128: every operand edge is TMA zero fill
+    (192, 3, 384, 2, 2, 328, 150),  # fused attention path (head dim 64): ragged tiles, two whole key blocks of padding
 ])
 def test_native_bert_forward_backward_matches_hf(hidden, heads, inter, layers, B, L, pad):
     from ctpa_clip_b200.text import NativeBert, supports
@@ -86,3 +87,43 @@ def test_native_bert_dropout_is_consistent_between_forward_and_backward():
     a = ops.dropout_add(y, None, 0.1, 77)
     b = ops.dropout_add(y, None, 0.1, 77)
     assert torch.equal(a, b) and 0.07 < (a == 0).float().mean().item() < 0.13
+
+
+@pytest.mark.parametrize("L,pad,p_drop", [(128, 0, 0.0), (200, 70, 0.0), (512, 256, 0.1), (96, 10, 0.25)])
+def test_fused_attention_equals_gemm_softmax_path(L, pad, p_drop):
+    """csrc/bert_attn.cu (scores in registers, mma.sync) against the batched tcgen05 GEMM + softmax kernels on the same packed
+    QKV: same math, same stateless dropout mask (element index and seed), bf16 operands in both"""
+    import math
+    from ctpa_clip_b200 import ops
+    B, H, D = 2, 3, 192
+    g = torch.Generator(device="cuda").manual_seed(L + pad)
+    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    dout = torch.randn(B * L, D, device="cuda", generator=g).bfloat16()
+    mask = torch.ones(B, L, dtype=torch.long, device="cuda")
+    if pad:
+        mask[:, L - pad:] = 0
+        mask[1, L - pad: L - pad + 5] = 1
+    scale, seed = 1.0 / math.sqrt(64), 4242
+
+    class M:   # the unfused product helpers of NativeBert only need these attributes
+        pass
+    from ctpa_clip_b200.text.bert import NativeBert
+    eng = NativeBert.__new__(NativeBert)
+    eng.D, eng.H, eng.hd = D, H, 64
+    S = eng._scores(qkv, B, L)
+    P, Pd = ops.bert_softmax_fwd(S, mask, B, H, L, scale, p_drop, seed)
+    cv_ref = eng._pv(Pd if Pd is not None else P, qkv, B, L)
+    dq_ref = eng._attention_backward_unfused(qkv, P, Pd, dout, B, L, scale, p_drop, seed - 1, qkv.device)
+
+    cv, lse = ops.bert_attn_fwd(qkv, mask, B, H, L, D, p_drop, seed)
+    dqkv = ops.bert_attn_bwd(qkv, mask, cv, lse, dout, B, H, L, D, p_drop, seed)
+    def close(a, b, tol):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= tol * b.float().abs().max().item(), f"{err} vs {b.float().abs().max().item()}"
+    close(cv, cv_ref, 2e-2)
+    for j, name in enumerate(("dq", "dk", "dv")):
+        close(dqkv[:, j * D:(j + 1) * D], dq_ref[:, j * D:(j + 1) * D], 3e-2)
+    # lse against the fp32 definition (log2 domain), valid queries only
+    ref = torch.logsumexp(S.float() * scale + torch.where(mask[:, None, None, :] != 0, 0.0, float("-inf")).expand(B, H, L, L)
+                          .reshape(B * H, L, L), dim=-1) / math.log(2.0)
+    assert (lse - ref).abs().max().item() < 2e-2
