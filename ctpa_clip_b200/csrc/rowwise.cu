@@ -363,6 +363,29 @@ colsum_kernel(const float* __restrict__ x, long long rows, int dim, float* __res
     atomicAdd(out + c, s);
   }
 }
+// batched 2-D bf16 copies (operand re-packing: zero-padded FF weights): desc[i] = {src, dst, rows, cols, src_ld, dst_ld}
+__global__ void __launch_bounds__(256)
+copy2d_batch_kernel(const long long* __restrict__ desc) {
+  const long long* d = desc + 6 * blockIdx.y;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(d[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  const long long rows = d[2], cols = d[3], sld = d[4], dld = d[5];
+  const bool vec = (cols % 8 == 0) && (sld % 8 == 0) && (dld % 8 == 0) && ((d[0] | d[1]) % 16 == 0);
+  if (vec) {
+    const long long cv = cols / 8, total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / cv, c = i - r * cv;
+      *reinterpret_cast<uint4*>(dst + r * dld + 8 * c) = *reinterpret_cast<const uint4*>(src + r * sld + 8 * c);
+    }
+  } else {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / cols, c = i - r * cols;
+      dst[r * dld + c] = src[r * sld + c];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 colsum_tile_kernel(const float* __restrict__ x, long long rows, int dim, float* __restrict__ out, int rows_per_block) {
   ptx::colsum_tile<float>(x, rows, dim, dim, out, rows_per_block);
@@ -390,4 +413,13 @@ extern "C" int ctclip_colsum(const float* x, long long rows, int dim, float* out
   }
   colsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, out, rpb);
   return ctclip::check_launch("colsum");
+}
+
+extern "C" int ctclip_copy2d_batch_bf16(const long long* desc_dev, int n, void* stream) {
+  if (n <= 0) return CTCLIP_OK;
+  if (desc_dev == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "copy2d_batch: null descriptor table");
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  copy2d_batch_kernel<<<dim3((unsigned)ctclip::sm_count(), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(desc_dev);
+  return ctclip::check_launch("copy2d_batch");
 }

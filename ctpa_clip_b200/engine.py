@@ -46,9 +46,9 @@ class LayerWeights:
             keep["w1p"] = torch.zeros(2 * self.ffp, dim, device=dev, dtype=torch.bfloat16)  # [x rows | gate rows], zero padded
             keep["w2p"] = torch.zeros(dim, self.ffp, device=dev, dtype=torch.bfloat16)
         w1p, w2p = keep["w1p"], keep["w2p"]
-        w1p[: self.ffi] = w1[: self.ffi]
-        w1p[self.ffp: self.ffp + self.ffi] = w1[self.ffi:]
-        w2p[:, : self.ffi] = bf16_of(ff[4].weight)
+        # payload copies are collected by the caller and done in ONE launch (ops.copy2d_batch)
+        self.repack = [(w1[: self.ffi], w1p[: self.ffi]), (w1[self.ffi:], w1p[self.ffp: self.ffp + self.ffi]),
+                       (bf16_of(ff[4].weight), w2p[:, : self.ffi])]
         self.w1p, self.w2p = w1p, w2p
 
 
@@ -76,6 +76,9 @@ class EncoderWeights:
                         for i, l in enumerate(vit.enc_spatial_transformer.layers)]
         self.temporal = [LayerWeights(l[0], l[1], l[3], dim, keep.setdefault(("t", i), {}))
                          for i, l in enumerate(vit.enc_temporal_transformer.layers)]
+        pairs = [pr for L in self.spatial + self.temporal for pr in L.repack]
+        self._repack_sources = [s for s, _ in pairs]     # keep fresh casts alive until the copy has run
+        ops.copy2d_batch(pairs, keep)
         self.s_out = vit.enc_spatial_transformer.norm_out.gamma.detach()
         self.t_out = vit.enc_temporal_transformer.norm_out.gamma.detach()
         embed = vit.vq._codebook.embed.detach()[0]

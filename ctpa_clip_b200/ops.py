@@ -545,3 +545,18 @@ def bert_attn_bwd(qkv, mask, out, lse, dout, B, H, L, D, p_drop=0.0, seed=0):
     _call("ctclip_bert_attn_bwd", _ptr(qkv), _ptr(mask), _ptr(out), _ptr(lse), _ptr(dout), B, H, L, D, _ptr(dqkv), _ptr(ws),
           _f(p_drop), C.c_uint(seed & 0xFFFFFFFF), _stream())
     return dqkv
+
+
+def copy2d_batch(pairs, cache: dict):
+    """pairs: list of (src, dst) 2-D bf16 tensors (same shape, last dim contiguous). One launch for all copies; the device
+    descriptor table is cached in `cache` and reused while every address / shape is unchanged."""
+    key = tuple((s.data_ptr(), d.data_ptr(), tuple(s.shape), s.stride(0), d.stride(0)) for s, d in pairs)
+    if cache.get("copy2d_key") != key:
+        rows = []
+        for s, d in pairs:
+            assert s.dtype == d.dtype == torch.bfloat16 and s.shape == d.shape and s.dim() == 2
+            assert s.stride(1) == 1 and d.stride(1) == 1
+            rows.append([s.data_ptr(), d.data_ptr(), s.shape[0], s.shape[1], s.stride(0), d.stride(0)])
+        cache["copy2d_table"] = torch.tensor(rows, dtype=torch.int64).to(pairs[0][0].device)
+        cache["copy2d_key"] = key
+    _call("ctclip_copy2d_batch_bf16", _ptr(cache["copy2d_table"]), len(pairs), _stream())

@@ -80,6 +80,9 @@ int ctclip_layernorm_bwd(const void* dy /* fp32, or bf16 when dy_is_bf16 (straig
 int ctclip_geglu_fwd(const void* h, void* u, long long rows, int ld_half, void* stream);
 int ctclip_geglu_bwd(const void* h, const void* du, void* dh, long long rows, int ld_half, void* stream);
 int ctclip_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+/* n independent 2-D bf16 copies in one launch; desc_dev: device array of n x {src, dst, rows, cols, src_ld, dst_ld} (int64) —
+ * re-packs the zero-padded FF operands from the bf16 parameter mirror after an optimiser step */
+int ctclip_copy2d_batch_bf16(const long long* desc_dev, int n, void* stream);
 /* out[c] += sum_rows x[row][c]  (bias gradients) */
 int ctclip_colsum(const float* x, long long rows, int dim, float* out, void* stream);
 
