@@ -10,22 +10,32 @@ tot = sum(v["ms"] for k, v in rows)
 grp = lambda pred: sum(v["ms"] for k, v in rows if pred(k))
 g = {"tcgen05 GEMMs (CTViT + VQ + latent projections)": grp(lambda k: k.startswith("gemm") and "bert" not in k),
      "tcgen05 GEMMs (BERT, incl. batched per-head products)": grp(lambda k: k.startswith("gemm:bert")),
-     "attention fwd+bwd (spatial + temporal)": grp(lambda k: k.startswith("attn")),
+     "CTViT attention fwd+bwd (spatial tcgen05 + temporal mma.sync)": grp(lambda k: k.startswith("attn")),
+     "BERT fused attention fwd+bwd": grp(lambda k: k.startswith("bert_attn")),
      "LayerNorm fwd+bwd (CTViT + BERT)": grp(lambda k: k.startswith("layernorm")),
      "GEGLU fwd+bwd": grp(lambda k: k.startswith("geglu")),
      "PEG fwd + data grad + weight grad": grp(lambda k: k.startswith("peg")),
-     "BERT softmax / GELU / dropout / embeddings / bf16 colsum": grp(lambda k: k.startswith("bert_") or k in ("gelu_fwd", "gelu_bwd", "dropout_add", "colsum_bf16")),
+     "BERT softmax / GELU / dropout / embeddings / bf16 colsum": grp(lambda k: (k.startswith("bert_") and not k.startswith("bert_attn")) or k in ("gelu_fwd", "gelu_bwd", "dropout_add", "colsum_bf16")),
      "clip-norm + Adam": grp(lambda k: k in ("adam_step", "sumsq"))}
 other = tot - sum(g.values())
 L = []
 L.append("# Round 1 — measurement summary (1×B200 unless noted; B = 8 volumes 480×480×240 + 8 reports × 512 ids per rank)\n")
 L.append("All numbers are CUDA-event timings from `bench.py` / `tools/bench_components.py` runs on the GPU box (no profiler attached);")
-L.append("ncu evidence is in `r01_ncu_launches_v2.txt` (launch list of one training step) and `r01_ncu_kernels_v3.txt` (`--set full` extracts).\n")
+L.append("ncu evidence: `r01_ncu_launches_v5.txt` + `r01_step_traffic.json` (launch list and DRAM bytes of one training step), `r01_ncu_kernels_v3.txt` / `r01_ncu_kernels_v7.txt` (`--set full` extracts).\n")
 L.append(f"## Headline (`r01_bench_{tag}.log`)\n")
-L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (round start: 79.2 ms / 101 volumes/s with the text tower still on torch)")
+L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (session start: 79.2 ms / 101 volumes/s with the text tower still on torch; previous snapshot v4: 58.8 ms)")
 L.append(f"* end to end (pinned host volumes → H2D on a copy stream → step → `loss.item()` every step): **{bench['e2e']['value']:.1f} volumes/s** ({bench['e2e']['ms_per_step']:.1f} ms/step, {bench['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB H2D per step)")
 L.append(f"* all `gemm_bf16_kernel` launches of the step: {bench['roofline']['achieved']:.0f} TFLOP/s = {100 * bench['roofline']['frac']:.0f} % of the measured sustained cuBLAS bf16 rate, {100 * bench['roofline']['share_of_step']:.0f} % of the step")
-L.append("* 2×B200 (`r01_bench_2gpu_v3.log`, weak scaling, global batch 16, latents all-gathered, gradients all-reduced over NVLink; build before the CTA-pair GEMM): 64.5 ms/step = 248 volumes/s (97 % of 2× that build's 1-GPU step)")
+try:
+    b2 = json.loads([l for l in open(f"profiles/r01_bench_2gpu_{tag}.log") if l.startswith("{")][-1])
+    L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log`, weak scaling, global batch 16, latents all-gathered, gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
+except FileNotFoundError:
+    pass
+try:
+    br = json.loads([l for l in open(f"profiles/r01_bench_reference_arm_{tag}.log") if l.startswith("{")][-1])
+    L.append(f"* `bench.py --impl reference` (the reference's CPU path, oracle port on all host threads): {br['value']:.2f} volumes/s")
+except FileNotFoundError:
+    pass
 L.append(f"* CPU oracle (fp32 port of the reference, {bench['cpu_baseline']['cores']} host threads): {bench['cpu_baseline']['value']:.2f} volumes/s\n")
 L.append("## Where the step goes (`r01_step_breakdown_%s.json`, one instrumented step, Σ = %.1f ms of the %.1f ms step)\n" % (tag, tot, d["ms_per_step"]))
 L.append("| group | ms | share |\n|---|---|---|")
