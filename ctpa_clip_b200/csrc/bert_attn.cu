@@ -157,7 +157,7 @@ __device__ __forceinline__ void load_key_mask(const BertAttnParams& p, int b, fl
 }
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 bert_attn_fwd_kernel(const BertAttnParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nkb = (p.L + BT - 1) / BT;
@@ -377,7 +377,7 @@ bert_attn_bwd_dkv_kernel(const BertAttnParams p) {
 }
 
 // dQ of one 64-query block: key blocks stream through (padding-only blocks are skipped)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 bert_attn_bwd_dq_kernel(const BertAttnParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nkb = (p.L + BT - 1) / BT;
