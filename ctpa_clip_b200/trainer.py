@@ -6,6 +6,8 @@ Adam-moment arenas, so clipping and the optimiser are two HBM passes and the all
 """
 from __future__ import annotations
 
+from pathlib import Path
+
 import torch
 import torch.distributed as dist
 
@@ -166,3 +168,50 @@ class CTClipTrainStep:
         self.reduce_gradients()
         self.optimizer_step()
         return loss
+
+    # ---------------------------------------------------------------- checkpoint I/O (CTCLIPTrainer.py:289-307)
+    def save(self, path):
+        """Same package layout as CTClipTrainer.save: dict(model=<state_dict>, optim=<optimiser state>), written by rank 0.
+        The model part loads into the reference CTCLIP unchanged; the optimiser part is keyed by parameter NAME
+        (exp_avg / exp_avg_sq / step) because the flat-arena Adam has no torch param-group numbering."""
+        if self.distributed and dist.get_rank() != 0:
+            return
+        a = self.arena
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        exp_avg, exp_avg_sq = {}, {}
+        for p in a.params:
+            off, _ = a.span[id(p)]
+            exp_avg[names[id(p)]] = a.m[off: off + p.numel()].view(p.shape).clone()
+            exp_avg_sq[names[id(p)]] = a.v[off: off + p.numel()].view(p.shape).clone()
+        pkg = dict(model=self.model.state_dict(),
+                   optim=dict(format="ctpa_clip_b200.flat_adam", step=self.step_count, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
+                              lr=self.lr, betas=self.betas, eps=self.eps, max_grad_norm=self.max_grad_norm))
+        torch.save(pkg, str(path))
+
+    def load(self, path):
+        """CTClipTrainer.load: model state_dict (parameters stay views of the arena: load_state_dict copies in place), then
+        the Adam moments when the package was written by `save`; a torch.optim state (reference trainer) restores the model
+        only. Derived operands (bf16 mirror, cached bf16 / padded weights) are re-synchronised."""
+        path = Path(path)
+        assert path.exists()
+        pkg = torch.load(str(path), map_location=self.arena.flat.device)
+        state = pkg["model"] if isinstance(pkg, dict) and "model" in pkg else pkg     # CTCLIP.load takes the bare state_dict
+        self.model.load_state_dict(state, strict=False)
+        opt = pkg.get("optim") if isinstance(pkg, dict) else None
+        if isinstance(opt, dict) and opt.get("format") == "ctpa_clip_b200.flat_adam":
+            a = self.arena
+            names = {id(p): n for n, p in self.model.named_parameters()}
+            with torch.no_grad():
+                for p in a.params:
+                    off, _ = a.span[id(p)]
+                    n = names[id(p)]
+                    if n in opt["exp_avg"]:
+                        a.m[off: off + p.numel()].view(p.shape).copy_(opt["exp_avg"][n])
+                        a.v[off: off + p.numel()].view(p.shape).copy_(opt["exp_avg_sq"][n])
+            self.step_count = int(opt["step"])
+        self.arena.sync_shadow()
+        self.model.visual_transformer.invalidate_weights()
+        self.model._sh_text.key = None
+        self.model._sh_vis.key = None
+        if getattr(self.model, "_native_text", None) is not None:
+            self.model._native_text.invalidate()

@@ -173,3 +173,34 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation():
         assert (a - b).abs().max().item() <= 2e-3 * scale + 1e-7, n
         checked += 1
     assert checked > 100
+
+
+def test_trainer_checkpoint_round_trip(tmp_path):
+    """CTClipTrainStep.save / load (CTCLIPTrainer.py:289-307): a restored trainer continues exactly where the saved one was —
+    parameters, Adam moments, step count, and the derived bf16 operands (mirror) are all re-synchronised"""
+    from ctpa_clip_b200.trainer import CTClipTrainStep
+    cfg = O.TINY
+    video, ids, mask = O.make_inputs(cfg, 4, 1)
+    text, vid = text_of(ids, mask), video.cuda()
+    m1 = build(cfg, O.init_state_dict(cfg, 0), O.make_text_encoder(cfg, 0))
+    t1 = CTClipTrainStep(m1, lr=1e-3)
+    for _ in range(3):
+        t1.step(text, vid)
+    ck = tmp_path / "ck.pt"
+    t1.save(ck)
+    m2 = build(cfg, O.init_state_dict(cfg, 5), O.make_text_encoder(cfg, 5))      # different initial weights
+    t2 = CTClipTrainStep(m2, lr=1e-3)
+    t2.step(text, vid)                                                           # dirty moments / caches before the load
+    t2.load(ck)
+    assert t2.step_count == t1.step_count
+    assert torch.equal(t1.arena.m, t2.arena.m) and torch.equal(t1.arena.v, t2.arena.v)
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+    m1.eval(); m2.eval()
+    l1, l2 = float(t1.step(text, vid)), float(t2.step(text, vid))
+    assert abs(l1 - l2) <= 1e-5 * max(1.0, abs(l1)), (l1, l2)
+    # the bare model state_dict loads into a fresh CTCLIP the way CTCLIP.load does
+    sd = torch.load(str(ck))["model"]
+    m3 = build(cfg, O.init_state_dict(cfg, 7), O.make_text_encoder(cfg, 7))
+    missing = m3.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
