@@ -211,27 +211,42 @@ prep_resample_kernel(const PrepParams p, const float* __restrict__ lut, int lut_
 // q0 = c * 0.001f, q1 = fma(fma(-q0, 1000, c), 0.001f, q0) for all 2001 values (checked exhaustively in
 // tests/test_resample_oracle.py) — three FP32 instructions instead of a random-bank table look-up. Otherwise the exact
 // LUT is used.
-constexpr int FG = 8, FOH = 32, FCPR = 2;  // depth groups (warps), oh per CTA, 16-byte chunks per thread per row
-constexpr int FJP = 33;                    // shared row pitch (words): <= 32 columns + 1 -> transposing stores hit 32 banks
-constexpr int FKMAX = 16;                  // input depth planes a thread keeps in registers
+constexpr int FG = 8, FOH = 96;            // depth groups (warps), oh per CTA
+// Variant NC = 1: lane = one output column, 16 register planes (12 outputs per warp run at 4:3), row pitch 33 words.
+// Variant NC = 2: lane = TWO output columns `fw` apart (each group of fw columns spans <= 32 input words, so every
+// shared-memory load stays conflict-free); all three lerp levels run as packed FMUL2 / FFMA2 on the column pair, the depth /
+// height tap loads, the emission tests and the per-row bookkeeping are shared by the pair — about 0.6x the instructions
+// per output voxel. 10 register planes (6 outputs per warp run at 4:3), row pitch 69 words, 3 chunks per thread per row.
+template <int NC> struct FastCfg;
+template <> struct FastCfg<1> { static constexpr int KMAX = 16, CPR = 2, JP = 33; using W = float; };
+template <> struct FastCfg<2> { static constexpr int KMAX = 10, CPR = 3, JP = 69; using W = float2; };
 
-template <bool ARITH>
+__device__ __forceinline__ float lerpw(float t0, float w0, float t1, float w1) { return combine(t0, w0, t1, w1); }
+__device__ __forceinline__ float2 lerpw(float2 t0, float2 w0, float2 t1, float2 w1) { return ptx::ffma2(t0, w0, ptx::fmul2(t1, w1)); }
+__device__ __forceinline__ void splat(float& d, float v) { d = v; }
+__device__ __forceinline__ void splat(float2& d, float v) { d = make_float2(v, v); }
+
+template <bool ARITH, int NC>
 __global__ void __launch_bounds__(256, 2)
 prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_lo, int lut_n, int icpt, int ftd, int fw,
                     int kn8_max) {
+  using Cfg = FastCfg<NC>;
+  using W = typename Cfg::W;
+  constexpr int FKMAX = Cfg::KMAX, FCPR = Cfg::CPR, FJP = Cfg::JP;
   extern __shared__ float tile[];  // [3][kn8_max + 1][FJP] + FKMAX rows of slack | d taps [ftd] | h taps [FOH] | lut
   const int slot_elems = (kn8_max + 1) * FJP;
   float4* s_dtap = reinterpret_cast<float4*>(tile + ((3 * slot_elems + FKMAX * FJP + 3) & ~3));
   float4* s_htap = s_dtap + ftd;
   float* s_lut = reinterpret_cast<float*>(s_htap + FOH);
   const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
-  const int n_wt = (p.wwn + fw - 1) / fw;
+  const int ctw = NC * fw;   // output columns per CTA
+  const int n_wt = (p.wwn + ctw - 1) / ctw;
   const int oh_base = p.wh0 + blockIdx.x * FOH;
   const int n_oh = min(FOH, p.wh0 + p.whn - oh_base);
   const int od_base = p.wd0 + (blockIdx.y / n_wt) * ftd;
-  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * fw;
+  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * ctw;
   const int nd = min(ftd, p.wd0 + p.wdn - od_base);
-  const int nw = min(fw, p.ww0 + p.wwn - ow_base);
+  const int nw = min(ctw, p.ww0 + p.wwn - ow_base);
   const short* in16 = reinterpret_cast<const short*>(p.in) + (long long)blockIdx.z * p.sbatch;
 
   for (int z = tid; z < nd; z += 256) {
@@ -257,11 +272,21 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
   const int kc_n = (k_hi - k_lo8) / 8 + 1;   // 16-byte chunks per input column
   const int jn = j_hi - j_lo + 1;
   const int chunks = kc_n * jn;
-  // this thread's w taps
-  const bool ow_ok = lane < nw;
-  int ja, jb; float wa, wb;
-  taps(p.W, p.oW, ow_base + (ow_ok ? lane : nw - 1), ja, jb, wa, wb);
-  ja -= j_lo; jb -= j_lo;
+  // this thread's w taps: column lane + c * fw of the CTA's column tile
+  bool ow_ok[NC];
+  int ja[NC], jb[NC];
+  W wa, wb;
+  {
+    float fa[NC], fb[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = lane + c * fw;
+      ow_ok[c] = lane < fw && col < nw;
+      taps(p.W, p.oW, ow_base + (ow_ok[c] ? col : nw - 1), ja[c], jb[c], fa[c], fb[c]);
+      ja[c] -= j_lo; jb[c] -= j_lo;
+    }
+    if constexpr (NC == 1) { wa = fa[0]; wb = fb[0]; } else { wa = make_float2(fa[0], fa[1]); wb = make_float2(fb[0], fb[1]); }
+  }
   const int lut_hi = lut_lo + lut_n - 1;
   // chunk -> (column j, depth chunk kc) of this thread's staging slots (same for every row)
   int cj[FCPR], ck[FCPR];
@@ -336,15 +361,24 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
   }
   __syncthreads();
 
-  const int woff = (kf - k_lo8) * FJP + ja;      // word offset of W(kf) inside a slot
-  const int djb = jb - ja;                       // 0 or 1
-  float wA[FKMAX], wB[FKMAX];                    // w-interpolated planes of two input rows (rowA, rowB)
-  int rowA = -1, rowB = -1;
-  auto wrow = [&](int row, float (&w)[FKMAX]) {  // planes beyond kn_t read slack / stale words: never used
-    const float* ra = tile + (row % 3) * slot_elems + woff;
-    const float* rb = ra + djb;
+  int woff[NC], djb[NC];                         // word offset of W(kf) inside a slot ; jb - ja (0 or 1)
 #pragma unroll
-    for (int kk = 0; kk < FKMAX; ++kk) w[kk] = combine(ra[kk * FJP], wa, rb[kk * FJP], wb);
+  for (int c = 0; c < NC; ++c) { woff[c] = (kf - k_lo8) * FJP + ja[c]; djb[c] = jb[c] - ja[c]; }
+  W wA[FKMAX], wB[FKMAX];                        // w-interpolated planes of two input rows (rowA, rowB)
+  int rowA = -1, rowB = -1;
+  auto wrow = [&](int row, W (&w)[FKMAX]) {      // planes beyond kn_t read slack / stale words: never used
+    const float* ra = tile + (row % 3) * slot_elems + woff[0];
+    const float* rb = ra + djb[0];
+    if constexpr (NC == 1) {
+#pragma unroll
+      for (int kk = 0; kk < FKMAX; ++kk) w[kk] = lerpw(ra[kk * FJP], wa, rb[kk * FJP], wb);
+    } else {
+      const float* ra1 = tile + (row % 3) * slot_elems + woff[NC - 1];
+      const float* rb1 = ra1 + djb[NC - 1];
+#pragma unroll
+      for (int kk = 0; kk < FKMAX; ++kk)
+        w[kk] = lerpw(make_float2(ra[kk * FJP], ra1[kk * FJP]), wa, make_float2(rb[kk * FJP], rb1[kk * FJP]), wb);
+    }
   };
   const long long oplane = (long long)p.tH * p.tW;
   float* out_t = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
@@ -365,17 +399,28 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
     }
     if (kn_t > 0) {
       float* optr = out_t + (long long)(oh - p.wh0 + p.ph0) * p.tW;
-      auto march = [&](const float (&x)[FKMAX], const float (&y)[FKMAX]) {   // x: row h0, y: row h1
-        float pc = combine(x[0], wh0, y[0], wh1);
+      W vh0, vh1;
+      splat(vh0, wh0);
+      splat(vh1, wh1);
+      auto march = [&](const W (&x)[FKMAX], const W (&y)[FKMAX]) {   // x: row h0, y: row h1
+        W pc = lerpw(x[0], vh0, y[0], vh1);
         const float4* wp = s_dtap + zbeg;     // depth taps of the next output of this run
         float* op = optr;
 #pragma unroll
         for (int kk = 0; kk < FKMAX; ++kk) {
-          const float pn = (kk + 1 < FKMAX) ? combine(x[(kk + 1) % FKMAX], wh0, y[(kk + 1) % FKMAX], wh1) : pc;
+          const W pn = (kk + 1 < FKMAX) ? lerpw(x[(kk + 1) % FKMAX], vh0, y[(kk + 1) % FKMAX], vh1) : pc;
           if (emask & (1u << kk)) {           // warp-uniform
             const float4 tp = *wp++;
-            const float v = combine(pc, tp.y, pn, tp.z);
-            if (ow_ok) *op = v;
+            W t0, t1;
+            splat(t0, tp.y);
+            splat(t1, tp.z);
+            const W v = lerpw(pc, t0, pn, t1);
+            if constexpr (NC == 1) {
+              if (ow_ok[0]) *op = v;
+            } else {
+              if (ow_ok[0]) *op = v.x;
+              if (ow_ok[NC - 1]) op[fw] = v.y;
+            }
             op += oplane;
           }
           pc = pn;
@@ -516,26 +561,40 @@ extern "C" int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream) {
 }
 
 // fast path (see prep_hwn_i16_kernel); returns 1 when it does not apply
-template <bool ARITH>
+template <bool ARITH, int NC>
 static int launch_fast_t(const PrepParams& p, dim3 grid, size_t smem, float* lut_ws, int lut_lo, int lut_n, int icpt,
                          int ftd, int fw, int kn8, cudaStream_t s) {
   static size_t configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(prep_hwn_i16_kernel<ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+    if (cudaFuncSetAttribute(prep_hwn_i16_kernel<ARITH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess)
       return 1;
     configured = smem;
   }
-  prep_hwn_i16_kernel<ARITH><<<grid, 256, smem, s>>>(p, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8);
+  prep_hwn_i16_kernel<ARITH, NC><<<grid, 256, smem, s>>>(p, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8);
   return ctclip::check_launch("prep_resample(hwn/i16)");
 }
 
+template <int NC>
+static int launch_fast_nc(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s);
+
 static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s) {
+  const char* e = getenv("CTCLIP_PREP_X2");   // 0: one output column per lane only (A/B and test hook)
+  if (!(e != nullptr && e[0] == '0')) {
+    const int rc = launch_fast_nc<2>(p, batch, lut_ws, lut_lo, lut_n, s);
+    if (rc <= 0) return rc;
+  }
+  return launch_fast_nc<1>(p, batch, lut_ws, lut_lo, lut_n, s);
+}
+
+template <int NC>
+static int launch_fast_nc(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s) {
+  constexpr int FKMAX = FastCfg<NC>::KMAX, FCPR = FastCfg<NC>::CPR, FJP = FastCfg<NC>::JP;
   if (!p.in_is_i16 || lut_n <= 0 || p.sd != 1 || p.sw != p.D || (p.D % 8) || (p.sh % 8) || (p.sbatch % 8) ||
       (reinterpret_cast<uintptr_t>(p.in) % 16) || p.D < p.oD /* the k-indexed tap table needs depth down-sampling */)
     return 1;
   // depth run per warp: as long as the input planes it spans fit the FKMAX register planes
-  int opt = 12;
+  int opt = NC == 1 ? 12 : 7;
   auto planes_ok = [&](int o) {
     for (int b = p.wd0; b < p.wd0 + p.wdn; b += o) {
       const int e = (b + o < p.wd0 + p.wdn ? b + o : p.wd0 + p.wdn) - 1;
@@ -569,16 +628,16 @@ static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int l
   int fw = 32;
   while (fw >= 16 && max_span(p.W, p.oW, p.ww0, p.wwn, fw) > 32) --fw;
   if (fw < 16) return 1;
-  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, fw);
-  if ((kn8 / 8) * jn > FCPR * 256) return 1;
+  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, NC * fw);
+  if ((kn8 / 8) * jn > FCPR * 256 || jn > FJP - 1) return 1;
   p.jn_max = jn;
   const bool arith = p.slope == 1.0 && p.intercept == floor(p.intercept) && fabs(p.intercept) <= 32768.0;
   const size_t smem = (((size_t)3 * (kn8 + 1) * FJP + FKMAX * FJP + 3) & ~(size_t)3) * sizeof(float) +
                       (size_t)(ftd + FOH) * 16 + (arith ? 0 : (size_t)lut_n * sizeof(float));
   if (smem > 100 * 1024) return 1;
-  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + fw - 1) / fw)),
+  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + NC * fw - 1) / (NC * fw))),
             (unsigned)batch);
   const int icpt = arith ? (int)p.intercept : 0;
-  return arith ? launch_fast_t<true>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s)
-               : launch_fast_t<false>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s);
+  return arith ? launch_fast_t<true, NC>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s)
+               : launch_fast_t<false, NC>(p, grid, smem, lut_ws, lut_lo, lut_n, icpt, ftd, fw, kn8, s);
 }

@@ -390,9 +390,12 @@ def test_resample_full_size_volume_bit_exact_and_properties(ops):
     ((50, 50, 24), (0.75, 1.5), None, (2.0, -1000.0)),            # identity grid on every axis
     ((64, 64, 40), (0.703125, 1.125), (24, 70, 48), (1.0, 0.0)),  # centre crop (h) + pad(-1) (w) window
     ((30, 30, 128), (1.6, 4.0), None, (0.5, 12.5)),               # strong down-sampling on every axis, fractional HU
+    ((200, 136, 320), (0.703125, 1.125), None, (1.0, -1024.0)),   # production ratios (512->480-like 15/16, 320->240), two column tiles
+    ((96, 144, 160), (0.72, 1.2), (110, 90, 100), (1.0, 0.0)),    # ragged last column tile + crop / pad window
 ])
-def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spacing, target, hu):
-    """the depth-marching int16 (H,W,N) kernel and the generic brick kernel must agree bit for bit with the C oracle"""
+def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spacing, target, hu, monkeypatch):
+    """the depth-marching int16 (H,W,N) kernels (two output columns per lane, and the one-column variant selected by
+    CTCLIP_PREP_X2=0) and the generic brick kernel must agree bit for bit with the C oracle"""
     from ctpa_clip_b200.data_prep.preprocess import resize_shape
     rng = np.random.default_rng(11)
     raw = rng.integers(-2000, 3000, size=shape, dtype=np.int16)
@@ -402,10 +405,11 @@ def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spaci
     H, W, N = shape
     grid = resize_shape((N, H, W), (spacing[1], spacing[0], spacing[0]), (1.5, 0.75, 0.75))
     dev = torch.from_numpy(raw)[None].cuda()
-    for force in (False, True):
+    for force, x2 in ((False, "1"), (False, "0"), (True, "1")):
+        monkeypatch.setenv("CTCLIP_PREP_X2", x2)
         got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
         assert got.shape == want.shape
-        assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force}"
+        assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force} x2={x2}"
 
 
 # ---- DataLoader conversions on the GPU ---------------------------------------------------------------
