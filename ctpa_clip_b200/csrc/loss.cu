@@ -99,6 +99,42 @@ clip_grad_kernel(const float* __restrict__ T, const float* __restrict__ I, const
   }
 }
 
+// zero-shot scoring (ctclip_inference.py:286-336): for volume v and pathology p the reference forms the two logits
+// exp(tau) <I_v, T_{2p}> ("present") and exp(tau) <I_v, T_{2p+1}> ("not present") and keeps softmax(.)[0].
+// One warp per (v, p).
+__global__ void __launch_bounds__(256)
+zero_shot_kernel(const float* __restrict__ I, const float* __restrict__ T, const float* __restrict__ tau, int V, int P, int d,
+                 float* __restrict__ prob, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= (long long)V * P) return;
+  const int v = (int)(item / P), p = (int)(item % P);
+  const float* iv = I + (long long)v * d;
+  const float* t0 = T + (long long)(2 * p) * d;
+  const float* t1 = t0 + d;
+  float s0 = 0.f, s1 = 0.f;
+  for (int k = lane * 4; k < d; k += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(iv + k);
+    const float4 b = *reinterpret_cast<const float4*>(t0 + k);
+    const float4 c = *reinterpret_cast<const float4*>(t1 + k);
+    s0 += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+    s1 += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    const float et = __expf(*tau);
+    const float l0 = et * s0, l1 = et * s1;
+    const float m = fmaxf(l0, l1);
+    const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
+    prob[item] = e0 / (e0 + e1);
+    if (logits != nullptr) {
+      logits[2 * item] = l0;
+      logits[2 * item + 1] = l1;
+    }
+  }
+}
+
 // y = x / max(|x|, eps):  dx = (g - y <y, g>) * inv_norm          (F.normalize backward)
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv_norm, const float* __restrict__ g,
@@ -115,6 +151,28 @@ l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv_nor
 
 }  // namespace
 
+namespace ctclip {
+// logits already in work[0, B*B): row/column log-sum-exp, then loss + gradient of rows [row0, row0+rows_local).
+// Shared by ctclip_clip_loss and the peer-memory path (symm.cu: ctclip_clip_loss_allgather).
+int clip_lse_grad_launch(const float* T, const float* I, const float* tau, int B, int d, int row0, int rows_local,
+                         float* work, float* loss, float* dT, float* dI, float* dtau, cudaStream_t s) {
+  float* L = work;
+  float* lse = work + (long long)B * B;
+  clip_lse_kernel<<<(2 * B + 7) / 8, 256, 0, s>>>(L, B, lse);
+  int rc = ctclip::check_launch("clip_lse");
+  if (rc) return rc;
+  const int blocks = (dT != nullptr && dI != nullptr) ? 2 * rows_local : 0;
+  if (blocks > 0) {
+    clip_grad_kernel<<<blocks, 128, B * sizeof(float), s>>>(T, I, L, lse, tau, B, d, row0, rows_local, dT, dI, loss, dtau);
+  } else {
+    // loss only: a single "text row" block whose gradient rows land in the scratch tail of `work`
+    clip_grad_kernel<<<1, 128, B * sizeof(float), s>>>(T, I, L, lse, tau, B, d, 0, 1, work + (long long)B * B + 2 * B,
+                                                       work + (long long)B * B + 2 * B, loss, nullptr);
+  }
+  return ctclip::check_launch("clip_grad");
+}
+}  // namespace ctclip
+
 // T, I: fp32 [B][d] l2-normalised latents of the whole (global) batch; tau: device scalar (temperature parameter).
 // work: fp32 [B*B + 2*B]. Outputs: loss (device scalar), dT/dI fp32 [rows_local][d] (grad w.r.t. the normalised latents of
 // rows [row0, row0+rows_local)), dtau (+= this rank's share). Any of loss/dtau may be NULL.
@@ -126,25 +184,10 @@ extern "C" int ctclip_clip_loss(const float* T, const float* I, const float* tau
   int rc = ctclip::require_sm100();
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  float* L = work;
-  float* lse = work + (long long)B * B;
-  clip_logits_kernel<<<(unsigned)(((long long)B * B + 7) / 8), 256, 0, s>>>(T, I, tau, B, d, L);
+  clip_logits_kernel<<<(unsigned)(((long long)B * B + 7) / 8), 256, 0, s>>>(T, I, tau, B, d, work);
   rc = ctclip::check_launch("clip_logits");
   if (rc) return rc;
-  clip_lse_kernel<<<(2 * B + 7) / 8, 256, 0, s>>>(L, B, lse);
-  rc = ctclip::check_launch("clip_lse");
-  if (rc) return rc;
-  const int blocks = (dT != nullptr && dI != nullptr) ? 2 * rows_local : 0;
-  if (blocks > 0) {
-    clip_grad_kernel<<<blocks, 128, B * sizeof(float), s>>>(T, I, L, lse, tau, B, d, row0, rows_local, dT, dI, loss, dtau);
-  } else {
-    // loss only: run a single "text row" block that writes nothing but the loss
-    static float* dummy = nullptr;
-    (void)dummy;
-    clip_grad_kernel<<<1, 128, B * sizeof(float), s>>>(T, I, L, lse, tau, B, d, 0, 1, work + (long long)B * B + 2 * B,
-                                                       work + (long long)B * B + 2 * B, loss, nullptr);
-  }
-  return ctclip::check_launch("clip_grad");
+  return ctclip::clip_lse_grad_launch(T, I, tau, B, d, row0, rows_local, work, loss, dT, dI, dtau, s);
 }
 
 extern "C" int ctclip_l2norm_bwd(const float* y, const float* inv_norm, const float* g, long long rows, int dim, float* dx,
@@ -154,4 +197,15 @@ extern "C" int ctclip_l2norm_bwd(const float* y, const float* inv_norm, const fl
   if (rc) return rc;
   l2norm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(y, inv_norm, g, rows, dim, dx);
   return ctclip::check_launch("l2norm_bwd");
+}
+
+// I: fp32 [V][d] normalised image latents; T: fp32 [2P][d] normalised text latents ordered [present_0, absent_0, ...];
+// prob: fp32 [V][P] = softmax pair [0]; logits (may be NULL): fp32 [V][P][2].
+extern "C" int ctclip_zero_shot_scores(const float* I, const float* T, const float* tau, int V, int P, int d, float* prob,
+                                       float* logits, void* stream) {
+  if (V <= 0 || P <= 0 || d <= 0 || d % 4) return ctclip::fail(CTCLIP_E_SHAPE, "zero_shot_scores: bad shape V=%d P=%d d=%d", V, P, d);
+  int rc = ctclip::require_sm100();
+  if (rc) return rc;
+  zero_shot_kernel<<<(unsigned)(((long long)V * P + 7) / 8), 256, 0, (cudaStream_t)stream>>>(I, T, tau, V, P, d, prob, logits);
+  return ctclip::check_launch("zero_shot_scores");
 }

@@ -92,3 +92,23 @@ extern "C" int ctclip_last_error(char* buf, size_t n) {
 }
 
 extern "C" long long ctclip_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Caller-owned workspace sizes (bytes) of the entry points that take one; dims as documented per op in ctclip_b200.h.
+extern "C" long long ctclip_workspace_bytes(const char* op, const long long* dims, int ndims) {
+  if (op == nullptr || (ndims > 0 && dims == nullptr)) return -1;
+  auto need = [&](int n) { return ndims == n; };
+  const long long f = (long long)sizeof(float);
+  if (!strcmp(op, "clip_loss") && need(2)) return (dims[0] * dims[0] + 2 * dims[0] + dims[1]) * f;            // (B, d)
+  if (!strcmp(op, "clip_loss_allgather") && need(3)) {                                                        // (b_local, d, world)
+    const long long B = dims[0] * dims[2];
+    return (B * B + 2 * B + dims[1]) * f;
+  }
+  if ((!strcmp(op, "cpb_table_fwd") || !strcmp(op, "cpb_table_bwd")) && need(3)) {                            // (h, w, dim)
+    const long long R = (2 * dims[0] - 1) * (2 * dims[1] - 1);
+    return (!strcmp(op, "cpb_table_fwd") ? 2 * R + 2 * R * dims[2] : 2 * R * dims[2]) * f;
+  }
+  if (!strcmp(op, "bert_attn_bwd") && need(3)) return dims[0] * dims[1] * dims[2] * f;                        // (batch, heads, seq_len)
+  if (!strcmp(op, "prep_resample") && need(0)) return 8192 * f;                                               // exact HU table
+  ctclip::fail(CTCLIP_E_SHAPE, "workspace_bytes: unknown op '%s' or wrong number of dims (%d)", op, ndims);
+  return -1;
+}

@@ -7,6 +7,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .. import ops
+
 
 def exists(val):
     return val is not None
@@ -114,12 +116,27 @@ class ContinuousPositionBias(nn.Module):
             rel = torch.sign(rel) * torch.log(rel.abs() + 1)
         return rel.float()
 
-    def table(self, h, w, device):
-        """(heads, (2h-1)(2w-1)) bias per relative offset (query - key); entry (dy+h-1)*(2w-1) + (dx+w-1)"""
-        x = self.rel_offsets(h, w, device)
-        for layer in self.net:
-            x = layer(x)
-        return x.t().contiguous()
+    def _mlp(self):
+        if len(self.net) != 3 or self.num_dims != 2:
+            raise NotImplementedError("the CUDA path implements the CTViT configuration: 2 -> dim -> dim -> heads (layers=2)")
+        l0, l1, l2 = self.net[0][0], self.net[1][0], self.net[2]
+        return l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias
+
+    def table_fwd(self, h, w):
+        """(table [heads, (2h-1)(2w-1)], rowmax [heads, h*w], saved activations) from `ctclip_cpb_table_fwd`;
+        entry (dy+h-1)*(2w-1) + (dx+w-1) for the offset (dy, dx) = query - key"""
+        with torch.no_grad():
+            return ops.cpb_table_fwd(h, w, *[p.detach().float() for p in self._mlp()], log_dist=self.log_dist)
+
+    def table_bwd(self, h, w, acts, dtable):
+        """parameter gradients {name: grad} of the MLP from the table gradient (`ctclip_cpb_table_bwd`)"""
+        _, _, w1, _, w2, _ = self._mlp()
+        grads = ops.cpb_table_bwd(h, w, w1.detach().float(), w2.detach().float(), acts, dtable)
+        names = ("net.0.0.weight", "net.0.0.bias", "net.1.0.weight", "net.1.0.bias", "net.2.weight", "net.2.bias")
+        return dict(zip(names, grads))
+
+    def table(self, h, w, device=None):
+        return self.table_fwd(h, w)[0]
 
     def forward(self, *dimensions, device=None):
         """full (heads, h*w, h*w) bias, as the reference returns it (gathered from the table)"""

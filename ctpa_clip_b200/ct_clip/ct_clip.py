@@ -3,8 +3,10 @@ CTPA_CLIP/ct_clip/ct_clip.py:407-901 (image_encoder / text_encoder injected; ext
 FILIP/DCL and multiview branches are disabled by pretrained_model.py:37-40 and raise here if requested).
 
 The image tower, latent projections, l2norm and the symmetric InfoNCE run in libctclip_sm100.so. With
-torch.distributed initialised the loss is the GLOBAL-batch InfoNCE: every rank all-gathers the l2-normalised latents
-over NCCL/NVLink and differentiates its own rows; the reference's local-batch loss is the world_size=1 case.
+torch.distributed initialised the loss is the GLOBAL-batch InfoNCE: one kernel pushes every rank's l2-normalised latents
+into its peers' symmetric buffers over NVLink and forms the logits (csrc/symm.cu; NCCL all-gather with
+CTCLIP_LATENT_EXCHANGE=nccl), and every rank differentiates its own rows; the reference's local-batch
+loss is the world_size=1 case.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from .. import ops
+from .. import ops, symm
 from .ctvit import CTViT
 
 
@@ -85,18 +87,22 @@ class ClipLossFunction(torch.autograd.Function):
         t_hat, _, t_inv = ops.l2norm_rows(text_raw.contiguous().float(), want_f32=True)
         i_hat, _, i_inv = ops.l2norm_rows(image_raw.contiguous().float(), want_f32=True)
         b = t_hat.shape[0]
+        tau = temperature.detach().reshape(1).float().contiguous()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             ws, rank = dist.get_world_size(), dist.get_rank()
-            local = torch.stack((t_hat, i_hat))                                     # [2, b, d]
-            gathered = torch.empty((ws, *local.shape), device=local.device, dtype=local.dtype)
-            dist.all_gather_into_tensor(gathered, local)                            # 2*b*d fp32 per rank over NVLink
-            T = gathered[:, 0].reshape(ws * b, -1).contiguous()
-            I = gathered[:, 1].reshape(ws * b, -1).contiguous()
-            row0 = rank * b
+            ex = symm.get_exchange(b, t_hat.shape[1])
+            if ex is not None:
+                # ONE kernel pushes the latents into every peer's buffer over NVLink and forms the global-batch logits
+                loss, dT, dI, dtau = ops.clip_loss_allgather(t_hat, i_hat, tau, rank, ws, ex.table, ex.next_step())
+            else:
+                local = torch.stack((t_hat, i_hat))                                 # [2, b, d]
+                gathered = torch.empty((ws, *local.shape), device=local.device, dtype=local.dtype)
+                dist.all_gather_into_tensor(gathered, local)                        # 2*b*d fp32 per rank over NVLink
+                T = gathered[:, 0].reshape(ws * b, -1).contiguous()
+                I = gathered[:, 1].reshape(ws * b, -1).contiguous()
+                loss, dT, dI, dtau = ops.clip_loss(T, I, tau, rank * b, b, want_grad=True)
         else:
-            T, I, row0 = t_hat, i_hat, 0
-        tau = temperature.detach().reshape(1).float().contiguous()
-        loss, dT, dI, dtau = ops.clip_loss(T, I, tau, row0, b, want_grad=True)
+            loss, dT, dI, dtau = ops.clip_loss(t_hat, i_hat, tau, 0, b, want_grad=True)
         ctx.save_for_backward(t_hat, t_inv, i_hat, i_inv, dT, dI, dtau)
         return loss
 
@@ -248,6 +254,5 @@ class CTCLIP(nn.Module):
         Encodes every volume ONCE (the reference re-encodes it per pathology) and returns softmax-pair prob[present] (V, P)."""
         t_lat = L2NormFunction.apply(self.text_latents_raw(self.encode_text(prompt_pairs)))
         i_lat = L2NormFunction.apply(self.image_latents_raw(images))
-        logits = (i_lat @ t_lat.t()) * self.temperature.exp()                       # (V, 2P)
-        v = logits.shape[0]
-        return logits.view(v, -1, 2).softmax(dim=-1)[..., 0]
+        tau = self.temperature.detach().reshape(1).float().contiguous()
+        return ops.zero_shot_scores(i_lat, t_lat, tau)                              # (V, P) softmax-pair prob[present]

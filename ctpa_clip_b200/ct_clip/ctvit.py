@@ -208,7 +208,7 @@ class CTViT(nn.Module):
         x = tokens.reshape(-1, d).contiguous().float()
         grid = (b, t, h, w)
         with torch.no_grad():
-            tab, rowmax = engine.bias_tables(self, h, w, x.device)
+            tab, rowmax, _ = engine.bias_tables(self, h, w, x.device)
             for L in W.spatial:
                 x, _ = engine.layer_forward(x, L, grid, W.heads, False, tab, rowmax, False)
             _, _, x = ops.layernorm_fwd(x, W.s_out, None, want_bf16=False, want_f32=True)

@@ -114,13 +114,10 @@ def layer_forward(x, L: LayerWeights, grid, heads, temporal, tab, rowmax, save: 
     return x3, c
 
 
-def bias_tables(vit, h, w, device):
-    """(2h-1)(2w-1) relative-position bias table per head and its per-query-position maximum over keys"""
-    tab = vit.spatial_rel_pos_bias.table(h, w, device)                    # attention.py:257-276 on distinct offsets
-    from .ct_clip.attention import pair_index
-    idx = pair_index(h, w, device)
-    rowmax = tab[:, idx].amax(dim=-1).contiguous()
-    return tab, rowmax
+def bias_tables(vit, h, w, device=None):
+    """(2h-1)(2w-1) relative-position bias table per head, its per-query-position maximum over keys, and the MLP
+    activations kept for the backward (attention.py:257-276 on the distinct offsets; `ctclip_cpb_table_fwd`)"""
+    return vit.spatial_rel_pos_bias.table_fwd(h, w)
 
 
 def patch_embed_forward(W: EncoderWeights, video, save: bool):
@@ -141,8 +138,10 @@ def encoder_forward(vit, W: EncoderWeights, video, save: bool, tab=None, rowmax=
     x, ctx.pe = patch_embed_forward(W, video, save)
     if tab is None:
         with torch.no_grad():
-            tab, rowmax = bias_tables(vit, h, w, video.device)
-    ctx.tab, ctx.rowmax = tab, rowmax
+            tab, rowmax, cpb_acts = bias_tables(vit, h, w, video.device)
+    else:
+        cpb_acts = None
+    ctx.tab, ctx.rowmax, ctx.cpb_acts = tab, rowmax, cpb_acts
     ctx.spatial, ctx.temporal = [], []
     for L in W.spatial:
         x, c = layer_forward(x, L, grid, W.heads, False, tab, rowmax, save)
@@ -286,14 +285,13 @@ def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
     db1 = gs.zeros("to_patch_emb.1.bias", (W.pdim,))
     dwp_c = dwp[:, : W.pdim].contiguous() if a.shape[1] != W.pdim else dwp
     ops.patch_ln_param_grad(vit.to_patch_emb[2].weight.detach().contiguous(), dwp_c, dbias, W.pe_g, W.pe_b, dg1, db1)
-    # continuous position bias MLP: tiny (2h-1)(2w-1)-row parameter-only graph, differentiated by autograd
+    # continuous position bias MLP on the (2h-1)(2w-1) distinct offsets (`ctclip_cpb_table_bwd`)
     _, _, h, w = grid
-    with torch.enable_grad():
-        tab = vit.spatial_rel_pos_bias.table(h, w, dev)
-        cpb_params = list(vit.spatial_rel_pos_bias.parameters())
-        cpb_grads = torch.autograd.grad(tab, cpb_params, dtab)
+    acts = ctx.cpb_acts
+    if acts is None:
+        acts = vit.spatial_rel_pos_bias.table_fwd(h, w)[2]
     out = {}
-    for (name, _), gr in zip(vit.spatial_rel_pos_bias.named_parameters(), cpb_grads):
+    for name, gr in vit.spatial_rel_pos_bias.table_bwd(h, w, acts, dtab).items():
         out["spatial_rel_pos_bias." + name] = gr
     # kernel layouts -> reference parameter shapes
     for name, t in gs.g.items():

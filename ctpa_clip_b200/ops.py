@@ -382,6 +382,68 @@ def clip_loss(T, I, tau, row0, rows_local, want_grad=True):
     return loss, dT, dI, dtau
 
 
+def clip_loss_allgather(t_hat, i_hat, tau, rank, world, peer_table, step):
+    """Peer-memory latent exchange fused with the global-batch logits (csrc/symm.cu), then lse + gradient of the local rows.
+    t_hat, i_hat fp32 [b, d] normalised LOCAL latents; peer_table: ctypes array of `world` symmetric-buffer pointers."""
+    b, d = t_hat.shape
+    B = world * b
+    work = torch.empty(B * B + 2 * B + d, device=t_hat.device, dtype=torch.float32)
+    loss = torch.zeros((), device=t_hat.device, dtype=torch.float32)
+    dT = torch.empty((b, d), device=t_hat.device, dtype=torch.float32)
+    dI = torch.empty((b, d), device=t_hat.device, dtype=torch.float32)
+    dtau = torch.zeros((), device=t_hat.device, dtype=torch.float32)
+    _call("ctclip_clip_loss_allgather", _ptr(t_hat), _ptr(i_hat), _ptr(tau), b, d, rank, world, peer_table, C.c_uint(step),
+          _ptr(work), _ptr(loss), _ptr(dT), _ptr(dI), _ptr(dtau), _stream())
+    return loss, dT, dI, dtau
+
+
+def cpb_table_fwd(h, w, W0, b0, W1, b1, W2, b2, log_dist=True, want_rowmax=True):
+    """continuous-position-bias MLP on the (2h-1)(2w-1) distinct offsets -> (table [heads, R], rowmax [heads, h*w], acts)"""
+    dim, heads = W1.shape[0], W2.shape[0]
+    for t in (W0, b0, W1, b1, W2, b2):
+        _req(t, torch.float32, "cpb_table_fwd")
+    R = (2 * h - 1) * (2 * w - 1)
+    dev = W0.device
+    acts = torch.empty(2 * R + 2 * R * dim, device=dev, dtype=torch.float32)
+    table = torch.empty((heads, R), device=dev, dtype=torch.float32)
+    rowmax = torch.empty((heads, h * w), device=dev, dtype=torch.float32) if want_rowmax else None
+    _call("ctclip_cpb_table_fwd", h, w, dim, heads, int(log_dist), _ptr(W0.contiguous()), _ptr(b0.contiguous()),
+          _ptr(W1.contiguous()), _ptr(b1.contiguous()), _ptr(W2.contiguous()), _ptr(b2.contiguous()), _ptr(acts), _ptr(table),
+          _ptr(rowmax), _stream())
+    return table, rowmax, acts
+
+
+def cpb_table_bwd(h, w, W1, W2, acts, dtable):
+    """gradients of the CPB MLP parameters from dtable [heads, R]: (dW0, db0, dW1, db1, dW2, db2)"""
+    dim, heads = W1.shape[0], W2.shape[0]
+    R = (2 * h - 1) * (2 * w - 1)
+    dev = W1.device
+    _req(dtable, torch.float32, "cpb_table_bwd")
+    work = torch.empty(2 * R * dim, device=dev, dtype=torch.float32)
+    dW0 = torch.empty((dim, 2), device=dev, dtype=torch.float32)
+    db0 = torch.empty(dim, device=dev, dtype=torch.float32)
+    dW1 = torch.empty((dim, dim), device=dev, dtype=torch.float32)
+    db1 = torch.empty(dim, device=dev, dtype=torch.float32)
+    dW2 = torch.empty((heads, dim), device=dev, dtype=torch.float32)
+    db2 = torch.empty(heads, device=dev, dtype=torch.float32)
+    _call("ctclip_cpb_table_bwd", h, w, dim, heads, _ptr(W1.contiguous()), _ptr(W2.contiguous()), _ptr(acts),
+          _ptr(dtable.contiguous()), _ptr(work), _ptr(dW0), _ptr(db0), _ptr(dW1), _ptr(db1), _ptr(dW2), _ptr(db2), _stream())
+    return dW0, db0, dW1, db1, dW2, db2
+
+
+def zero_shot_scores(i_hat, t_hat, tau, want_logits=False):
+    """i_hat fp32 [V, d], t_hat fp32 [2P, d] (present/absent pairs) -> prob[present] [V, P] (+ logits [V, P, 2])"""
+    _req(i_hat, torch.float32, "zero_shot_scores")
+    _req(t_hat, torch.float32, "zero_shot_scores")
+    V, d = i_hat.shape
+    P = t_hat.shape[0] // 2
+    prob = torch.empty((V, P), device=i_hat.device, dtype=torch.float32)
+    logits = torch.empty((V, P, 2), device=i_hat.device, dtype=torch.float32) if want_logits else None
+    _call("ctclip_zero_shot_scores", _ptr(i_hat.contiguous()), _ptr(t_hat.contiguous()), _ptr(tau), V, P, d, _ptr(prob),
+          _ptr(logits), _stream())
+    return (prob, logits) if want_logits else prob
+
+
 def sumsq(g, out):
     _call("ctclip_sumsq", _ptr(g), _ll(g.numel()), _ptr(out), _stream())
 

@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - plain pointers + sizes, no torch types. All pointers are DEVICE pointers unless named host_*.
- *   - the library never allocates, frees or retains device memory; workspaces are caller-owned.
+ *   - the library never allocates, frees or retains device memory; workspaces are caller-owned. The one
+ *     exception are the explicitly registered symmetric buffers of the peer-memory latent exchange (ctclip_symm_*).
  *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no internal syncs.
  *   - return 0 on success, negative CTCLIP_E_* otherwise; text via ctclip_last_error (thread-local).
  *   - there is NO CPU fallback: on a non-sm_100 device every compute entry returns CTCLIP_E_ARCH.
@@ -32,6 +33,10 @@ extern "C" {
 int ctclip_version(void);
 /* copies the calling thread's last error text into buf (NUL-terminated); returns its length */
 int ctclip_last_error(char* buf, size_t n);
+/* bytes of the caller-owned workspace of an entry point: op in {"clip_loss" (B, d), "clip_loss_allgather" (b_local, d, world),
+ * "cpb_table_fwd" (h, w, dim) [the `acts` buffer], "cpb_table_bwd" (h, w, dim), "bert_attn_bwd" (batch, heads, seq_len),
+ * "prep_resample" () [lut_workspace]}; -1 for an unknown op / wrong ndims. Pure host arithmetic. */
+long long ctclip_workspace_bytes(const char* op, const long long* dims, int ndims);
 /* number of kernels launched by this process through the library since load (bench.py: gpu_launches) */
 long long ctclip_launch_count(void);
 
@@ -193,6 +198,56 @@ int ctclip_vq_ema_update(float* embed, float* cluster_size, const float* bins, c
  * rows [row0,row0+rows_local) (NULL -> loss only). dtau += this rank's share of dloss/dtemperature. */
 int ctclip_clip_loss(const float* T, const float* I, const float* tau, int B, int d, int row0, int rows_local, float* work,
                      float* loss, float* dT, float* dI, float* dtau, void* stream);
+
+/* Zero-shot scoring (ctclip_inference.py:286-336, CTCLIPTrainer.py:356-454): I fp32 [V][d] normalised image latents (each
+ * volume encoded ONCE; the reference re-encodes it per pathology), T fp32 [2P][d] normalised prompt latents ordered
+ * [present_0, absent_0, present_1, ...]. prob[v][p] = softmax(exp(tau) <I_v, T_2p>, exp(tau) <I_v, T_2p+1>)[0];
+ * logits (may be NULL): fp32 [V][P][2]. */
+int ctclip_zero_shot_scores(const float* I, const float* T, const float* tau, int V, int P, int d, float* prob, float* logits,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel InfoNCE over NVLink peer memory: the all-gather of the l2-normalised latents fused with
+ * the global-batch logits. The reference trains with local-batch InfoNCE under DDP (CTCLIPTrainer.py:213-217 around
+ * ct_clip.py:845-878); this entry replaces "NCCL all-gather -> ctclip_clip_loss" of the global-batch extension.
+ *
+ * Symmetric buffers: every rank allocates one buffer of ctclip_symm_latent_bytes(b_local, d, world) bytes with
+ * ctclip_symm_alloc (plain cudaMalloc, zero-filled: the ONE place the library owns device memory, because CUDA IPC can
+ * only export cudaMalloc allocations), exports a 64-byte IPC handle (ctclip_symm_export), exchanges handles out of band
+ * (torch.distributed all_gather_object) and maps every peer's buffer (ctclip_symm_import; peer access is enabled
+ * lazily). host_peer_bufs is a HOST array of `world` device pointers, [rank] = the rank's own buffer.
+ *
+ * ctclip_clip_loss_allgather: t_hat / i_hat fp32 [b_local][d] are THIS rank's normalised latents. One kernel pushes
+ * them into every peer's buffer (16-byte peer stores + st.release.sys of a per-rank flag carrying `step`) and computes
+ * each b_local x b_local block of L = exp(tau) T I^T as soon as the two ranks it depends on have arrived
+ * (ld.acquire.sys); then the log-sum-exp and gradient kernels of ctclip_clip_loss run on the gathered latents in
+ * place. `step` must be the same on all ranks, start at 1 and increase by 1 per call (two buffer parities); all ranks
+ * must call collectively, on one stream per rank. A peer that does not arrive within 20 s turns the loss into NaN
+ * instead of hanging. work: fp32 [B*B + 2*B + d] with B = world*b_local; outputs as ctclip_clip_loss. */
+size_t ctclip_symm_latent_bytes(int b_local, int d, int world);
+int ctclip_symm_alloc(size_t bytes, void** ptr);
+int ctclip_symm_free(void* ptr);
+int ctclip_symm_export(void* ptr, unsigned char* handle64);
+int ctclip_symm_import(const unsigned char* handle64, void** ptr);
+int ctclip_symm_unimport(void* ptr);
+int ctclip_clip_loss_allgather(const float* t_hat, const float* i_hat, const float* tau, int b_local, int d, int rank,
+                               int world, void* const* host_peer_bufs, unsigned step, float* work, float* loss, float* dT,
+                               float* dI, float* dtau, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Continuous position bias (attention.py:229-276; called ctvit.py:317): the 2 -> dim -> dim -> heads MLP with
+ * LeakyReLU(0.1) on sign(v)*log(|v|+1) of the relative offsets of an h x w grid, evaluated on the R = (2h-1)(2w-1)
+ * DISTINCT offsets (the reference evaluates all (h*w)^2 pairs). table[head][(dy+h-1)*(2w-1) + (dx+w-1)] for the offset
+ * (dy, dx) = query - key; the attention kernels gather from it. rowmax (may be NULL): fp32 [heads][h*w] = max over
+ * keys of the gathered bias per query position. acts: fp32 workspace [2*R + 2*R*dim] kept for the backward.
+ * W0 [dim][2], b0 [dim], W1 [dim][dim], b1 [dim], W2 [heads][dim], b2 [heads] = net.0.0 / net.1.0 / net.2 of the module.
+ * Backward: dtable fp32 [heads][R]; work fp32 [2*R*dim]; the six gradients are overwritten. fp32 throughout. */
+int ctclip_cpb_table_fwd(int h, int w, int dim, int heads, int log_dist, const float* W0, const float* b0, const float* W1,
+                         const float* b1, const float* W2, const float* b2, float* acts, float* table, float* rowmax,
+                         void* stream);
+int ctclip_cpb_table_bwd(int h, int w, int dim, int heads, const float* W1, const float* W2, const float* acts,
+                         const float* dtable, float* work, float* dW0, float* db0, float* dW1, float* db1, float* dW2,
+                         float* db2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Trainer step (CTCLIPTrainer.py:347-353, optimizer.py:10-24) on flat fp32 arenas: sum of squares for the global-norm

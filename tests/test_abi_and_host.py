@@ -92,3 +92,34 @@ def test_unused_parameter_set_is_static():
     fx = torch.load("tests/golden/ctclip_tiny.pt", weights_only=False)
     with_grad = set(fx["grads"].keys())            # parameters the REFERENCE's backward touches
     assert set(names) == with_grad
+
+
+def test_workspace_bytes_host_arithmetic():
+    """ctclip_workspace_bytes is pure host code: sizes equal the buffers ctpa_clip_b200.ops allocates"""
+    from ctpa_clip_b200 import _lib
+    lib = _lib.lib()
+    lib.ctclip_workspace_bytes.restype = ctypes.c_longlong
+
+    def ws(op, *dims):
+        arr = (ctypes.c_longlong * max(1, len(dims)))(*dims)
+        return lib.ctclip_workspace_bytes(op.encode(), arr, len(dims))
+
+    assert ws("clip_loss", 64, 512) == (64 * 64 + 128 + 512) * 4
+    assert ws("clip_loss_allgather", 8, 512, 8) == (64 * 64 + 128 + 512) * 4
+    R = 47 * 47
+    assert ws("cpb_table_fwd", 24, 24, 512) == (2 * R + 2 * R * 512) * 4
+    assert ws("cpb_table_bwd", 24, 24, 512) == 2 * R * 512 * 4
+    assert ws("bert_attn_bwd", 8, 12, 512) == 8 * 12 * 512 * 4
+    assert ws("prep_resample") == 8192 * 4
+    assert ws("no_such_op", 1) == -1
+    assert "unknown op" in _lib.last_error()
+
+
+def test_symmetric_buffer_layout_size():
+    """ctclip_symm_latent_bytes: flag header + two parities of [T; I] for the whole global batch (host arithmetic only)"""
+    from ctpa_clip_b200 import _lib
+    lib = _lib.lib()
+    lib.ctclip_symm_latent_bytes.restype = ctypes.c_size_t
+    assert lib.ctclip_symm_latent_bytes(8, 512, 8) == (2 * 32 * 8 + 2 * 2 * 64 * 512) * 4
+    assert lib.ctclip_symm_latent_bytes(8, 512, 33) == 0          # more ranks than the flag header holds
+    assert lib.ctclip_symm_latent_bytes(0, 512, 2) == 0

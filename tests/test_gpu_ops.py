@@ -484,3 +484,48 @@ def test_column_sums(ops, rows, dim):
         outs = torch.zeros(d, device="cuda")
         ops.colsum_bf16(xb[:, d:2 * d], outs, dim=d, ld=dim)
         close(outs, xb[:, d:2 * d].double().sum(0).float(), 2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ continuous position bias
+@pytest.mark.parametrize("h,w,dim,heads", [(24, 24, 512, 8), (3, 5, 64, 4), (2, 2, 96, 3)])
+def test_cpb_table_fwd_bwd(ops, h, w, dim, heads):
+    """ctclip_cpb_table_{fwd,bwd} vs the reference MLP (attention.py:229-276) evaluated by torch on ALL (h*w)^2 pairs in fp32:
+    the table gathered to (heads, n, n) must equal the reference bias, and the parameter gradients must match autograd."""
+    from ctpa_clip_b200.ct_clip.attention import ContinuousPositionBias, pair_index
+    torch.manual_seed(h * 100 + w)
+    cpb = ContinuousPositionBias(dim=dim, heads=heads).cuda()
+    # reference restatement, full pair grid exactly as attention.py:257-276 builds it
+    pos = torch.stack(torch.meshgrid(torch.arange(h, device="cuda"), torch.arange(w, device="cuda"), indexing="ij"))
+    grid = pos.reshape(2, -1).t()
+    rel = (grid[:, None, :] - grid[None, :, :]).float()
+    rel = torch.sign(rel) * torch.log(rel.abs() + 1)
+    x = rel
+    for layer in cpb.net:
+        x = layer(x)
+    ref = x.permute(2, 0, 1)                                            # 'i j h -> h i j'
+    tab, rowmax, acts = cpb.table_fwd(h, w)
+    idx = pair_index(h, w, "cuda")
+    close(tab[:, idx], ref, 2e-5)
+    close(rowmax, ref.amax(dim=-1), 2e-5)
+    close(cpb(h, w), ref, 2e-5)                                         # module forward = gathered table
+    g = torch.randn(heads, h * w, h * w, device="cuda")
+    ref_grads = torch.autograd.grad(ref, list(cpb.parameters()), g)
+    dtab = torch.zeros_like(tab).index_add_(1, idx.reshape(-1), g.reshape(heads, -1))
+    got = cpb.table_bwd(h, w, acts, dtab)
+    for (name, _), rg in zip(cpb.named_parameters(), ref_grads):
+        close(got[name], rg, 2e-4)
+
+
+# ------------------------------------------------------------------------------------------------ zero-shot scoring
+@pytest.mark.parametrize("V,P,d", [(32, 18, 512), (5, 3, 64), (1, 1, 4)])
+def test_zero_shot_scores_kernel(ops, V, P, d):
+    """ctclip_zero_shot_scores vs the reference's per-pathology pattern (ctclip_inference.py:318-330): softmax over the
+    (present, absent) logit pair, element 0."""
+    g = torch.Generator(device="cuda").manual_seed(V * 7 + P)
+    I = F.normalize(torch.randn(V, d, device="cuda", generator=g), dim=-1)
+    T = F.normalize(torch.randn(2 * P, d, device="cuda", generator=g), dim=-1)
+    tau = torch.tensor([2.3], device="cuda")
+    prob, logits = ops.zero_shot_scores(I, T, tau, want_logits=True)
+    ref_logits = (I.double() @ T.double().t() * tau.double().exp()).view(V, P, 2)
+    assert torch.allclose(logits.double(), ref_logits, atol=1e-4)
+    assert torch.allclose(prob.double(), ref_logits.softmax(dim=-1)[..., 0], atol=1e-5)
