@@ -249,10 +249,16 @@ class CTCLIP(nn.Module):
 
     # ---------------------------------------------------------------- batched zero-shot scoring (ctclip_inference.py:286-336)
     @torch.no_grad()
-    def zero_shot_scores(self, prompt_pairs, images):
+    def prompt_latents(self, prompt_pairs):
+        """l2-normalised text latents (2P, d) of tokenised prompt rows [present_0, absent_0, present_1, ...]"""
+        return L2NormFunction.apply(self.text_latents_raw(self.encode_text(prompt_pairs)))
+
+    @torch.no_grad()
+    def zero_shot_scores(self, prompt_pairs, images, prompt_latents=None):
         """prompt_pairs: tokenised (P*2, L) rows ordered [present_0, absent_0, present_1, ...]; images (V,1,f,h,w).
-        Encodes every volume ONCE (the reference re-encodes it per pathology) and returns softmax-pair prob[present] (V, P)."""
-        t_lat = L2NormFunction.apply(self.text_latents_raw(self.encode_text(prompt_pairs)))
+        Encodes every volume ONCE (the reference re-encodes it, and the prompts, per pathology) and returns the softmax-pair
+        prob[present] (V, P). `prompt_latents` (from `prompt_latents()`) skips the text tower for a fixed prompt set."""
+        t_lat = prompt_latents if prompt_latents is not None else self.prompt_latents(prompt_pairs)
         i_lat = L2NormFunction.apply(self.image_latents_raw(images))
         tau = self.temperature.detach().reshape(1).float().contiguous()
         return ops.zero_shot_scores(i_lat, t_lat, tau)                              # (V, P) softmax-pair prob[present]

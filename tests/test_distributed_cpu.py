@@ -61,3 +61,37 @@ def test_global_infonce_partition_two_ranks():
         assert torch.allclose(dT, T.grad[r * b:(r + 1) * b], atol=1e-6)
         assert torch.allclose(dI, I.grad[r * b:(r + 1) * b], atol=1e-6)
         assert torch.allclose(dtau, tau.grad, atol=1e-6)
+
+
+# ---------------------------------------------------------------- zero-shot evaluation: replicas, round-robin shards (config 5)
+def _gather_worker(rank, world, port, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ctpa_clip_b200.inference import gather_rows, shard_indices
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)         # row i = "scores of volume i"
+    mine = shard_indices(n, rank, world)
+    out = gather_rows(full[mine], n, rank, world)
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 8, 1])
+def test_zero_shot_shard_and_gather_two_ranks(n):
+    """every rank ends with the (N, P) score matrix in dataset order, also when N is not a multiple of the world size"""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_gather_worker, args=(world, 29618 + n, n, ret), nprocs=world, join=True)
+    want = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    for r in range(world):
+        assert torch.equal(ret[r], want)
+
+
+def test_zero_shot_prompts_and_aurocs():
+    from ctpa_clip_b200 import inference as inf
+    texts = inf.prompt_texts()
+    assert len(texts) == 36 and texts[0] == "Medical material is present." and texts[1] == "Medical material is not present."
+    assert texts[22:24] == ["Pulmonary Embolism is present.", "Pulmonary Embolism is not present."]   # ctclip_inference.py:318
+    pred = torch.tensor([[0.9, 0.2], [0.8, 0.7], [0.3, 0.6], [0.1, 0.4]]).numpy()
+    real = torch.tensor([[1, 0], [1, 1], [0, 0], [0, 1]]).numpy()
+    a = inf.aurocs(pred, real, ["a", "b"])
+    assert a["a_auc"] == 1.0 and abs(a["b_auc"] - 0.75) < 1e-9

@@ -206,3 +206,19 @@ def test_trainer_checkpoint_round_trip(tmp_path):
     m3 = build(cfg, O.init_state_dict(cfg, 7), O.make_text_encoder(cfg, 7))
     missing = m3.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys
+
+
+def test_zero_shot_evaluator_encodes_once_and_matches_per_volume_scoring():
+    """ZeroShotEvaluator (prompt latents cached, volumes batched, scores by ctclip_zero_shot_scores) must reproduce
+    CTCLIP.zero_shot_scores volume by volume — i.e. the reference's one-volume-at-a-time loop (ctclip_inference.py:305-336)"""
+    from ctpa_clip_b200.inference import ZeroShotEvaluator
+    cfg = O.TINY
+    m = build(cfg, O.init_state_dict(cfg, 0), O.make_text_encoder(cfg, 0)).eval()
+    video, ids, mask = O.make_inputs(cfg, 5, 3)
+    p_ids, p_mask = ids[:4].repeat(2, 1)[:6].clone(), mask[:4].repeat(2, 1)[:6].clone()      # 3 pathologies x 2 prompts
+    p_ids[:, 1] = torch.arange(6) + 5
+    ev = ZeroShotEvaluator(m, text_of(p_ids, p_mask), batch_size=2)
+    pred, real = ev.evaluate([v for v in video], labels=[[1, 0, 0]] * 5)
+    assert pred.shape == (5, 3) and real.shape == (5, 3)
+    one_by_one = torch.cat([m.zero_shot_scores(text_of(p_ids, p_mask), video[i:i + 1].cuda()) for i in range(5)]).cpu()
+    assert torch.allclose(torch.from_numpy(pred), one_by_one, atol=2e-3)   # batch-of-2 vs batch-of-1 GEMM shapes (bf16 operands)
