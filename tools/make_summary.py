@@ -21,21 +21,23 @@ other = tot - sum(g.values())
 L = []
 L.append("# Round 1 — measurement summary (1×B200 unless noted; B = 8 volumes 480×480×240 + 8 reports × 512 ids per rank)\n")
 L.append("All numbers are CUDA-event timings from `bench.py` / `tools/bench_components.py` runs on the GPU box (no profiler attached);")
-L.append("ncu evidence: `r01_ncu_launches_v5.txt` + `r01_step_traffic.json` (launch list and DRAM bytes of one training step), `r01_ncu_kernels_v3.txt` / `r01_ncu_kernels_v7.txt` (`--set full` extracts).\n")
+L.append("ncu evidence: `r01_ncu_launches_v8.txt` + `r01_step_traffic.json` (launch list and DRAM bytes of one training step), `r01_ncu_kernels_v3.txt` / `r01_ncu_kernels_v7.txt` (`--set full` extracts).\n")
 L.append(f"## Headline (`r01_bench_{tag}.log`)\n")
-L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (session start: 79.2 ms / 101 volumes/s with the text tower still on torch; previous snapshot v4: 58.8 ms)")
+L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (session start: 79.2 ms / 101 volumes/s with the text tower still on torch; previous snapshots v4: 58.8 ms, v7: 52.1 ms)")
 L.append(f"* end to end (pinned host volumes → H2D on a copy stream → step → `loss.item()` every step): **{bench['e2e']['value']:.1f} volumes/s** ({bench['e2e']['ms_per_step']:.1f} ms/step, {bench['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB H2D per step)")
 L.append(f"* all `gemm_bf16_kernel` launches of the step: {bench['roofline']['achieved']:.0f} TFLOP/s = {100 * bench['roofline']['frac']:.0f} % of the measured sustained cuBLAS bf16 rate, {100 * bench['roofline']['share_of_step']:.0f} % of the step")
 try:
     b2 = json.loads([l for l in open(f"profiles/r01_bench_2gpu_{tag}.log") if l.startswith("{")][-1])
-    L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log`, weak scaling, global batch 16, latents all-gathered, gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
+    L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log`, weak scaling, global batch 16, latents exchanged by the fused peer-memory loss kernel (NCCL arm: `r01_bench_2gpu_v8_nccl.log`), gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
 except FileNotFoundError:
     pass
-try:
-    br = json.loads([l for l in open(f"profiles/r01_bench_reference_arm_{tag}.log") if l.startswith("{")][-1])
-    L.append(f"* `bench.py --impl reference` (the reference's CPU path, oracle port on all host threads): {br['value']:.2f} volumes/s")
-except FileNotFoundError:
-    pass
+for rtag in (tag, "v7"):   # the reference arm does not depend on our kernels: the last measured run is reused
+    try:
+        br = json.loads([l for l in open(f"profiles/r01_bench_reference_arm_{rtag}.log") if l.startswith("{")][-1])
+        L.append(f"* `bench.py --impl reference` (the reference's CPU path, oracle port on all host threads; `r01_bench_reference_arm_{rtag}.log`): {br['value']:.2f} volumes/s")
+        break
+    except FileNotFoundError:
+        pass
 L.append(f"* CPU oracle (fp32 port of the reference, {bench['cpu_baseline']['cores']} host threads): {bench['cpu_baseline']['value']:.2f} volumes/s\n")
 L.append("## Where the step goes (`r01_step_breakdown_%s.json`, one instrumented step, Σ = %.1f ms of the %.1f ms step)\n" % (tag, tot, d["ms_per_step"]))
 L.append("| group | ms | share |\n|---|---|---|")
