@@ -46,7 +46,7 @@ class LinearFunction(torch.autograd.Function):
     """y = x W^T (bias-free nn.Linear, ct_clip.py:549,564) on the tcgen05 GEMM; fp32 accumulate, fp32 out"""
 
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, x_bf16, direct=False, ready=None):
+    def forward(ctx, x, weight, w_bf16, x_bf16, direct=False, ready=None, factor_gather=False):
         xb = x_bf16 if x_bf16 is not None else ops.cast_bf16(x.contiguous().float())
         M = xb.shape[0]
         y = torch.zeros((M, weight.shape[0]), device=x.device, dtype=torch.float32)
@@ -55,6 +55,7 @@ class LinearFunction(torch.autograd.Function):
         ctx.need = (x.requires_grad, weight.requires_grad)
         ctx.weight = weight if direct else None
         ctx.ready = ready
+        ctx.factor_gather = factor_gather
         return y
 
     @staticmethod
@@ -70,12 +71,25 @@ class LinearFunction(torch.autograd.Function):
                 # direct mode: accumulate into the parameter's gradient buffer (no 600 MB temporary + add for the
                 # 294912 -> 512 projection); autograd gets None
                 # (in-place "+=" through the residual epilogue: plain 128-bit loads / stores instead of 151 M atomics)
-                ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, resid=w.grad)
-                if ctx.ready is not None:
-                    ctx.ready([w])       # this gradient is final: the trainer may start its all-reduce now
+                if ctx.factor_gather and dist.is_initialized() and dist.get_world_size() > 1:
+                    # dW = dy^T x is rank-B: all-gather the two FACTORS (B_loc x N and B_loc x K bf16, 4.7 MB per rank for
+                    # the 294912 -> 512 projection) and form the global-batch gradient locally, instead of all-reducing
+                    # the N x K fp32 product (604 MB) — SURVEY 7.2-6 / 8(e). Every rank ends with the identical sum.
+                    ws = dist.get_world_size()
+                    dy_all = torch.empty((ws * dyb.shape[0], dyb.shape[1]), device=dyb.device, dtype=dyb.dtype)
+                    x_all = torch.empty((ws * xb.shape[0], xb.shape[1]), device=xb.device, dtype=xb.dtype)
+                    dist.all_gather_into_tensor(dy_all, dyb.contiguous())
+                    dist.all_gather_into_tensor(x_all, xb.contiguous())
+                    ops.gemm(dy_all, x_all, a_t=True, b_t=True, out=w.grad, resid=w.grad)
+                    if ctx.ready is not None:
+                        ctx.ready([w], reduced=True)     # already the sum over ranks: no all-reduce for this span
+                else:
+                    ops.gemm(dyb, xb, a_t=True, b_t=True, out=w.grad, resid=w.grad)
+                    if ctx.ready is not None:
+                        ctx.ready([w])   # this gradient is final: the trainer may start its all-reduce now
             else:
                 dw = ops.gemm(dyb, xb, a_t=True, b_t=True, out_dtype=torch.float32)  # [N, K], reduction over the batch
-        return dx, dw, None, None, None, None
+        return dx, dw, None, None, None, None, None
 
 
 class ClipLossFunction(torch.autograd.Function):
@@ -184,6 +198,7 @@ class CTCLIP(nn.Module):
         # set by CTClipTrainStep: kernels accumulate parameter gradients straight into the existing p.grad buffers
         self.direct_grad = False
         self.grad_ready = None      # optional callable(list of parameters): their .grad is final (direct mode only)
+        self.factor_gather = False  # data-parallel: all-gather the factors of the rank-B to_visual_latent gradient (trainer sets it)
         self._sh_text, self._sh_vis = _Shadow(), _Shadow()
 
     def load(self, path):
@@ -221,7 +236,7 @@ class CTCLIP(nn.Module):
         vit = self.visual_transformer
         pooled = vit.encode_pooled(image)                                           # ct_clip.py:715,724,740
         return LinearFunction.apply(pooled, self.to_visual_latent.weight, self._sh_vis.get(self.to_visual_latent.weight),
-                                    vit.last_pooled_bf16, self.direct_grad, self.grad_ready)
+                                    vit.last_pooled_bf16, self.direct_grad, self.grad_ready, self.factor_gather)
 
     # ---------------------------------------------------------------- forward (ct_clip.py:614-901)
     def forward(self, text, image, device=None, return_loss=False, return_encodings=False, return_latents=False,

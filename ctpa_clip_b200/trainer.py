@@ -6,6 +6,7 @@ Adam-moment arenas, so clipping and the optimiser are two HBM passes and the all
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
 
 import torch
@@ -113,9 +114,13 @@ class CTClipTrainStep:
             # (its 294912 -> 512 projection is the FIRST thing the backward computes, the text tower runs next); their
             # all-reduce (1.04 of the 1.13 GB) starts the moment the kernels that wrote them are enqueued.
             model.grad_ready = self._on_grads_ready
+            # the 294912 -> 512 projection's gradient (604 of the 1130 MB) is rank-B_glob: its bf16 factors are all-gathered
+            # (4.7 MB per rank) and multiplied locally instead of all-reducing the product (CTCLIP_FACTOR_GATHER=0: all-reduce)
+            model.factor_gather = os.environ.get("CTCLIP_FACTOR_GATHER", "0") != "0"
 
-    def _on_grads_ready(self, params):
-        """called from inside backward (direct-gradient mode): these parameters' .grad in the arena is final"""
+    def _on_grads_ready(self, params, reduced=False):
+        """called from inside backward (direct-gradient mode): these parameters' .grad in the arena is final;
+        reduced=True: it already is the sum over ranks (factor gather), so the span is only excluded from the all-reduce"""
         spans = sorted(self.arena.span[id(p)] for p in params if id(p) in self.arena.span)
         merged = []
         for off, n in spans:
@@ -124,6 +129,9 @@ class CTClipTrainStep:
             else:
                 merged.append([off, n])
         for off, n in merged:
+            if reduced:
+                self._reduced.append((off, off + n))
+                continue
             for o in range(off, off + n, self.bucket):
                 e = min(off + n, o + self.bucket)
                 self._pending.append(dist.all_reduce(self.arena.grad[o:e], async_op=True))

@@ -95,3 +95,32 @@ def test_zero_shot_prompts_and_aurocs():
     real = torch.tensor([[1, 0], [1, 1], [0, 0], [0, 1]]).numpy()
     a = inf.aurocs(pred, real, ["a", "b"])
     assert a["a_auc"] == 1.0 and abs(a["b_auc"] - 0.75) < 1e-9
+
+
+# ---------------------------------------------------------------- factor gather of the rank-B to_visual_latent gradient
+def _factor_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7 + rank)
+    b, n, k = 3, 8, 40
+    dy, x = torch.randn(b, n, generator=g), torch.randn(b, k, generator=g)
+    # route 1 (reference DDP semantics, summed): all-reduce of the N x K product
+    prod = dy.t() @ x
+    dist.all_reduce(prod)
+    # route 2 (ct_clip.LinearFunction.backward, factor_gather): all-gather both factors, multiply locally
+    dy_all, x_all = torch.empty(world * b, n), torch.empty(world * b, k)
+    dist.all_gather_into_tensor(dy_all, dy)
+    dist.all_gather_into_tensor(x_all, x)
+    ret[rank] = (prod, dy_all.t() @ x_all)
+    dist.destroy_process_group()
+
+
+def test_factor_gather_equals_allreduce_of_product():
+    """dW = sum_r dL_r^T E_r = [dL_0; dL_1]^T [E_0; E_1]: gathering 2*B_loc*(N+K) numbers replaces reducing N*K"""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_factor_worker, args=(world, 29631, ret), nprocs=world, join=True)
+    for r in range(world):
+        prod, fact = ret[r]
+        assert torch.allclose(prod, fact, atol=1e-5)
+    assert torch.equal(ret[0][1], ret[1][1])        # every rank holds the identical global-batch gradient

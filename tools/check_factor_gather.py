@@ -1,0 +1,54 @@
+"""torchrun --nproc-per-node 2 tools/check_factor_gather.py
+Data-parallel gradient of `to_visual_latent`: the factor gather (all-gather dL and E, multiply locally; trainer default)
+against the plain all-reduce of the 512 x 294912 product (CTCLIP_FACTOR_GATHER=0 path) on identical models and inputs.
+Prints the relative difference per rank; exits non-zero above 1e-3 (bf16 operands, fp32 accumulation in another order)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.distributed as dist
+from transformers import BatchEncoding
+
+
+def main():
+    import bench
+    from ctpa_clip_b200.trainer import CTClipTrainStep
+    from oracle import ctclip_oracle as O   # configs only
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    cfg = O.CONFIGS[os.environ.get("CHECK_CONFIG", "production")]
+    b = 2
+    video, ids, mask = bench.synth_batch(cfg, b, seed=100 + rank)
+    text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})
+    video = video.to(dev)
+    grads, losses = [], []
+    for fg in (True, False):
+        model = bench.build_model(cfg, dev, seed=0)
+        tr = CTClipTrainStep(model)
+        model.factor_gather = fg   # explicit: independent of the CTCLIP_FACTOR_GATHER default
+        loss = tr.forward_backward(text, video)
+        tr.reduce_gradients()
+        torch.cuda.synchronize()
+        w = model.to_visual_latent.weight
+        off, _ = tr.arena.span[id(w)]
+        grads.append((tr.arena.grad[off: off + w.numel()].clone(), tr.arena.grad.clone()))
+        losses.append(float(loss))
+        del tr, model
+        torch.cuda.empty_cache()
+    (gw_f, all_f), (gw_r, all_r) = grads
+    rel_w = ((gw_f - gw_r).norm() / gw_r.norm()).item()
+    rel_all = ((all_f - all_r).norm() / all_r.norm()).item()
+    print(f"rank {rank}: loss {losses[0]:.6f} / {losses[1]:.6f}; to_visual_latent grad |factor - allreduce| / |allreduce| = {rel_w:.3e} "
+          f"(norm {gw_r.norm().item():.4e}); whole arena {rel_all:.3e}", flush=True)
+    ok = rel_w < 1e-3 and rel_all < 1e-3 and gw_r.norm().item() > 0
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
