@@ -116,7 +116,7 @@ class CTClipTrainStep:
             model.grad_ready = self._on_grads_ready
             # the 294912 -> 512 projection's gradient (604 of the 1130 MB) is rank-B_glob: its bf16 factors are all-gathered
             # (4.7 MB per rank) and multiplied locally instead of all-reducing the product (CTCLIP_FACTOR_GATHER=0: all-reduce)
-            model.factor_gather = os.environ.get("CTCLIP_FACTOR_GATHER", "0") != "0"
+            model.factor_gather = os.environ.get("CTCLIP_FACTOR_GATHER", "1") != "0"
 
     def _on_grads_ready(self, params, reduced=False):
         """called from inside backward (direct-gradient mode): these parameters' .grad in the arena is final;

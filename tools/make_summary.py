@@ -31,6 +31,12 @@ try:
     L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log`, weak scaling, global batch 16, latents exchanged by the fused peer-memory loss kernel (NCCL arm: `r01_bench_2gpu_v8_nccl.log`), gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
 except FileNotFoundError:
     pass
+for n in (4, 8):
+    try:
+        bn = json.loads([l for l in open(f"profiles/r01_bench_{n}gpu_{tag}.log") if l.startswith("{")][-1])
+        L.append(f"* {n}×B200 (`r01_bench_{n}gpu_{tag}.log`, weak scaling, global batch {8 * n}): {bn['ms_per_step']:.1f} ms/step = {bn['value']:.0f} volumes/s ({100 * bn['value'] / (n * bench['value']):.0f} % of {n}× the 1-GPU step), end to end {bn['e2e']['value']:.0f} volumes/s")
+    except FileNotFoundError:
+        pass
 for rtag in (tag, "v7"):   # the reference arm does not depend on our kernels: the last measured run is reused
     try:
         br = json.loads([l for l in open(f"profiles/r01_bench_reference_arm_{rtag}.log") if l.startswith("{")][-1])
