@@ -138,7 +138,8 @@ class CTClipTrainStep:
             self._reduced.append((off, off + n))
 
     def forward_backward(self, text, video):
-        self.model.train()
+        if not self.model.training:       # nn.Module.train() walks ~600 modules: only when the mode actually changes
+            self.model.train()
         loss = self.model(text, video, return_loss=True)
         loss.backward()
         return loss

@@ -3,7 +3,9 @@
 import json, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "v4"
 d = json.load(open(f"profiles/r01_step_breakdown_{tag}.json"))
-c = json.load(open(f"profiles/r01_components_{tag}.json"))
+import os
+ctag = next(t for t in (tag, "v8", "v7") if os.path.exists(f"profiles/r01_components_{t}.json"))   # component bench: last run
+c = json.load(open(f"profiles/r01_components_{ctag}.json"))
 bench = json.loads([l for l in open(f"profiles/r01_bench_{tag}.log") if l.startswith("{")][-1])
 rows = d["ops"]
 tot = sum(v["ms"] for k, v in rows)
@@ -23,19 +25,19 @@ L.append("# Round 1 — measurement summary (1×B200 unless noted; B = 8 volumes
 L.append("All numbers are CUDA-event timings from `bench.py` / `tools/bench_components.py` runs on the GPU box (no profiler attached);")
 L.append("ncu evidence: `r01_ncu_launches_v8.txt` + `r01_step_traffic.json` (launch list and DRAM bytes of one training step), `r01_ncu_kernels_v3.txt` / `r01_ncu_kernels_v7.txt` (`--set full` extracts).\n")
 L.append(f"## Headline (`r01_bench_{tag}.log`)\n")
-L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (session start: 79.2 ms / 101 volumes/s with the text tower still on torch; previous snapshots v4: 58.8 ms, v7: 52.1 ms)")
-L.append(f"* end to end (pinned host volumes → H2D on a copy stream → step → `loss.item()` every step): **{bench['e2e']['value']:.1f} volumes/s** ({bench['e2e']['ms_per_step']:.1f} ms/step, {bench['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB H2D per step)")
+L.append(f"* device-resident step: **{bench['ms_per_step']:.1f} ms = {bench['value']:.1f} volumes/s** (session start: 79.2 ms / 101 volumes/s with the text tower still on torch; previous snapshots v4: 58.8 ms, v7: 52.1 ms, v8: 51.5 ms)")
+L.append(f"* end to end (pinned host volumes → H2D on a copy stream → step → loss copied back to pinned host memory every step, consumed one step later): **{bench['e2e']['value']:.1f} volumes/s** ({bench['e2e']['ms_per_step']:.1f} ms/step, {bench['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB H2D per step)")
 L.append(f"* all `gemm_bf16_kernel` launches of the step: {bench['roofline']['achieved']:.0f} TFLOP/s = {100 * bench['roofline']['frac']:.0f} % of the measured sustained cuBLAS bf16 rate, {100 * bench['roofline']['share_of_step']:.0f} % of the step")
 try:
-    b2 = json.loads([l for l in open(f"profiles/r01_bench_2gpu_{tag}.log") if l.startswith("{")][-1])
-    L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log`, weak scaling, global batch 16, latents exchanged by the fused peer-memory loss kernel (NCCL arm: `r01_bench_2gpu_v8_nccl.log`), gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
-except FileNotFoundError:
+    b2 = json.loads([l for l in open(next(f for f in (f"profiles/r01_bench_2gpu_{tag}.log", "profiles/r01_bench_2gpu_v8.log") if os.path.exists(f))) if l.startswith("{")][-1])
+    L.append(f"* 2×B200 (`r01_bench_2gpu_{tag}.log` if present, else `r01_bench_2gpu_v8.log`; weak scaling, global batch 16, latents exchanged by the fused peer-memory loss kernel (NCCL arm: `r01_bench_2gpu_v8_nccl.log`), gradients all-reduced over NVLink, the text-tower / latent-projection part overlapped with the image tower's backward): {b2['ms_per_step']:.1f} ms/step = {b2['value']:.0f} volumes/s ({100 * b2['value'] / (2 * bench['value']):.0f} % of 2× the 1-GPU step)")
+except (FileNotFoundError, StopIteration):
     pass
 for n in (4, 8):
     try:
-        bn = json.loads([l for l in open(f"profiles/r01_bench_{n}gpu_{tag}.log") if l.startswith("{")][-1])
-        L.append(f"* {n}×B200 (`r01_bench_{n}gpu_{tag}.log`, weak scaling, global batch {8 * n}): {bn['ms_per_step']:.1f} ms/step = {bn['value']:.0f} volumes/s ({100 * bn['value'] / (n * bench['value']):.0f} % of {n}× the 1-GPU step), end to end {bn['e2e']['value']:.0f} volumes/s")
-    except FileNotFoundError:
+        bn = json.loads([l for l in open(next(f for f in (f"profiles/r01_bench_{n}gpu_{tag}.log", f"profiles/r01_bench_{n}gpu_v8.log") if os.path.exists(f))) if l.startswith("{")][-1])
+        L.append(f"* {n}×B200 (`r01_bench_{n}gpu_{tag}.log` if present, else `..._v8.log`; weak scaling, global batch {8 * n}): {bn['ms_per_step']:.1f} ms/step = {bn['value']:.0f} volumes/s ({100 * bn['value'] / (n * bench['value']):.0f} % of {n}× the 1-GPU step), end to end {bn['e2e']['value']:.0f} volumes/s")
+    except (FileNotFoundError, StopIteration):
         pass
 for rtag in (tag, "v7"):   # the reference arm does not depend on our kernels: the last measured run is reused
     try:
@@ -55,7 +57,7 @@ L.append("| op (shape MxNxK for GEMMs) | ms | launches | TFLOP/s |\n|---|---|---
 for k, v in rows[:24]:
     tf = f"{v['flops'] / v['ms'] / 1e9:.0f}" if v["flops"] else ""
     L.append(f"| {k} | {v['ms']:.2f} | {v['n']} | {tf} |")
-L.append(f"\n## Kernel rooflines on production shapes (`r01_components_{tag}.json`)\n")
+L.append(f"\n## Kernel rooflines on production shapes (`r01_components_{ctag}.json`)\n")
 L.append("| kernel / shape | time | achieved | of measured peak |\n|---|---|---|---|")
 for k, v in c.items():
     if "TFLOPs" in v:
