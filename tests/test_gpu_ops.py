@@ -529,3 +529,18 @@ def test_zero_shot_scores_kernel(ops, V, P, d):
     ref_logits = (I.double() @ T.double().t() * tau.double().exp()).view(V, P, 2)
     assert torch.allclose(logits.double(), ref_logits, atol=1e-4)
     assert torch.allclose(prob.double(), ref_logits.softmax(dim=-1)[..., 0], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ factor-gather weight gradient
+@pytest.mark.parametrize("K", [8, 16, 32, 64])
+def test_factor_gather_wgrad_gemm(ops, K):
+    """dW[512, 294912] += dL_all^T E_all at the global batches of 1 / 2 / 4 / 8 ranks (ct_clip.LinearFunction.backward,
+    factor_gather): MN-major bf16 operands, in-place fp32 residual epilogue, against torch fp32 (operands are exact in bf16,
+    accumulation is fp32 -> 1e-5 of the result's scale)."""
+    g = torch.Generator(device="cuda").manual_seed(K)
+    dy = torch.randn(K, 512, device="cuda", generator=g).bfloat16()
+    x = torch.randn(K, 294912, device="cuda", generator=g).bfloat16()
+    w = torch.randn(512, 294912, device="cuda", generator=g)
+    ref = w + dy.float().t() @ x.float()
+    ops.gemm(dy, x, a_t=True, b_t=True, out=w, resid=w)
+    close(w, ref, 1e-5)
