@@ -383,6 +383,7 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
   const long long oplane = (long long)p.tH * p.tW;
   float* out_t = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
                  (ow_base + lane - p.ww0 + p.pw0);
+  bool synced_prev = true;   // the barrier after the initial row stores
   for (int t = 0; t < n_oh; ++t) {
     const int oh = oh_base + t;
     const float4 ht = s_htap[t];
@@ -440,10 +441,19 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
       }
     }
     if (na >= 0 || nb >= 0) {
-      __syncthreads();  // every reader of the slots being replaced is done
+      // Slot reads happen only in wrow() at the top of an iteration and only for rows h0 / h1. A new row whose slot is
+      // neither of those two was last read in an EARLIER iteration; if that iteration ended with the barrier below, every
+      // warp is past those reads and the store needs no barrier of its own (the usual 512 -> 480 step: rows r, r+1 in use,
+      // row r+2 replaces r-1). Otherwise (two new rows, one of them landing on h0's slot; or no barrier last time) wait.
+      const int s0 = h0 % 3, s1 = h1 % 3;
+      const bool clash = (na >= 0 && (na % 3 == s0 || na % 3 == s1)) || (nb >= 0 && (nb % 3 == s0 || nb % 3 == s1));
+      if (clash || !synced_prev) __syncthreads();  // every reader of the slots being replaced is done
       if (na >= 0) { row_store(na, pfa); hold(na); }
       if (nb >= 0) { row_store(nb, pfb); hold(nb); }
       __syncthreads();
+      synced_prev = true;
+    } else {
+      synced_prev = false;
     }
   }
 }
