@@ -8,8 +8,11 @@
 Workload (N=1): BASELINE.json configs[1] — production CT-CLIP (CTViT dim 512, patch 20x20x10, 4+4 layers, 8x32 heads,
 codebook 8192, BERT-base text tower, 294912->512 latent projection), 8 synthetic 480x480x240 volumes + 8 reports of 512
 token ids per rank; a step = forward(global-batch InfoNCE) + backward + gradient all-reduce + clip(0.5) + Adam.
-N>1 keeps 8 volumes per rank (weak scaling; N=8 is configs[2], global batch 64, latents all-gathered over NVLink).
-Prints ONE JSON line on rank 0.
+N>1 keeps 8 volumes per rank (weak scaling; N=8 is configs[2], global batch 64; latents exchanged over NVLink by the loss
+kernel itself, csrc/symm.cu). Prints ONE JSON line on rank 0: value = device-resident steps (CUDA events, max over ranks);
+e2e = the same steps fed from pinned host memory (volumes, token ids, masks copied every step on a copy stream, every step's
+loss copied back to pinned memory and consumed by the host one step later); gpu_launches = kernels of libctclip_sm100.so
+launched by this rank inside the timed region (gpu_launches_per_step = per step); roofline / cpu_baseline as DESIGN.md §8.
 """
 from __future__ import annotations
 
@@ -211,7 +214,8 @@ def run_ours(args):
         sampler.start()
     n0 = _lib.launch_count()
     ms_total = timed(step_resident, args.steps)
-    launches = (_lib.launch_count() - n0) // max(1, args.steps)
+    launches_total = _lib.launch_count() - n0                      # kernels of libctclip_sm100.so inside the timed region (this rank)
+    launches = launches_total // max(1, args.steps)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
@@ -313,7 +317,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(video_h.numel() * 4 + ids.numel() * 8 + mask.numel() * 8), "d2h_bytes_per_step": 4,
                 "note": "pinned host volumes + token ids + masks, double-buffered copy stream; every step's loss is copied to pinned host memory and read by the host one step later (last one after the closing sync)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "achieved_tflops_step": world * B * TRAIN_GF_PER_VOLUME / (ms_step * 1e-3) / 1e3 / world,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf_peak if tf_peak else None, "traffic": traffic, "traffic_note": traffic_note,
