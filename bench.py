@@ -91,33 +91,6 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_model(cfg, device, seed=0):
-    import torch
-    from ctpa_clip_b200.ct_clip import CTCLIP, CTViT
-    from transformers import BertConfig, BertModel
-    torch.manual_seed(seed)
-    vit = CTViT(dim=cfg["dim"], codebook_size=cfg["codebook_size"], image_size=cfg["image_size"],
-                patch_size=cfg["patch_size"], temporal_patch_size=cfg["temporal_patch_size"],
-                spatial_depth=cfg["spatial_depth"], temporal_depth=cfg["temporal_depth"], dim_head=cfg["dim_head"],
-                heads=cfg["heads"])
-    txt = BertModel(BertConfig(**cfg["text"]))   # random-init BERT-base: CXR-BERT weights are not available offline
-    model = CTCLIP(image_encoder=vit, text_encoder=txt, dim_text=cfg["dim_text"], dim_image=cfg["dim_image"],
-                   dim_latent=cfg["dim_latent"])
-    return model.to(device)
-
-
-def synth_batch(cfg, batch, seed):
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    video = torch.rand(batch, 1, cfg["frames"], cfg["image_size"], cfg["image_size"], generator=g) * 2 - 1
-    L = cfg["seq_len"]
-    ids = torch.randint(1, cfg["text"]["vocab_size"], (batch, L), generator=g)
-    mask = torch.ones(batch, L, dtype=torch.long)
-    ids[:, L // 2:] = 0
-    mask[:, L // 2:] = 0
-    return video, ids, mask
-
-
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_step(cfg, batch, threads, seed=0):
     """one forward+backward of the reference algorithm (oracle port, fp32) on the host cores; returns seconds"""
@@ -167,7 +140,7 @@ def run_ours(args):
     from transformers import BatchEncoding
     from ctpa_clip_b200 import _lib, ops
     from ctpa_clip_b200.trainer import CTClipTrainStep
-    from oracle import ctclip_oracle as O  # configs only (shapes); nothing of the oracle runs on this arm's path
+    from ctpa_clip_b200 import configs as O   # shapes + seeded synthetic inputs; the product arm imports nothing from oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,9 +151,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = O.CONFIGS[args.config]
     B = args.batch
-    model = build_model(cfg, dev, seed=0)
+    model = O.build_model(cfg, dev, seed=0)
     trainer = CTClipTrainStep(model)
-    video_h, ids, mask = synth_batch(cfg, B, seed=100 + rank)
+    video_h, ids, mask = O.synth_batch(cfg, B, seed=100 + rank)
     host = [video_h.pin_memory(), video_h.clone().pin_memory()]
     video_d = video_h.to(dev)
     text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})

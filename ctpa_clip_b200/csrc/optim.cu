@@ -28,11 +28,20 @@ sumsq_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ o
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             uint2* __restrict__ shadow, long long nvec, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-            const float* __restrict__ norm_sq, float max_norm, int zero_grad) {
+            const float* __restrict__ norm_sq, float max_norm, int zero_grad, int* __restrict__ skipped) {
   float clip = 1.f;
-  if (norm_sq != nullptr && max_norm > 0.f) {
-    const float c = max_norm / (sqrtf(*norm_sq) + 1e-6f);  // torch.nn.utils.clip_grad_norm_
-    clip = c < 1.f ? c : 1.f;
+  if (norm_sq != nullptr) {
+    const float nsq = *norm_sq;
+    // NaN / Inf gradients (a peer that timed out in the latent exchange, an overflow): never a training update. Nothing is
+    // written — parameters, moments, bf16 mirror and the gradients themselves stay for the host to inspect.
+    if (!(fabsf(nsq) <= 3.0e38f)) {
+      if (skipped != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(skipped, 1);
+      return;
+    }
+    if (max_norm > 0.f) {
+      const float c = max_norm / (sqrtf(nsq) + 1e-6f);  // torch.nn.utils.clip_grad_norm_
+      clip = c < 1.f ? c : 1.f;
+    }
   }
   const float step = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
@@ -69,7 +78,7 @@ extern "C" int ctclip_sumsq(const float* g, long long n, float* out, void* strea
 // one Adam step over flat arenas; `step` is the 1-based step count; norm_sq (device scalar, may be NULL) enables clipping
 extern "C" int ctclip_adam_step(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, float lr, float beta1,
                                 float beta2, float eps, int step, const float* norm_sq, float max_norm, int zero_grad,
-                                void* stream) {
+                                int* skipped, void* stream) {
   if (n <= 0) return CTCLIP_OK;
   if (n % 4) return ctclip::fail(CTCLIP_E_ALIGN, "adam_step: n must be a multiple of 4");
   int rc = ctclip::require_sm100();
@@ -81,6 +90,6 @@ extern "C" int ctclip_adam_step(float* p, float* g, float* m, float* v, void* bf
   if (blocks > cap) blocks = cap;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v,
                                                                  (uint2*)bf16_shadow, n / 4, lr, beta1, beta2, eps, bc1,
-                                                                 bc2_sqrt, norm_sq, max_norm, zero_grad);
+                                                                 bc2_sqrt, norm_sq, max_norm, zero_grad, skipped);
   return ctclip::check_launch("adam_step");
 }

@@ -17,12 +17,27 @@
 // from plain cudaMalloc to be exportable through CUDA IPC, so ctclip_symm_alloc / _free wrap it explicitly.
 #include "ptx.cuh"
 #include "ctclip_internal.h"
+#include <cstdlib>
 
 namespace {
 
 constexpr int kMaxWorld = 32;
 constexpr int kFlagStride = 8;  // one flag per 32 bytes
-constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;
+// How long a CTA waits for a peer's flag before it gives up: default 600 s (torch.distributed's NCCL default; the
+// reference's accelerate process group uses 36000 s, CTCLIPTrainer.py:212), CTCLIP_PEER_TIMEOUT_S or
+// ctclip_symm_set_timeout_ms override it. Giving up poisons the logits with NaN AND raises the caller's status word, so
+// the host can tell a dead peer from a numerical problem; the optimiser kernel skips any update whose gradient norm is
+// not finite (optim.cu), so a timeout never becomes a training update.
+unsigned long long g_timeout_ns = 0;   // 0 = not initialised
+unsigned long long spin_timeout_ns() {
+  if (g_timeout_ns == 0) {
+    const char* e = getenv("CTCLIP_PEER_TIMEOUT_S");
+    double sec = e != nullptr ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    g_timeout_ns = (unsigned long long)(sec * 1e9);
+  }
+  return g_timeout_ns;
+}
 
 struct PeerTable {
   float* buf[kMaxWorld];
@@ -57,14 +72,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 __host__ __device__ inline size_t header_floats() { return (size_t)2 * kMaxWorld * kFlagStride; }
 __host__ __device__ inline size_t parity_floats(int world, int b, int d) { return (size_t)2 * world * b * d; }
 
-// grid (world, world), 256 threads.
+// grid (world, world), 256 threads. Emulation (rank < 0, grid (world, world, world), cooperative launch so that all CTAs
+// are co-resident): blockIdx.z plays the rank — all `world` symmetric buffers live on ONE device, t_hat / i_hat / L hold
+// every rank's slice back to back — which exercises the push / flag / wait protocol on a single GPU in a single launch.
 __global__ void __launch_bounds__(256)
 latent_exchange_logits_kernel(PeerTable peers, const float* __restrict__ t_hat, const float* __restrict__ i_hat,
                               const float* __restrict__ tau, int b, int d, int rank, int world, unsigned step,
-                              float* __restrict__ L) {
+                              float* __restrict__ L, unsigned long long timeout_ns, int* __restrict__ status) {
   const int p = blockIdx.x, q = blockIdx.y;
   const int par = step & 1u;
   const int B = world * b;
+  if (rank < 0) {
+    rank = blockIdx.z;
+    t_hat += (size_t)rank * b * d;
+    i_hat += (size_t)rank * b * d;
+    L += (size_t)rank * B * B;
+  }
   const size_t par_off = header_floats() + (size_t)par * parity_floats(world, b, d);
   if (q == 0) {
     // ---- push this rank's rows into rank p's buffer (p == rank: plain local stores), then publish
@@ -87,10 +110,11 @@ latent_exchange_logits_kernel(PeerTable peers, const float* __restrict__ t_hat, 
     const unsigned long long t0 = globaltimer_ns();
     int bad = 0;
     while (ld_acquire_sys(flags + p * kFlagStride) != step || ld_acquire_sys(flags + q * kFlagStride) != step) {
-      if (globaltimer_ns() - t0 > kSpinTimeoutNs) { bad = 1; break; }
+      if (globaltimer_ns() - t0 > timeout_ns) { bad = 1; break; }
       __nanosleep(64);
     }
     timed_out = bad;
+    if (bad && status != nullptr) atomicOr(status, 1);
   }
   __syncthreads();
   const float* T = peers.buf[rank] + par_off;
@@ -106,7 +130,7 @@ latent_exchange_logits_kernel(PeerTable peers, const float* __restrict__ t_hat, 
       s += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
     }
     s = warp_sum(s);
-    // a peer that never arrived poisons the loss instead of hanging the box
+    // a peer that never arrived poisons the loss (and raised *status above) instead of hanging the box
     if (lane == 0) L[(size_t)i * B + j] = timed_out ? __int_as_float(0x7fc00000) : et * s;
   }
 }
@@ -166,32 +190,92 @@ extern "C" int ctclip_symm_unimport(void* ptr) {
   return CTCLIP_OK;
 }
 
+extern "C" int ctclip_symm_set_timeout_ms(unsigned long long ms) {
+  if (ms == 0) return ctclip::fail(CTCLIP_E_SHAPE, "symm_set_timeout_ms: the timeout must be positive");
+  g_timeout_ns = ms * 1000000ull;
+  return CTCLIP_OK;
+}
+
+namespace {
+int check_exchange_args(const char* who, const float* t_hat, const float* i_hat, int b_local, int d, int world,
+                        void* const* host_peer_bufs, unsigned step, PeerTable* peers) {
+  if (b_local <= 0 || d <= 0 || d % 4) return ctclip::fail(CTCLIP_E_SHAPE, "%s: bad shape b=%d d=%d", who, b_local, d);
+  if (world <= 0 || world > kMaxWorld) return ctclip::fail(CTCLIP_E_SHAPE, "%s: bad world %d (max %d)", who, world, kMaxWorld);
+  if (step == 0) return ctclip::fail(CTCLIP_E_SHAPE, "%s: step counter starts at 1 (flags are zero-initialised)", who);
+  if ((long long)world * b_local > 8192) return ctclip::fail(CTCLIP_E_SHAPE, "%s: global batch too large", who);
+  if (host_peer_bufs == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "%s: no peer table", who);
+  for (int r = 0; r < kMaxWorld; ++r) peers->buf[r] = r < world ? static_cast<float*>(host_peer_bufs[r]) : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (peers->buf[r] == nullptr || (reinterpret_cast<uintptr_t>(peers->buf[r]) & 15))
+      return ctclip::fail(CTCLIP_E_ALIGN, "%s: peer buffer %d missing or not 16-byte aligned", who, r);
+  if ((reinterpret_cast<uintptr_t>(t_hat) | reinterpret_cast<uintptr_t>(i_hat)) & 15)
+    return ctclip::fail(CTCLIP_E_ALIGN, "%s: latents must be 16-byte aligned", who);
+  return ctclip::require_sm100();
+}
+}  // namespace
+
 extern "C" int ctclip_clip_loss_allgather(const float* t_hat, const float* i_hat, const float* tau, int b_local, int d,
                                           int rank, int world, void* const* host_peer_bufs, unsigned step, float* work,
-                                          float* loss, float* dT, float* dI, float* dtau, void* stream) {
-  if (b_local <= 0 || d <= 0 || d % 4) return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: bad shape b=%d d=%d", b_local, d);
-  if (world <= 0 || world > kMaxWorld || rank < 0 || rank >= world)
-    return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: bad rank %d / world %d (max %d)", rank, world, kMaxWorld);
-  if (step == 0) return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: step counter starts at 1 (flags are zero-initialised)");
-  if ((long long)world * b_local > 8192) return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: global batch too large");
-  if (host_peer_bufs == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: no peer table");
-  int rc = ctclip::require_sm100();
-  if (rc) return rc;
+                                          float* loss, float* dT, float* dI, float* dtau, int* status, void* stream) {
+  if (rank < 0 || rank >= world) return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather: bad rank %d / world %d", rank, world);
   PeerTable peers;
-  for (int r = 0; r < kMaxWorld; ++r) peers.buf[r] = r < world ? static_cast<float*>(host_peer_bufs[r]) : nullptr;
-  for (int r = 0; r < world; ++r)
-    if (peers.buf[r] == nullptr || (reinterpret_cast<uintptr_t>(peers.buf[r]) & 15))
-      return ctclip::fail(CTCLIP_E_ALIGN, "clip_loss_allgather: peer buffer %d missing or not 16-byte aligned", r);
-  if ((reinterpret_cast<uintptr_t>(t_hat) | reinterpret_cast<uintptr_t>(i_hat)) & 15)
-    return ctclip::fail(CTCLIP_E_ALIGN, "clip_loss_allgather: latents must be 16-byte aligned");
+  int rc = check_exchange_args("clip_loss_allgather", t_hat, i_hat, b_local, d, world, host_peer_bufs, step, &peers);
+  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int B = world * b_local;
   float* L = work;
-  latent_exchange_logits_kernel<<<dim3(world, world), 256, 0, s>>>(peers, t_hat, i_hat, tau, b_local, d, rank, world, step, L);
+  latent_exchange_logits_kernel<<<dim3(world, world), 256, 0, s>>>(peers, t_hat, i_hat, tau, b_local, d, rank, world, step, L,
+                                                                  spin_timeout_ns(), status);
   rc = ctclip::check_launch("latent_exchange_logits");
   if (rc) return rc;
   const size_t par_off = header_floats() + (size_t)(step & 1u) * parity_floats(world, b_local, d);
   const float* T = peers.buf[rank] + par_off;
   const float* I = T + (size_t)B * d;
   return ctclip::clip_lse_grad_launch(T, I, tau, B, d, rank * b_local, b_local, work, loss, dT, dI, dtau, s);
+}
+
+// All `world` ranks of the exchange on ONE device in ONE cooperative launch (bring-up / single-GPU test of the push / flag /
+// wait protocol; B200_PROFILING.md: mutually waiting kernels must never be separate launches on one GPU). bufs[r] are
+// `world` symmetric buffers of this device; t_hat_all / i_hat_all fp32 [world*b_local][d]; per-rank outputs back to back:
+// work_all [world][B*B + 2*B + d], loss_all [world], dT_all / dI_all [world*b_local][d], dtau_all [world].
+extern "C" int ctclip_clip_loss_allgather_emulated(const float* t_hat_all, const float* i_hat_all, const float* tau,
+                                                   int b_local, int d, int world, void* const* host_bufs, unsigned step,
+                                                   float* work_all, float* loss_all, float* dT_all, float* dI_all,
+                                                   float* dtau_all, int* status, void* stream) {
+  PeerTable peers;
+  int rc = check_exchange_args("clip_loss_allgather_emulated", t_hat_all, i_hat_all, b_local, d, world, host_bufs, step, &peers);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = world * b_local;
+  const size_t work_stride = (size_t)B * B + 2 * (size_t)B + d;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latent_exchange_logits_kernel, 256, 0);
+  if ((long long)world * world * world > (long long)per_sm * ctclip::sm_count())
+    return ctclip::fail(CTCLIP_E_SHAPE, "clip_loss_allgather_emulated: %d^3 CTAs cannot be co-resident", world);
+  // the per-rank logits land at work_all + rank * B * B inside the kernel; the per-rank work areas are work_stride apart,
+  // so the logits are computed into a packed scratch at the head of work_all[0..] and copied out below
+  int rank = -1;
+  unsigned long long timeout = spin_timeout_ns();
+  float* Lall = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&Lall), (size_t)world * B * B * sizeof(float), s);
+  if (e != cudaSuccess) return ctclip::fail(CTCLIP_E_CUDA, "clip_loss_allgather_emulated: scratch: %s", cudaGetErrorString(e));
+  void* args[] = {&peers, &t_hat_all, &i_hat_all, &tau, &b_local, &d, &rank, &world, &step, &Lall, &timeout, &status};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(latent_exchange_logits_kernel), dim3(world, world, world), dim3(256),
+                                  args, 0, s);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(Lall, s);
+    return ctclip::fail(CTCLIP_E_CUDA, "clip_loss_allgather_emulated: cooperative launch: %s", cudaGetErrorString(e));
+  }
+  ctclip::count_launch();
+  const size_t par_off = header_floats() + (size_t)(step & 1u) * parity_floats(world, b_local, d);
+  for (int r = 0; r < world && rc == 0; ++r) {
+    float* work = work_all + r * work_stride;
+    cudaMemcpyAsync(work, Lall + (size_t)r * B * B, (size_t)B * B * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    const float* T = peers.buf[r] + par_off;
+    const float* I = T + (size_t)B * d;
+    rc = ctclip::clip_lse_grad_launch(T, I, tau, B, d, r * b_local, b_local, work, loss_all + r,
+                                      dT_all + (size_t)r * b_local * d, dI_all + (size_t)r * b_local * d, dtau_all + r, s);
+  }
+  cudaFreeAsync(Lall, s);
+  return rc;
 }

@@ -1,6 +1,9 @@
-"""Parameter containers mirroring CTPA_CLIP/ct_clip/attention.py (same class names, constructor arguments and
-state_dict keys). They hold weights only: the arithmetic of PEG / Attention / FeedForward / LayerNorm on the CT-CLIP
-path runs in libctclip_sm100.so through ctpa_clip_b200.engine; calling a block on its own dispatches there too.
+"""Modules mirroring CTPA_CLIP/ct_clip/attention.py (same class names, constructor arguments, forward signatures and
+state_dict keys). On the CT-CLIP path (CTViT / CTCLIP forward + backward) they are parameter containers: the engine
+(ctpa_clip_b200.engine) evaluates whole layers on libctclip_sm100.so without materialising the reference's rearranges.
+Called on their own — `vit.enc_spatial_transformer(tokens, attn_bias=..., video_shape=...)` as
+ctpa_report/vqa_meditron.py:107 does, `PEG(x, shape)`, `Attention(x, attn_bias=...)` — `forward` dispatches into the same
+kernels with the reference's semantics on the caller's memory layout (inference surface: no autograd through a lone block).
 """
 from __future__ import annotations
 
@@ -8,6 +11,7 @@ import torch
 from torch import nn
 
 from .. import ops
+from ..shadow import bf16_of
 
 
 def exists(val):
@@ -31,9 +35,29 @@ class LayerNorm(nn.Module):
         return engine.layernorm_module_forward(x, self.gamma, None)
 
 
+def _no_block_autograd(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("autograd through a lone block is not implemented: differentiate through CTViT / CTCLIP "
+                                  "(hand-written backward of the whole encoder), or call the block under torch.no_grad()")
+
+
+def _flat_f32(x):
+    return x.reshape(-1, x.shape[-1]).contiguous().float()
+
+
 class GEGLU(nn.Module):
-    def forward(self, x):  # only reachable through FeedForward, which the engine evaluates as a whole
-        raise RuntimeError("GEGLU is fused into the feed-forward kernels; call the FeedForward block")
+    """x, gate = chunk(2); gelu(gate) * x (reference attention.py:39-42) on `ctclip_geglu_fwd`"""
+
+    def forward(self, x):
+        _no_block_autograd(x)
+        shape, half = x.shape, x.shape[-1] // 2
+        hp = (half + 7) // 8 * 8                      # the kernel wants [x | gate] halves at a 16-byte pitch
+        flat = x.reshape(-1, 2 * half)
+        h = torch.zeros((flat.shape[0], 2 * hp), device=x.device, dtype=torch.bfloat16)
+        h[:, :half] = flat[:, :half]
+        h[:, hp: hp + half] = flat[:, half:]
+        u = ops.geglu_fwd(h)[:, :half]
+        return u.to(x.dtype).reshape(*shape[:-1], half)
 
 
 def FeedForward(dim, mult=4, dropout=0.0):
@@ -60,6 +84,24 @@ class PEG(nn.Module):
         self.causal = causal
         self.dsconv = nn.Conv3d(dim, dim, 3, groups=dim)
 
+    def forward(self, x, shape=None):
+        """x: (b, t, h, w, d), or (b', n, d) with shape=(b, t, h, w): the flat buffer is REINTERPRETED as (b, t, h, w, d)
+        exactly like the reference's `x.reshape(*shape, -1)` (attention.py:69-70), zero-padded (1,1,1,1,2,0) and convolved
+        depth-wise over (t, h, w), causal on the first grid axis. Returns the convolution alone (the caller adds x).
+        `ctclip_peg_fwd` computes x + conv(x) + bias in one pass; the residual is subtracted again here (fp32, one rounding)."""
+        _no_block_autograd(x)
+        needs_shape = x.ndim == 3
+        if needs_shape and shape is None:
+            raise ValueError("PEG.forward: a (b, n, d) input needs shape=(b, t, h, w)")
+        grid = tuple(shape) if needs_shape else tuple(x.shape[:-1])
+        dim = x.shape[-1]
+        if len(grid) != 4 or x.numel() != grid[0] * grid[1] * grid[2] * grid[3] * dim:
+            raise ValueError(f"PEG.forward: input of shape {tuple(x.shape)} is not a (b, t, h, w, d) grid {grid}")
+        xf = _flat_f32(x)
+        w27 = self.dsconv.weight.detach().reshape(dim, 27).t().contiguous().float()
+        y = ops.peg_fwd(xf, w27, self.dsconv.bias.detach().float(), grid, False)
+        return (y - xf).to(x.dtype).reshape(x.shape)
+
 
 class Attention(nn.Module):
     """cosine-sim attention weights (reference attention.py:88-125)"""
@@ -85,6 +127,36 @@ class Attention(nn.Module):
         self.q_scale = nn.Parameter(torch.ones(dim_head))
         self.k_scale = nn.Parameter(torch.ones(dim_head))
         self.to_out = nn.Linear(inner_dim, dim, bias=False)
+
+    def forward(self, x, mask=None, context=None, attn_bias=None):
+        """x: (b', n, d) -> to_out(softmax(8 * l2norm(q) q_scale . l2norm(k) k_scale + attn_bias) v)   (attention.py:127-181),
+        K/V from the un-normalised x, Q from LayerNorm(x). attn_bias: (heads, n, n) relative-position bias of an (h, w) grid
+        with h*w = n (what ContinuousPositionBias.forward returns); it is folded back into its (2h-1)(2w-1) table — the form
+        the kernels gather from — and rejected if it is not translation-invariant."""
+        _no_block_autograd(x)
+        if mask is not None or context is not None:
+            raise NotImplementedError("attention masks / cross-attention context are not used by CTViT and not implemented")
+        b, n, dim = x.shape
+        tab = rowmax = None
+        grid = (b, 1, 1, n)
+        if attn_bias is not None:
+            hw = getattr(attn_bias, "_grid_hw", None)
+            if hw is None:
+                r = int(round(n ** 0.5))
+                if r * r != n:
+                    raise NotImplementedError("attn_bias of a non-square grid: pass the tensor returned by "
+                                              "ContinuousPositionBias.forward (it carries its (h, w))")
+                hw = (r, r)
+            tab, rowmax = table_from_full_bias(attn_bias.detach().float(), *hw)
+            grid = (b, 1, hw[0], hw[1])
+        xf = _flat_f32(x)
+        xn, xr, _ = ops.layernorm_fwd(xf, self.norm.gamma.detach().float(), None, want_bf16=True, want_raw_bf16=True)
+        q = ops.gemm(xn, bf16_of(self.to_q.weight))
+        kv = ops.gemm(xr, bf16_of(self.to_kv.weight))
+        o, _ = ops.attn_fwd(q, kv, grid, self.heads, False, self.q_scale.detach().float(), self.k_scale.detach().float(),
+                            tab, rowmax)
+        out = ops.gemm(o, bf16_of(self.to_out.weight), out_dtype=torch.float32)
+        return out.to(x.dtype).reshape(b, n, dim)
 
 
 def leaky_relu(p=0.1):
@@ -139,17 +211,35 @@ class ContinuousPositionBias(nn.Module):
         return self.table_fwd(h, w)[0]
 
     def forward(self, *dimensions, device=None):
-        """full (heads, h*w, h*w) bias, as the reference returns it (gathered from the table)"""
+        """full (heads, h*w, h*w) bias, as the reference returns it (gathered from the table); tagged with its grid so that
+        Attention / Transformer.forward can fold it back into the table without guessing (h, w)"""
         h, w = dimensions
         device = self.net[0][0].weight.device
         tab = self.table(h, w, device)
-        return tab[:, pair_index(h, w, device)]
+        out = tab[:, pair_index(h, w, device)]
+        out._grid_hw = (h, w)
+        return out
 
 
 def pair_index(h, w, device):
     pos = torch.stack(torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")).reshape(2, -1).t()
     rel = pos[:, None, :] - pos[None, :, :]
     return (rel[..., 0] + h - 1) * (2 * w - 1) + (rel[..., 1] + w - 1)
+
+
+def table_from_full_bias(bias, h, w):
+    """(heads, n, n) relative-position bias of an (h, w) grid -> (table [heads, (2h-1)(2w-1)], rowmax [heads, n]); raises if
+    the bias is not a function of the (dy, dx) offset alone (the kernels gather from the table)"""
+    heads, n, n2 = bias.shape
+    if n != h * w or n2 != n:
+        raise ValueError(f"attn_bias {tuple(bias.shape)} does not belong to a {h} x {w} grid")
+    idx = pair_index(h, w, bias.device)
+    table = torch.zeros((heads, (2 * h - 1) * (2 * w - 1)), device=bias.device, dtype=torch.float32)
+    table[:, idx.reshape(-1)] = bias.reshape(heads, -1)
+    if not torch.equal(table[:, idx], bias):
+        raise NotImplementedError("attn_bias is not translation-invariant: only relative-position biases "
+                                  "(ContinuousPositionBias) are implemented")
+    return table.contiguous(), bias.max(dim=-1).values.contiguous()
 
 
 class Transformer(nn.Module):
@@ -173,5 +263,33 @@ class Transformer(nn.Module):
 
     def forward(self, x, video_shape=None, attn_bias=None, context=None, self_attn_mask=None,
                 cross_attn_context_mask=None):
-        raise RuntimeError("Transformer blocks are evaluated by CTViT.encode on canonical (b,t,h,w,d) tokens; "
-                           "call CTViT.encode / CTViT.forward")
+        """x: (b', n, d) tokens, video_shape = (b, t, h, w) (attention.py:312-333): per layer x = peg(x) + x (the flat buffer
+        reinterpreted as video_shape), x = attn(x, attn_bias) + x over the n tokens of each of the b' sequences, x = ff(x) + x;
+        then norm_out. Works on the caller's layout — '(b t) (h w) d' with attn_bias for the spatial transformer,
+        '(b h w) t d' for the temporal one (ctvit.py:315-329) — through `engine.layer_forward`."""
+        from .. import engine
+        _no_block_autograd(x)
+        if context is not None or self_attn_mask is not None or cross_attn_context_mask is not None:
+            raise NotImplementedError("cross-attention context / masks are not used by CTViT and not implemented")
+        if video_shape is None:
+            raise ValueError("Transformer.forward: video_shape=(b, t, h, w) is required (PEG)")
+        bprime, n, dim = x.shape
+        grid = tuple(int(v) for v in video_shape)
+        if bprime * n != grid[0] * grid[1] * grid[2] * grid[3]:
+            raise ValueError(f"Transformer.forward: {tuple(x.shape)} tokens do not fill video_shape {grid}")
+        tab = rowmax = None
+        attn_grid = (bprime, 1, 1, n)
+        if attn_bias is not None:
+            hw = getattr(attn_bias, "_grid_hw", None) or (grid[2], grid[3])
+            tab, rowmax = table_from_full_bias(attn_bias.detach().float(), *hw)
+            attn_grid = (bprime, 1, hw[0], hw[1])
+        with torch.no_grad():
+            keep = self.__dict__.setdefault("_operand_buffers", {})
+            Ls = [engine.LayerWeights(l[0], l[1], l[3], dim, keep.setdefault(i, {})) for i, l in enumerate(self.layers)]
+            pairs = [pr for L in Ls for pr in L.repack]
+            ops.copy2d_batch(pairs, keep)
+            xf = _flat_f32(x)
+            for L in Ls:
+                xf, _ = engine.layer_forward(xf, L, grid, self.heads, False, tab, rowmax, False, attn_grid=attn_grid)
+            _, _, xf = ops.layernorm_fwd(xf, self.norm_out.gamma.detach().float(), None, want_bf16=False, want_f32=True)
+        return xf.to(x.dtype).reshape(bprime, n, dim)

@@ -107,7 +107,7 @@ class ClipLossFunction(torch.autograd.Function):
             ex = symm.get_exchange(b, t_hat.shape[1])
             if ex is not None:
                 # ONE kernel pushes the latents into every peer's buffer over NVLink and forms the global-batch logits
-                loss, dT, dI, dtau = ops.clip_loss_allgather(t_hat, i_hat, tau, rank, ws, ex.table, ex.next_step())
+                loss, dT, dI, dtau = ops.clip_loss_allgather(t_hat, i_hat, tau, rank, ws, ex.table, ex.next_step(), ex.status)
             else:
                 local = torch.stack((t_hat, i_hat))                                 # [2, b, d]
                 gathered = torch.empty((ws, *local.shape), device=local.device, dtype=local.dtype)
@@ -207,14 +207,19 @@ class CTCLIP(nn.Module):
         self.load_state_dict(torch.load(str(path)), strict=False)
 
     # ---------------------------------------------------------------- towers
+    def ensure_native_text(self):
+        """the NativeBert engine over the injected HF BertModel (None for any other text encoder)"""
+        if self._native_text is None and self.native_text:
+            from ..text import NativeBert, supports
+            if supports(self.text_transformer):
+                self._native_text = NativeBert(self.text_transformer)
+        return self._native_text
+
     def encode_text(self, text):
         dev = self.to_text_latent.weight.device
         if self.native_text and dev.type == "cuda":
-            from ..text import NativeBert, supports
             from ..text.bert import encode
-            if self._native_text is None and supports(self.text_transformer):
-                self._native_text = NativeBert(self.text_transformer)
-            if self._native_text is not None:   # BERT on the sm_100a kernels (ct_clip.py:685-686)
+            if self.ensure_native_text() is not None:   # BERT on the sm_100a kernels (ct_clip.py:685-686)
                 self._native_text.direct_grad = self.direct_grad
                 self._native_text.grad_ready = self.grad_ready
                 training = self.training and self.text_transformer.training and torch.is_grad_enabled()

@@ -159,9 +159,14 @@ class CTViT(nn.Module):
         return h * w
 
     def load(self, path):
+        """ctvit.py:292-296. A reference CTViT built with use_vgg_and_gan=True (pretrained_model.py) also carries the
+        `vgg.*` / `discr.*` weights of the reconstruction / GAN half, which does not exist here: those keys are dropped,
+        everything else must match exactly (strict)."""
         path = Path(path)
         assert path.exists()
-        self.load_state_dict(torch.load(str(path)))
+        sd = torch.load(str(path))
+        sd = {k: v for k, v in sd.items() if not (k.startswith("vgg.") or k.startswith("discr."))}
+        self.load_state_dict(sd)
 
     def get_video_patch_shape(self, num_frames, include_first_frame=True):
         patch_frames = 0

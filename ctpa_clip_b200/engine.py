@@ -95,9 +95,13 @@ class EncoderCtx:
 
 
 # ------------------------------------------------------------------------------------------------ forward
-def layer_forward(x, L: LayerWeights, grid, heads, temporal, tab, rowmax, save: bool):
-    """x = peg(x)+x ; x = attn(x)+x ; x = ff(x)+x   (attention.py:322-331) on canonical fp32 tokens [T, dim]"""
+def layer_forward(x, L: LayerWeights, grid, heads, temporal, tab, rowmax, save: bool, attn_grid=None):
+    """x = peg(x)+x ; x = attn(x)+x ; x = ff(x)+x   (attention.py:322-331) on canonical fp32 tokens [T, dim].
+    attn_grid (block-level `Transformer.forward` only): the attention sequences as a separate (b, t, h, w) grid when the
+    caller's memory layout is not the canonical one (the PEG then reinterprets the flat buffer as `grid`, attention.py:69-70)"""
     x1 = ops.peg_fwd(x, L.w27, L.peg_bias, grid, temporal)                                   # attention.py:324
+    if attn_grid is not None:
+        grid = attn_grid
     xn, xr, _ = ops.layernorm_fwd(x1, L.gamma, None, want_bf16=True, want_raw_bf16=True)     # :141 (q side), :139 (raw kv)
     q = ops.gemm(xn, L.wq)                                                                   # :143 to_q
     kv = ops.gemm(xr, L.wkv)                                                                 # :143 to_kv

@@ -382,9 +382,10 @@ def clip_loss(T, I, tau, row0, rows_local, want_grad=True):
     return loss, dT, dI, dtau
 
 
-def clip_loss_allgather(t_hat, i_hat, tau, rank, world, peer_table, step):
+def clip_loss_allgather(t_hat, i_hat, tau, rank, world, peer_table, step, status=None):
     """Peer-memory latent exchange fused with the global-batch logits (csrc/symm.cu), then lse + gradient of the local rows.
-    t_hat, i_hat fp32 [b, d] normalised LOCAL latents; peer_table: ctypes array of `world` symmetric-buffer pointers."""
+    t_hat, i_hat fp32 [b, d] normalised LOCAL latents; peer_table: ctypes array of `world` symmetric-buffer pointers;
+    status: int32 device scalar whose bit 0 is raised when a peer did not arrive within the timeout (loss = NaN)."""
     b, d = t_hat.shape
     B = world * b
     work = torch.empty(B * B + 2 * B + d, device=t_hat.device, dtype=torch.float32)
@@ -393,7 +394,24 @@ def clip_loss_allgather(t_hat, i_hat, tau, rank, world, peer_table, step):
     dI = torch.empty((b, d), device=t_hat.device, dtype=torch.float32)
     dtau = torch.zeros((), device=t_hat.device, dtype=torch.float32)
     _call("ctclip_clip_loss_allgather", _ptr(t_hat), _ptr(i_hat), _ptr(tau), b, d, rank, world, peer_table, C.c_uint(step),
-          _ptr(work), _ptr(loss), _ptr(dT), _ptr(dI), _ptr(dtau), _stream())
+          _ptr(work), _ptr(loss), _ptr(dT), _ptr(dI), _ptr(dtau), _ptr(status), _stream())
+    return loss, dT, dI, dtau
+
+
+def clip_loss_allgather_emulated(t_hat_all, i_hat_all, tau, world, bufs, step, status=None):
+    """every rank of the peer-memory exchange on ONE device in ONE cooperative launch (`ctclip_clip_loss_allgather_emulated`):
+    t_hat_all / i_hat_all fp32 [world*b, d]; bufs: ctypes array of `world` symmetric buffers on this device.
+    Returns per-rank (loss [world], dT [world*b, d], dI [world*b, d], dtau [world])."""
+    B, d = t_hat_all.shape
+    b = B // world
+    dev = t_hat_all.device
+    work = torch.empty(world * (B * B + 2 * B + d), device=dev, dtype=torch.float32)
+    loss = torch.zeros(world, device=dev, dtype=torch.float32)
+    dT = torch.empty((B, d), device=dev, dtype=torch.float32)
+    dI = torch.empty((B, d), device=dev, dtype=torch.float32)
+    dtau = torch.zeros(world, device=dev, dtype=torch.float32)
+    _call("ctclip_clip_loss_allgather_emulated", _ptr(t_hat_all), _ptr(i_hat_all), _ptr(tau), b, d, world, bufs,
+          C.c_uint(step), _ptr(work), _ptr(loss), _ptr(dT), _ptr(dI), _ptr(dtau), _ptr(status), _stream())
     return loss, dT, dI, dtau
 
 
@@ -448,9 +466,10 @@ def sumsq(g, out):
     _call("ctclip_sumsq", _ptr(g), _ll(g.numel()), _ptr(out), _stream())
 
 
-def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max_norm=0.0, zero_grad=True):
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max_norm=0.0, zero_grad=True, skipped=None):
+    """skipped: int32 device scalar, incremented (and the whole update skipped) when norm_sq is not finite"""
     _call("ctclip_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), _ll(p.numel()), _f(lr), _f(beta1),
-          _f(beta2), _f(eps), step, _ptr(norm_sq), _f(max_norm), int(zero_grad), _stream())
+          _f(beta2), _f(eps), step, _ptr(norm_sq), _f(max_norm), int(zero_grad), _ptr(skipped), _stream())
 
 
 PREP_PRE_OPS = {None: 0, "infer_window": 2, "affine": 3}

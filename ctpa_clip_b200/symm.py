@@ -73,6 +73,9 @@ class LatentExchange:
             self.close()
             raise _lib.CtclipError(f"latent exchange: peer mapping failed on some rank ({err or 'another rank'})")
         self.table = ptrs
+        # bit 0 is raised by the kernel when a peer did not arrive within the timeout (the loss of that step is NaN and the
+        # optimiser kernel skips the update); CTClipTrainStep.raise_if_skipped reads it
+        self.status = torch.zeros(1, device="cuda", dtype=torch.int32)
 
     def next_step(self) -> int:
         self.step += 1
@@ -107,6 +110,17 @@ def get_exchange(b_local: int, d: int, group=None):
             print(f"[ctpa_clip_b200] {e}; using the NCCL all-gather for the latents", file=sys.stderr, flush=True)
             _EXCHANGES[key] = None
     return _EXCHANGES[key]
+
+
+def set_timeout(seconds: float):
+    """how long the exchange kernel waits for a peer (default 600 s, env CTCLIP_PEER_TIMEOUT_S)"""
+    _lib.lib().ctclip_symm_set_timeout_ms.argtypes = [C.c_ulonglong]
+    _lib.check(_lib.lib().ctclip_symm_set_timeout_ms(C.c_ulonglong(max(1, int(seconds * 1000)))), "ctclip_symm_set_timeout_ms")
+
+
+def timed_out() -> bool:
+    """True when any exchange of this process gave up waiting for a peer (synchronises the device)"""
+    return any(ex is not None and int(ex.status.item()) != 0 for ex in _EXCHANGES.values())
 
 
 def shutdown():

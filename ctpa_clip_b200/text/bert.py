@@ -49,6 +49,11 @@ class NativeBert:
         self.p_hidden, self.p_attn = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob
         self.vocab = cfg.vocab_size
         self._key, self._layers = None, None
+        # train-mode dropout masks are a stateless hash of (seed, element): the per-call seed mixes torch's seed at
+        # construction (so torch.manual_seed controls it), the data-parallel rank (ranks draw different masks, as DDP replicas
+        # do) and the call counter; (seed_base, calls) travel with the trainer checkpoint so a resumed run continues the
+        # sequence instead of replaying it from step 0
+        self.seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
         self.calls = 0
         # fused attention core (csrc/bert_attn.cu) for head dim 64; CTCLIP_BERT_FUSED_ATTN=0 selects the GEMM + softmax path
         self.fused_attention = self.hd == 64 and os.environ.get("CTCLIP_BERT_FUSED_ATTN", "1") != "0"
@@ -92,6 +97,17 @@ class NativeBert:
 
     def invalidate(self):
         self._key = None
+
+    def _call_seed(self) -> int:
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return (self.seed_base * 1000003 + rank * 15485863 + self.calls * 7919 + 17) & 0x7FFFFFFF
+
+    def rng_state(self) -> dict:
+        return {"seed_base": self.seed_base, "calls": self.calls}
+
+    def load_rng_state(self, st: dict):
+        self.seed_base, self.calls = int(st["seed_base"]), int(st["calls"])
 
     def _packed_qkv_grad(self, pfx):
         """([3D, D] weight-gradient view, [3D] bias-gradient view) when the q / k / v .grad buffers of this layer sit back
@@ -165,7 +181,7 @@ class NativeBert:
         ph = self.p_hidden if training else 0.0
         pa = self.p_attn if training else 0.0
         self.calls += 1
-        seed0 = (self.calls * 7919 + 17) & 0x7FFFFFFF
+        seed0 = self._call_seed()
         ids = ids.contiguous()
         mask = mask.contiguous().to(torch.long)
         ctx = {"B": B, "L": L, "ph": ph, "pa": pa, "seed0": seed0, "ids": ids, "mask": mask, "layers": []}

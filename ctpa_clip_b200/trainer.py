@@ -103,7 +103,10 @@ class CTClipTrainStep:
         self.bucket = bucket_elems
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._pending, self._reduced = [], []
+        # incremented by the optimiser kernel whenever it refuses an update because the gradient norm is not finite
+        self.skipped = torch.zeros(1, device=self.arena.flat.device, dtype=torch.int32)
         if self.distributed:
+            self.broadcast_from_rank0()
             vit = model.visual_transformer
 
             def ema_reduce(bins, esum):
@@ -117,6 +120,45 @@ class CTClipTrainStep:
             # the 294912 -> 512 projection's gradient (604 of the 1130 MB) is rank-B_glob: its bf16 factors are all-gathered
             # (4.7 MB per rank) and multiplied locally instead of all-reducing the product (CTCLIP_FACTOR_GATHER=0: all-reduce)
             model.factor_gather = os.environ.get("CTCLIP_FACTOR_GATHER", "1") != "0"
+
+    def broadcast_from_rank0(self):
+        """Replicas must start bit-identical: gradient summation, the factor gather and the EMA all-reduce all assume it. The
+        reference gets this from the DDP wrap (parameters broadcast at construction, buffers before every forward,
+        CTCLIPTrainer.py:213-217); here the flat parameter arena and every buffer (VQ codebook, cluster_size, ...) are
+        broadcast once — the EMA statistics are all-reduced afterwards, so the buffers stay identical — and the derived
+        operands are rebuilt. A checksum across ranks confirms it."""
+        a = self.arena
+        dist.broadcast(a.flat, 0)
+        for b in self.model.buffers():
+            if b.is_floating_point() or b.dtype in (torch.int64, torch.int32, torch.bool):
+                dist.broadcast(b, 0)
+        a.sync_shadow()
+        self._invalidate_derived()
+        chk = torch.stack([a.flat.double().sum(), a.flat.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise RuntimeError("CTClipTrainStep: parameter replicas differ after the rank-0 broadcast")
+
+    def _invalidate_derived(self):
+        """parameters / buffers changed behind the operand caches' back: drop them"""
+        self.model.visual_transformer.invalidate_weights()
+        self.model._sh_text.key = None
+        self.model._sh_vis.key = None
+        if getattr(self.model, "_native_text", None) is not None:
+            self.model._native_text.invalidate()
+
+    def raise_if_skipped(self):
+        """synchronises: raises if the optimiser kernel ever refused an update (non-finite gradient norm) or the latent
+        exchange gave up waiting for a peer. Call it wherever the host already syncs (logging, checkpoints)."""
+        from . import symm
+        n = int(self.skipped.item())
+        peer = self.distributed and symm.timed_out()
+        if n or peer:
+            raise RuntimeError(f"CTClipTrainStep: {n} optimiser update(s) skipped because the gradient norm was not finite"
+                               + (" — the latent exchange timed out waiting for a peer rank" if peer else "")
+                               + "; parameters and Adam moments were left untouched")
 
     def _on_grads_ready(self, params, reduced=False):
         """called from inside backward (direct-gradient mode): these parameters' .grad in the arena is final;
@@ -164,13 +206,9 @@ class CTClipTrainStep:
         a.norm_sq.zero_()
         ops.sumsq(a.grad, a.norm_sq)
         ops.adam_step(a.flat, a.grad, a.m, a.v, a.bf16, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-                      norm_sq=a.norm_sq, max_norm=self.max_grad_norm, zero_grad=True)
+                      norm_sq=a.norm_sq, max_norm=self.max_grad_norm, zero_grad=True, skipped=self.skipped)
         # parameters changed in place behind autograd's back: drop the derived operand caches
-        self.model.visual_transformer.invalidate_weights()
-        self.model._sh_text.key = None
-        self.model._sh_vis.key = None
-        if getattr(self.model, "_native_text", None) is not None:
-            self.model._native_text.invalidate()
+        self._invalidate_derived()
 
     def step(self, text, video):
         loss = self.forward_backward(text, video)
@@ -180,10 +218,15 @@ class CTClipTrainStep:
 
     # ---------------------------------------------------------------- checkpoint I/O (CTCLIPTrainer.py:289-307)
     def save(self, path):
-        """Same package layout as CTClipTrainer.save: dict(model=<state_dict>, optim=<optimiser state>), written by rank 0.
-        The model part loads into the reference CTCLIP unchanged; the optimiser part is keyed by parameter NAME
-        (exp_avg / exp_avg_sq / step) because the flat-arena Adam has no torch param-group numbering."""
+        """Same package layout as CTClipTrainer.save: dict(model=<state_dict>, optim=<optimiser state>), written by rank 0;
+        all ranks leave together (barrier), so no rank runs ahead into the next step's latent exchange while rank 0 writes.
+        The model part loads with `CTCLIP.load` (strict=False, ct_clip.py:593-597) here and in the reference; a STRICT load
+        into a reference CTCLIP built with use_vgg_and_gan=True (pretrained_model.py) additionally expects the `vgg.*` /
+        `discr.*` keys of the reconstruction half, which this implementation never creates (out of scope). The optimiser part is
+        keyed by parameter NAME (exp_avg / exp_avg_sq / step) because the flat-arena Adam has no torch param-group numbering."""
+        self.raise_if_skipped()
         if self.distributed and dist.get_rank() != 0:
+            dist.barrier()
             return
         a = self.arena
         names = {id(p): n for n, p in self.model.named_parameters()}
@@ -195,7 +238,12 @@ class CTClipTrainStep:
         pkg = dict(model=self.model.state_dict(),
                    optim=dict(format="ctpa_clip_b200.flat_adam", step=self.step_count, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
                               lr=self.lr, betas=self.betas, eps=self.eps, max_grad_norm=self.max_grad_norm))
+        nt = self.model.ensure_native_text()
+        if nt is not None:
+            pkg["optim"]["text_dropout_rng"] = nt.rng_state()
         torch.save(pkg, str(path))
+        if self.distributed:
+            dist.barrier()
 
     def load(self, path):
         """CTClipTrainer.load: model state_dict (parameters stay views of the arena: load_state_dict copies in place), then
@@ -218,9 +266,9 @@ class CTClipTrainStep:
                         a.m[off: off + p.numel()].view(p.shape).copy_(opt["exp_avg"][n])
                         a.v[off: off + p.numel()].view(p.shape).copy_(opt["exp_avg_sq"][n])
             self.step_count = int(opt["step"])
+            if "text_dropout_rng" in opt:
+                nt = self.model.ensure_native_text()
+                if nt is not None:
+                    nt.load_rng_state(opt["text_dropout_rng"])
         self.arena.sync_shadow()
-        self.model.visual_transformer.invalidate_weights()
-        self.model._sh_text.key = None
-        self.model._sh_vis.key = None
-        if getattr(self.model, "_native_text", None) is not None:
-            self.model._native_text.invalidate()
+        self._invalidate_derived()

@@ -222,17 +222,28 @@ int ctclip_zero_shot_scores(const float* I, const float* T, const float* tau, in
  * each b_local x b_local block of L = exp(tau) T I^T as soon as the two ranks it depends on have arrived
  * (ld.acquire.sys); then the log-sum-exp and gradient kernels of ctclip_clip_loss run on the gathered latents in
  * place. `step` must be the same on all ranks, start at 1 and increase by 1 per call (two buffer parities); all ranks
- * must call collectively, on one stream per rank. A peer that does not arrive within 20 s turns the loss into NaN
- * instead of hanging. work: fp32 [B*B + 2*B + d] with B = world*b_local; outputs as ctclip_clip_loss. */
+ * must call collectively, on one stream per rank. A peer that does not arrive within the timeout (default 600 s;
+ * CTCLIP_PEER_TIMEOUT_S or ctclip_symm_set_timeout_ms) turns the loss into NaN AND sets bit 0 of *status (device int, may
+ * be NULL) instead of hanging; ctclip_adam_step never applies an update whose gradient norm is not finite.
+ * work: fp32 [B*B + 2*B + d] with B = world*b_local; outputs as ctclip_clip_loss.
+ *
+ * ctclip_clip_loss_allgather_emulated: all `world` ranks on ONE device in ONE cooperative launch (bring-up and single-GPU
+ * test of the push / flag / wait protocol; mutually waiting kernels must never be separate launches on one GPU).
+ * host_bufs: `world` symmetric buffers of this device; t_hat_all / i_hat_all fp32 [world*b_local][d]; per-rank outputs back
+ * to back: work_all [world][B*B + 2*B + d], loss_all [world], dT_all / dI_all [world*b_local][d], dtau_all [world]. */
 size_t ctclip_symm_latent_bytes(int b_local, int d, int world);
 int ctclip_symm_alloc(size_t bytes, void** ptr);
 int ctclip_symm_free(void* ptr);
 int ctclip_symm_export(void* ptr, unsigned char* handle64);
 int ctclip_symm_import(const unsigned char* handle64, void** ptr);
 int ctclip_symm_unimport(void* ptr);
+int ctclip_symm_set_timeout_ms(unsigned long long ms);
 int ctclip_clip_loss_allgather(const float* t_hat, const float* i_hat, const float* tau, int b_local, int d, int rank,
                                int world, void* const* host_peer_bufs, unsigned step, float* work, float* loss, float* dT,
-                               float* dI, float* dtau, void* stream);
+                               float* dI, float* dtau, int* status, void* stream);
+int ctclip_clip_loss_allgather_emulated(const float* t_hat_all, const float* i_hat_all, const float* tau, int b_local, int d,
+                                        int world, void* const* host_bufs, unsigned step, float* work_all, float* loss_all,
+                                        float* dT_all, float* dI_all, float* dtau_all, int* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Continuous position bias (attention.py:229-276; called ctvit.py:317): the 2 -> dim -> dim -> heads MLP with
@@ -251,10 +262,13 @@ int ctclip_cpb_table_bwd(int h, int w, int dim, int heads, const float* W1, cons
 
 /* ------------------------------------------------------------------------------------------------
  * Trainer step (CTCLIPTrainer.py:347-353, optimizer.py:10-24) on flat fp32 arenas: sum of squares for the global-norm
- * clip, then fused clip + Adam + bf16 shadow refresh + gradient zeroing. */
+ * clip, then fused clip + Adam + bf16 shadow refresh + gradient zeroing. A non-finite *norm_sq (NaN / Inf gradients, e.g. a
+ * data-parallel peer that timed out) SKIPS the whole update — parameters, moments and gradients stay as they are — and
+ * increments *skipped (device int, may be NULL); the host raises on it (CTClipTrainStep.raise_if_skipped). */
 int ctclip_sumsq(const float* g, long long n, float* out, void* stream);
 int ctclip_adam_step(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, float lr, float beta1,
-                     float beta2, float eps, int step, const float* norm_sq, float max_norm, int zero_grad, void* stream);
+                     float beta2, float eps, int step, const float* norm_sq, float max_norm, int zero_grad, int* skipped,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * data_prep volume normalisation (preprocess_train.py:99-109, resize_array :31-42, data.py:155-190).

@@ -123,3 +123,15 @@ def test_symmetric_buffer_layout_size():
     assert lib.ctclip_symm_latent_bytes(8, 512, 8) == (2 * 32 * 8 + 2 * 2 * 64 * 512) * 4
     assert lib.ctclip_symm_latent_bytes(8, 512, 33) == 0          # more ranks than the flag header holds
     assert lib.ctclip_symm_latent_bytes(0, 512, 2) == 0
+
+
+def test_package_configs_equal_the_oracles():
+    """bench.py's product arm takes its shapes from ctpa_clip_b200.configs (it imports nothing from oracle/)"""
+    from ctpa_clip_b200 import configs
+    from oracle import ctclip_oracle as O
+    assert configs.CONFIGS == O.CONFIGS
+    v, ids, mask = configs.synth_batch(configs.TINY, 2, 5)
+    assert v.shape == (2, 1, 50, 80, 80) and ids.shape == (2, 16) and int(mask[:, 8:].sum()) == 0
+    src = (ROOT / "bench.py").read_text()
+    ours = src[src.index("def run_ours"):src.index('if __name__ == "__main__"')]
+    assert "oracle" not in ours.replace("nothing from oracle/", "").replace("oracle port", ""), "product arm must not import oracle/"

@@ -114,6 +114,56 @@ def test_production_forward_vs_fixture_and_oracle():
         assert abs(float(loss2) - float(fx["loss_eval"])) < 2e-3
 
 
+def _probe(shape, seed):
+    """the Gaussian probe tools/make_golden.py projects every gradient on (same generator, same seed)"""
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_production_train_step_gradients_vs_fixture():
+    """BASELINE configs[1] shapes (CTA-pair GEMMs, split-K with K = 110 592, 576-token frames, persistent attention CTAs),
+    B = 2, train mode, VQ indices forced to the reference's: loss and EVERY parameter gradient of the unmodified reference's
+    backward (tests/golden/ctclip_production.pt: norm + projection on a seeded Gaussian probe per parameter, full tensor for
+    the small ones) + the EMA-updated codebook. Tolerances as for tiny / mid: norm within 5 %, full tensors within 4 %
+    (relative L2); the probe projection of an error vector of relative norm e is N(0, (e*norm)^2): 3 sigma at e = 4 %."""
+    fx = torch.load("tests/golden/ctclip_production.pt", weights_only=False)
+    cfg = O.PRODUCTION
+    sd = O.init_state_dict(cfg, 0)
+    video, ids, mask = O.make_inputs(cfg, fx["batch"], 0)
+    m = build(cfg, sd, O.make_text_encoder(cfg, 0)).train()
+    m.text_transformer.eval()                                          # the fixture was written with BERT dropout off
+    m.visual_transformer.force_indices = fx["indices"]
+    loss = m(text_of(ids, mask), video.cuda(), return_loss=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(fx["loss_train"])) < 2e-3, (float(loss), float(fx["loss_train"]))
+    params = dict(m.named_parameters())
+    worst = {"norm": (0.0, ""), "proj": (0.0, ""), "full": (0.0, "")}
+    n = 0
+    for k, g in fx["grads"].items():
+        if g["norm"] < 1e-6:
+            continue                                                   # analytically-zero gradients (softmax shift invariance)
+        assert params[k].grad is not None, k
+        got = params[k].grad.float().cpu()
+        e_norm = abs(got.norm().item() - g["norm"]) / g["norm"]
+        e_proj = abs((got * _probe(got.shape, g["probe_seed"])).sum().item() - g["proj"]) / g["norm"]
+        worst["norm"] = max(worst["norm"], (e_norm, k))
+        worst["proj"] = max(worst["proj"], (e_proj, k))
+        assert e_norm < 5e-2, (k, e_norm)
+        assert e_proj < 12e-2, (k, e_proj)
+        if g["full"] is not None:
+            e_full = ((got - g["full"]).norm() / g["full"].norm()).item()
+            worst["full"] = max(worst["full"], (e_full, k))
+            assert e_full < 4e-2, (k, e_full)
+        n += 1
+    print(f"production gradients: {n} parameters, worst relative errors {worst}")
+    assert n > 280
+    assert params["to_visual_latent_extra.weight"].grad is None
+    cb = m.visual_transformer.vq._codebook
+    assert torch.allclose(cb.cluster_size.cpu(), fx["ema_cluster_size"], atol=1e-5)
+    assert torch.allclose(cb.embed[0].sum(dim=-1).cpu(), fx["ema_embed_rowsum"], atol=5e-3)
+    assert torch.allclose(cb.embed[0, :16].cpu(), fx["ema_embed_head"], atol=2e-3)
+
+
 def test_train_step_reduces_loss_and_matches_adam_semantics():
     """a few optimisation steps through the flat-arena trainer on the tiny config: finite, decreasing loss"""
     from ctpa_clip_b200.trainer import CTClipTrainStep

@@ -13,7 +13,7 @@ def _probe(shape, seed):
 
 def _run(name, training):
     fx = torch.load(f"tests/golden/ctclip_{name}.pt", weights_only=False)
-    cfg = O.CONFIGS[name]
+    cfg = O.CONFIGS["mid" if name == "mid4" else name]
     sd = O.init_state_dict(cfg, fx["seed"])
     if training:
         sd = {k: v.requires_grad_(v.dtype.is_floating_point and v.numel() > 0 and "codebook" not in k and "beta" not in k)
@@ -35,7 +35,7 @@ def test_oracle_eval_matches_reference(name):
         assert torch.allclose(out["sim"], fx["sim_eval"], atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["tiny", "mid"])
+@pytest.mark.parametrize("name", ["tiny", "mid", "mid4"])
 def test_oracle_gradients_match_reference(name):
     fx, sd, txt, out = _run(name, True)
     out["loss"].backward()

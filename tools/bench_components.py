@@ -88,9 +88,9 @@ torch.cuda.empty_cache()
 sys.argv = sys.argv[:1]
 import bench
 from transformers import BatchEncoding
-from oracle import ctclip_oracle as O   # configs only
+from ctpa_clip_b200 import configs as O
 cfg = O.CONFIGS["production"]
-model = bench.build_model(cfg, torch.device("cuda"), seed=0).eval()
+model = O.build_model(cfg, torch.device("cuda"), seed=0).eval()
 vols = torch.rand(32, 1, 240, 480, 480, device=dev) * 2 - 1
 gq = torch.Generator().manual_seed(5)
 pid = torch.randint(1, 30522, (36, 512), generator=gq); pmask = torch.ones(36, 512, dtype=torch.long)

@@ -16,19 +16,19 @@ from transformers import BatchEncoding
 def main():
     import bench
     from ctpa_clip_b200.trainer import CTClipTrainStep
-    from oracle import ctclip_oracle as O   # configs only
+    from ctpa_clip_b200 import configs as O
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     cfg = O.CONFIGS[os.environ.get("CHECK_CONFIG", "production")]
     b = 2
-    video, ids, mask = bench.synth_batch(cfg, b, seed=100 + rank)
+    video, ids, mask = O.synth_batch(cfg, b, seed=100 + rank)
     text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})
     video = video.to(dev)
     grads, losses = [], []
     for fg in (True, False):
-        model = bench.build_model(cfg, dev, seed=0)
+        model = O.build_model(cfg, dev, seed=0)
         tr = CTClipTrainStep(model)
         model.factor_gather = fg   # explicit: independent of the CTCLIP_FACTOR_GATHER default
         loss = tr.forward_backward(text, video)

@@ -6,12 +6,12 @@ sys.argv = sys.argv[:1]
 import bench
 from transformers import BatchEncoding
 from ctpa_clip_b200.trainer import CTClipTrainStep
-from oracle import ctclip_oracle as O
+from ctpa_clip_b200 import configs as O
 cfg = O.CONFIGS["production"]
 dev = torch.device("cuda", 0)
-model = bench.build_model(cfg, dev)
+model = O.build_model(cfg, dev)
 tr = CTClipTrainStep(model)
-video_h, ids, mask = bench.synth_batch(cfg, 8, 100)
+video_h, ids, mask = O.synth_batch(cfg, 8, 100)
 host = [video_h.pin_memory(), video_h.clone().pin_memory()]
 video_d = video_h.to(dev)
 text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})

@@ -1,7 +1,7 @@
 """Writes tests/golden/*.pt / *.npz by running the UNMODIFIED reference (/root/reference, authoring container only)
 through oracle/ref_shim.py on the seeded synthetic weights / inputs of oracle/ctclip_oracle.py.
 
-    python tools/make_golden.py [tiny mid production resample loaders]
+    python tools/make_golden.py [tiny mid mid4 production resample loaders]
 
 The fixtures pin (i) the oracle restatement against the real reference modules, (ii) the data_prep index/weight rule and
 value arithmetic against the reference's own resize_array. They travel to the GPU box; /root/reference does not.
@@ -29,9 +29,13 @@ def probe_vector(shape, seed):
 
 
 def model_fixture(name):
+    """name: tiny | mid | production, or mid4 = the mid configuration on a batch of 4 (the concatenated global batch of the
+    2- and 4-rank data-parallel parity test, tests/test_gpu_multi.py)"""
     from transformers import BatchEncoding
+    tag = name
+    batch = {"production": 2, "mid4": 4}.get(name, 3)
+    name = "mid" if name == "mid4" else name
     cfg = O.CONFIGS[name]
-    batch = 2 if name == "production" else 3
     sd = O.init_state_dict(cfg, 0)
     txt = O.make_text_encoder(cfg, 0)
     model = ref_shim.build_reference_model(cfg, txt)
@@ -54,7 +58,7 @@ def model_fixture(name):
     fx["indices"] = idx.reshape(batch, -1).to(torch.int32)
     b, t, h, w, d = pre.shape
     pre = pre.reshape(batch, -1, d)
-    fx["pre_vq_full"] = pre.clone() if name != "production" else None
+    fx["pre_vq_full"] = pre.clone() if tag in ("tiny", "mid") else None
     fx["pre_vq_head"] = pre[:, :32].clone()
     fx["pre_vq_rowsum"] = pre.sum(dim=-1)
     fx["enc_checksum"] = enc.double().sum().item()
@@ -79,8 +83,8 @@ def model_fixture(name):
     fx["ema_cluster_size"] = cb.cluster_size.clone()
     fx["ema_embed_rowsum"] = cb.embed[0].sum(dim=-1).clone()
     fx["ema_embed_head"] = cb.embed[0, :16].clone()
-    torch.save(fx, GOLD / f"ctclip_{name}.pt")
-    print(name, "->", GOLD / f"ctclip_{name}.pt", (GOLD / f"ctclip_{name}.pt").stat().st_size // 1024, "KiB")
+    torch.save(fx, GOLD / f"ctclip_{tag}.pt")
+    print(tag, "->", GOLD / f"ctclip_{tag}.pt", (GOLD / f"ctclip_{tag}.pt").stat().st_size // 1024, "KiB")
 
 
 def resample_fixture():

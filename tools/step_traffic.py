@@ -12,12 +12,12 @@ def run():
     import bench
     from transformers import BatchEncoding
     from ctpa_clip_b200.trainer import CTClipTrainStep
-    from oracle import ctclip_oracle as O   # configs only
+    from ctpa_clip_b200 import configs as O
     cfg = O.CONFIGS["production"]
     dev = torch.device("cuda", 0)
-    model = bench.build_model(cfg, dev, seed=0)
+    model = O.build_model(cfg, dev, seed=0)
     trainer = CTClipTrainStep(model)
-    video_h, ids, mask = bench.synth_batch(cfg, 8, seed=100)
+    video_h, ids, mask = O.synth_batch(cfg, 8, seed=100)
     video = video_h.to(dev)
     text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})
     for _ in range(2):

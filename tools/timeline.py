@@ -8,14 +8,14 @@ from torch.profiler import profile, ProfilerActivity
 from transformers import BatchEncoding
 import bench
 from ctpa_clip_b200.trainer import CTClipTrainStep
-from oracle import ctclip_oracle as O   # configs only
+from ctpa_clip_b200 import configs as O
 
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 cfg = O.CONFIGS["production"]
 dev = torch.device("cuda", 0)
-model = bench.build_model(cfg, dev)
+model = O.build_model(cfg, dev)
 trainer = CTClipTrainStep(model)
-video, ids, mask = bench.synth_batch(cfg, B, 100)
+video, ids, mask = O.synth_batch(cfg, B, 100)
 video = video.to(dev)
 text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})
 for _ in range(2):

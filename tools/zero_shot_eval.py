@@ -35,7 +35,7 @@ class SyntheticVolumes:
 def main():
     import bench
     from ctpa_clip_b200.inference import PATHOLOGIES, ZeroShotEvaluator
-    from oracle import ctclip_oracle as O   # configs only
+    from ctpa_clip_b200 import configs as O
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -44,7 +44,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = O.CONFIGS[os.environ.get("ZS_CONFIG", "production")]
     n_vol = int(os.environ.get("ZS_VOLUMES", "256"))
-    model = bench.build_model(cfg, dev, seed=0).eval()
+    model = O.build_model(cfg, dev, seed=0).eval()
     # no tokenizer offline: 36 seeded id rows stand for the tokenised "<pathology> is present." / "... is not present." pairs
     g = torch.Generator().manual_seed(9)
     P, L = len(PATHOLOGIES), cfg["seq_len"]
