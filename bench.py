@@ -7,12 +7,18 @@
 
 Workload (N=1): BASELINE.json configs[1] — production CT-CLIP (CTViT dim 512, patch 20x20x10, 4+4 layers, 8x32 heads,
 codebook 8192, BERT-base text tower, 294912->512 latent projection), 8 synthetic 480x480x240 volumes + 8 reports of 512
-token ids per rank; a step = forward(global-batch InfoNCE) + backward + gradient all-reduce + clip(0.5) + Adam.
-N>1 keeps 8 volumes per rank (weak scaling; N=8 is configs[2], global batch 64; latents exchanged over NVLink by the loss
-kernel itself, csrc/symm.cu). Prints ONE JSON line on rank 0: value = device-resident steps (CUDA events, max over ranks);
-e2e = the same steps fed from pinned host memory (volumes, token ids, masks copied every step on a copy stream, every step's
-loss copied back to pinned memory and consumed by the host one step later); gpu_launches = kernels of libctclip_sm100.so
-launched by this rank inside the timed region (gpu_launches_per_step = per step); roofline / cpu_baseline as DESIGN.md §8.
+token ids per rank; a step = forward(global-batch InfoNCE) + backward + gradient reduction + clip(0.5) + Adam.
+N>1 keeps 8 volumes per rank by default (weak scaling; N=8 is configs[2], global batch 64; latents exchanged over NVLink by
+the loss kernel itself, csrc/symm.cu); `--batch 32 / 16` at N = 2 / 4 runs configs[2] literally (global batch 64).
+Prints ONE JSON line on rank 0:
+  value        device-resident steps (CUDA events, barrier + synchronize on both sides, max over ranks)
+  e2e          the same steps fed from pinned HOST memory every step: raw int16 scans -> H2D on a copy stream -> bit-exact
+               data_prep kernel on the device -> step -> loss copied back to pinned memory and read by the host
+               (e2e.fp32_volumes: the same with already normalised fp32 volumes, the round-1 definition)
+  roofline     all gemm_bf16_kernel launches of one instrumented step against MEASURED_PEAKS.json (+ per-shape table)
+  prep         BASELINE configs[3] (data_prep, batch 32) against the measured HBM copy bandwidth
+  zero_shot    BASELINE configs[4] (256 volumes x 18 prompt pairs), device-resident and end to end
+  gpu_launches kernels of libctclip_sm100.so launched by this rank inside the timed region; cpu_baseline as DESIGN.md §8.
 """
 from __future__ import annotations
 
@@ -43,6 +49,9 @@ def parse():
     ap.add_argument("--config", default="production")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-op device-time breakdown of one step to this file")
+    ap.add_argument("--e2e-mode", default="both", choices=["both", "raw", "fp32"],
+                    help="end-to-end input: raw int16 scans + on-device data_prep (headline), pre-normalised fp32 volumes, or both")
+    ap.add_argument("--no-extras", action="store_true", help="skip the data_prep (configs[3]) and zero-shot (configs[4]) legs")
     return ap.parse_args()
 
 
@@ -115,10 +124,10 @@ def run_reference(args):
     from oracle import ctclip_oracle as O
     cfg = O.CONFIGS[args.config]
     threads = os.cpu_count() or 1
-    sample_b = 1
+    sample_b = 2          # B = 1 would make the InfoNCE loss identically 0
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(cfg, sample_b, threads)
-    times = [cpu_reference_step(cfg, sample_b, threads) for _ in range(max(1, min(args.steps, 8)))]
+    times = [cpu_reference_step(cfg, sample_b, threads) for _ in range(max(1, min(args.steps, 4)))]
     t = sorted(times)[len(times) // 2]
     value = sample_b / t
     sample = f"{sample_b} volume(s) forward+backward per step, fp32, oracle port of the reference CT_CLIP on {threads} host threads"
@@ -134,27 +143,67 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+RAW_SHAPE = (512, 512, 320)            # (H, W, N) int16 as a NIfTI array stores it — SURVEY §8(d) config 4
+RAW_SPACING = (0.703125, 1.125)        # xy, z  -> int(512*0.9375) = 480, int(320*0.75) = 240 exactly
+PREP_BYTES_PER_VOLUME = 512 * 512 * 320 * 2 + 240 * 480 * 480 * 4   # 389.0 MB algorithmic
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and with them its first-touch pinned allocations) to the NUMA node its GPU hangs off, so
+    that the per-step host->device copies of 8 ranks do not all cross one socket's memory controller / UPI.
+    CTCLIP_BENCH_NUMA=0 disables it (A/B)."""
+    if os.environ.get("CTCLIP_BENCH_NUMA", "1") == "0":
+        return {"bound": False, "why": "CTCLIP_BENCH_NUMA=0"}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return {"bound": False, "why": f"{bdf}: numa_node = -1"}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": f"no allowed CPU on node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "gpu": bdf, "node": node, "cpus": len(cpus)}
+    except Exception as e:                      # containers without sysfs NUMA info: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"[:120]}
+
+
+def synth_raw_scans(batch, seed):
+    """`batch` raw int16 scans (H, W, N) = (512, 512, 320), values randint(-1024, 3071)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-1024, 3071, (batch, *RAW_SHAPE), generator=g, dtype=torch.int16)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from transformers import BatchEncoding
     from ctpa_clip_b200 import _lib, ops
-    from ctpa_clip_b200.trainer import CTClipTrainStep
     from ctpa_clip_b200 import configs as O   # shapes + seeded synthetic inputs; the product arm imports nothing from oracle/
+    from ctpa_clip_b200.data_prep import preprocess_volumes
+    from ctpa_clip_b200.trainer import CTClipTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = O.CONFIGS[args.config]
+    production = args.config == "production"
     B = args.batch
     model = O.build_model(cfg, dev, seed=0)
     trainer = CTClipTrainStep(model)
     video_h, ids, mask = O.synth_batch(cfg, B, seed=100 + rank)
-    host = [video_h.pin_memory(), video_h.clone().pin_memory()]
     video_d = video_h.to(dev)
     text = BatchEncoding({"input_ids": ids.to(dev), "attention_mask": mask.to(dev)})
 
@@ -192,114 +241,230 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- end to end: pinned host volumes -> (copy stream, double buffered) -> step -> loss read back
+    # ---- end to end. Host buffers -> H2D on a copy stream (double buffered) -> step -> loss read back, every step.
+    # mode "raw" (headline, production config): the host holds RAW int16 scans (512, 512, 320), 168 MB each; the bit-exact
+    #   data_prep kernel (HU clip / normalise / trilinear resample, ctclip_prep_resample) runs on the device behind the copy
+    #   and hands the step its (B, 1, 240, 480, 480) fp32 volumes — the reference's own order of work (data.py:138-192
+    #   resamples inside the DataLoader, on the CPU) and 24 % fewer PCIe bytes than shipping 221 MB fp32 volumes.
+    # mode "fp32": already normalised fp32 volumes in pinned memory (round-1 definition), kept as the comparison.
     copy_stream = torch.cuda.Stream()
-    bufs = [torch.empty_like(video_d), torch.empty_like(video_d)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
     ids_h, mask_h = ids.pin_memory(), mask.pin_memory()
-    tbufs = [(torch.empty_like(text.input_ids), torch.empty_like(text.attention_mask)) for _ in range(2)]
-    texts = [BatchEncoding({"input_ids": a, "attention_mask": b}) for a, b in tbufs]
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])
-            bufs[i % 2].copy_(host[i % 2], non_blocking=True)          # this step's volumes ...
-            tbufs[i % 2][0].copy_(ids_h, non_blocking=True)            # ... and token ids / attention mask
-            tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    def run_e2e(mode):
+        if mode == "raw":
+            raw = synth_raw_scans(B, seed=200 + rank)
+            host = [raw.pin_memory(), raw.clone().pin_memory()]
+            stage = [torch.empty(host[0].shape, device=dev, dtype=torch.int16) for _ in range(2)]
+            del raw
+        else:
+            host = [video_h.pin_memory(), video_h.clone().pin_memory()]
+            stage = None
+        bufs = [torch.empty_like(video_d), torch.empty_like(video_d)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        tbufs = [(torch.empty_like(text.input_ids), torch.empty_like(text.attention_mask)) for _ in range(2)]
+        texts = [BatchEncoding({"input_ids": a, "attention_mask": b}) for a, b in tbufs]
+        h2d_events = []
 
-    losses = []
-    k = [0]                                   # running step index: step k reads bufs[k % 2], prefetches step k + 1
-    loss_host = torch.empty(args.steps + 8, dtype=torch.float32).pin_memory()   # one pinned slot per step
-    in_flight = []                            # (slot, event) of losses copied back but not yet consumed by the host
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(copy_stream)
+                if mode == "raw":
+                    stage[i % 2].copy_(host[i % 2], non_blocking=True)             # this step's raw scans ...
+                else:
+                    bufs[i % 2].copy_(host[i % 2], non_blocking=True)
+                tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                    # ... token ids / attention mask
+                tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
+                c1.record(copy_stream)
+                h2d_events.append((c0, c1))
+                if mode == "raw":                                                  # data_prep on the device, behind the copy
+                    out = preprocess_volumes(stage[i % 2], 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1])
+                    bufs[i % 2].view(out.shape).copy_(out) if out.data_ptr() != bufs[i % 2].data_ptr() else None
+                ready[i % 2].record(copy_stream)
 
-    def step_e2e(_):
-        i = k[0]
-        k[0] += 1
-        prefetch(i + 1)                       # next step's volumes: H2D overlaps this step's kernels
-        torch.cuda.current_stream().wait_event(ready[i % 2])
-        loss = trainer.step(texts[i % 2], bufs[i % 2])
-        consumed[i % 2].record()
-        # D2H read of the step's result, EVERY step (the trainer's `loss.item()`, CTCLIPTrainer.py:346), as an async copy into
-        # pinned memory; the host consumes step i-1's value here, while step i is already enqueued, so its Python prelude
-        # (module walk, operand-cache rebuild) no longer idles the GPU after each step. The host never runs more than one
-        # step ahead; the last value is consumed right after the closing synchronize.
-        slot = i % loss_host.numel()
-        loss_host[slot: slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        if in_flight:
-            s_prev, e_prev = in_flight.pop(0)
+        losses = []
+        k = [0]                                   # running step index: step k reads bufs[k % 2], prefetches step k + 1
+        loss_host = torch.empty(args.steps + 8, dtype=torch.float32).pin_memory()   # one pinned slot per step
+        in_flight = []                            # (slot, event) of losses copied back but not yet consumed by the host
+
+        def step_e2e(_):
+            i = k[0]
+            k[0] += 1
+            prefetch(i + 1)                       # next step's inputs: H2D (+ prep) overlaps this step's kernels
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            loss = trainer.step(texts[i % 2], bufs[i % 2])
+            consumed[i % 2].record()
+            # D2H read of the step's result, EVERY step (the trainer's `loss.item()`, CTCLIPTrainer.py:346), as an async copy
+            # into pinned memory; the host consumes step i-1's value here, while step i is already enqueued. The host never
+            # runs more than one step ahead; the last value is consumed right after the closing synchronize.
+            slot = i % loss_host.numel()
+            loss_host[slot: slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if in_flight:
+                s_prev, e_prev = in_flight.pop(0)
+                e_prev.synchronize()
+                losses.append(float(loss_host[s_prev]))
+            in_flight.append((slot, ev))
+
+        for e in consumed:
+            e.record()
+        prefetch(0)
+        for i in range(min(2, args.warmup)):      # the copy pipeline reaches steady state after two steps
+            step_e2e(i)
+        h2d_events.clear()
+        ms = timed(step_e2e, args.steps) / args.steps
+        for s_prev, e_prev in in_flight:          # timed() ended with a device synchronize: the last loss is on the host
             e_prev.synchronize()
             losses.append(float(loss_host[s_prev]))
-        in_flight.append((slot, ev))
+        in_flight.clear()
+        nbytes = int(host[0].numel() * host[0].element_size() + ids.numel() * 8 + mask.numel() * 8)
+        copy_ms = sorted(a.elapsed_time(b) for a, b in h2d_events[:-1]) or [float("nan")]
+        gbps = torch.tensor([nbytes / (copy_ms[len(copy_ms) // 2] * 1e-3) / 1e9], device=dev)   # median copy of this rank
+        if world > 1:
+            dist.all_reduce(gbps, op=dist.ReduceOp.MIN)
+        return {"ms": ms, "h2d_bytes": nbytes, "loss": losses[-1] if losses else None, "h2d_GBps_slowest_rank": float(gbps)}
 
-    for e in consumed:
-        e.record()
-    prefetch(0)
-    for i in range(min(2, args.warmup)):      # the copy pipeline reaches steady state after two steps
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    for s_prev, e_prev in in_flight:          # timed() ended with a device synchronize: the last loss is already on the host
-        e_prev.synchronize()
-        losses.append(float(loss_host[s_prev]))
-    in_flight.clear()
+    e2e_modes = ["raw", "fp32"] if production else ["fp32"]
+    if args.e2e_mode != "both":
+        e2e_modes = [m for m in e2e_modes if m == args.e2e_mode] or e2e_modes[:1]
+    e2e_runs = {m: run_e2e(m) for m in e2e_modes}
+    torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = world * B / (ms_e2e * 1e-3)
+    head = e2e_runs[e2e_modes[0]]
+    e2e_value = world * B / (head["ms"] * 1e-3)
 
     # ---- one instrumented step: per-op device time (CUDA events on the launching stream)
     ops.profile_begin()
     trainer.step(text, video_d)
     torch.cuda.synchronize()
     prof = ops.profile_end()
-    gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm"))
-    gemm_flops = sum(v["flops"] for k, v in prof.items() if k.startswith("gemm"))
+    gemms = {k: v for k, v in prof.items() if k.startswith("gemm")}
+    gemm_ms = sum(v["ms"] for v in gemms.values())
+    gemm_flops = sum(v["flops"] for v in gemms.values())
+    gemm_n = sum(v["n"] for v in gemms.values())
     total_prof_ms = sum(v["ms"] for v in prof.values())
     tf_peak, hbm_peak, peak_src = peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    per_shape = [{"shape": k[5:], "launches": v["n"], "ms": round(v["ms"], 4),
+                  "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None,
+                  "frac": round(v["flops"] / (v["ms"] * 1e-3) / 1e12 / tf_peak, 3) if v["ms"] > 0 else None}
+                 for k, v in sorted(gemms.items(), key=lambda kv: -kv[1]["ms"])][:16]
     if args.breakdown and rank == 0:
         rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
         Path(args.breakdown).write_text(json.dumps({"ms_per_step": ms_step, "ops": rows}, indent=1))
+    trainer.raise_if_skipped()                 # no optimiser update was refused (non-finite gradients / peer timeout)
+
+    # ---- BASELINE configs[3]: data_prep, batch 32 raw scans (32 / N per rank), resident in HBM; HBM roofline
+    prep = None
+    if production and not args.no_extras:
+        nb = max(1, 32 // world)
+        raw_d = synth_raw_scans(min(nb, 4), seed=300 + rank).to(dev)
+        raw_d = raw_d.repeat((nb + raw_d.shape[0] - 1) // raw_d.shape[0], 1, 1, 1)[:nb].contiguous()
+        for _ in range(3):
+            out = preprocess_volumes(raw_d, 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1])
+        iters = 10
+        prep_ms = timed(lambda i: preprocess_volumes(raw_d, 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1]), iters) / iters
+        gbs = nb * PREP_BYTES_PER_VOLUME / (prep_ms * 1e-3) / 1e9          # per GPU, algorithmic bytes
+        prep = {"workload": f"BASELINE configs[3]: HU clip + normalise + trilinear resample of {nb * world} raw int16 512x512x320 "
+                            f"scans to 240x480x480 fp32 ({nb} per GPU), inputs resident (12.4 GB per 32 scans >> L2)",
+                "ms": prep_ms, "volumes_per_s": nb * world / (prep_ms * 1e-3), "GBps_per_gpu": gbs, "peak_GBps": hbm_peak,
+                "frac": gbs / hbm_peak, "algorithmic_bytes_per_volume": PREP_BYTES_PER_VOLUME,
+                "out_shape": list(out.shape), "kernel": "prep_hwn_i16_kernel (bit-exact vs the C oracle / the reference's resize_array)"}
+        del raw_d, out
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: zero-shot scoring, 256 volumes x 18 prompt pairs (replicas: 256 / N volumes per rank)
+    zero_shot = None
+    if production and not args.no_extras:
+        from ctpa_clip_b200.inference import PATHOLOGIES, ZeroShotEvaluator
+        g = torch.Generator().manual_seed(9)
+        P, L = len(PATHOLOGIES), cfg["seq_len"]
+        pid = torch.randint(1, cfg["text"]["vocab_size"], (2 * P, L), generator=g)   # no tokenizer offline: seeded id rows
+        pmask = torch.ones(2 * P, L, dtype=torch.long)
+        pid[:, 16:] = 0
+        pmask[:, 16:] = 0
+        ev = ZeroShotEvaluator(model, BatchEncoding({"input_ids": pid.to(dev), "attention_mask": pmask.to(dev)}), batch_size=8)
+        n_vol = 256
+
+        class Vols:
+            def __init__(self, base, n):
+                self.base, self.n = base, n
+
+            def __len__(self):
+                return self.n
+
+            def __getitem__(self, i):
+                return self.base[i % len(self.base)]
+
+        pinned = [v.pin_memory() for v in video_h]                 # (1, f, h, w) each; cycled (host memory stays small)
+        ev.evaluate(Vols(pinned, 8 * world))                       # warm-up (copy pipeline, eval-mode operand caches)
+        zs_e2e_ms = timed(lambda i: ev.evaluate(Vols(pinned, n_vol)), 1)
+        resident = [v for v in video_d]
+        ev.evaluate(Vols(resident, 8 * world))
+        zs_ms = timed(lambda i: ev.evaluate(Vols(resident, n_vol)), 1)
+        zero_shot = {"workload": f"BASELINE configs[4]: {n_vol} volumes x {P} pathology prompt pairs, {n_vol // world} volumes per GPU, "
+                                 "each volume encoded once, prompt latents once (the reference re-encodes both per pathology)",
+                     "volumes_per_s": n_vol / (zs_ms * 1e-3), "ms": zs_ms,
+                     "e2e": {"volumes_per_s": n_vol / (zs_e2e_ms * 1e-3), "ms": zs_e2e_ms,
+                             "h2d_bytes": int(n_vol // world * video_h[0].numel() * 4), "d2h_bytes": n_vol * P * 4}}
+        model.train()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     # DRAM bytes per GEMM launch: NOT measured in this run (a profiler is never attached to a bench run) — the committed ncu
-    # metrics pass over one identical training step (tools/step_traffic.py -> profiles/r01_step_traffic.json)
-    traffic, traffic_note = None, "profiles/r01_step_traffic.json not found"
-    tpath = Path(__file__).resolve().parent / "profiles" / "r01_step_traffic.json"
-    if tpath.exists():
-        tj = json.loads(tpath.read_text())["gemm"]
+    # metrics pass over one identical training step (tools/step_traffic.py -> profiles/rNN_step_traffic.json, newest round)
+    traffic, traffic_note = None, "no profiles/r*_step_traffic.json"
+    tfiles = sorted((ROOT / "profiles").glob("r*_step_traffic.json"))
+    if tfiles:
+        tj = json.loads(tfiles[-1].read_text())["gemm"]
         traffic = tj["dram_bytes_per_launch"]
         traffic_note = (f"bytes per launch: dram__bytes_read+write summed over the {tj['launches']} gemm_bf16_kernel launches of one "
-                        f"step / launches, from the committed ncu pass profiles/r01_step_traffic.json "
+                        f"step / launches, from the committed ncu pass profiles/{tfiles[-1].name} "
                         f"(GEMM share of that serialised step: {tj['share_of_step']:.3f})")
+    e2e_note = {"raw": "pinned RAW int16 scans (512x512x320) + token ids + masks copied every step on a copy stream (double "
+                       "buffered); the bit-exact data_prep kernel (HU clip/normalise/trilinear resample) runs on the device "
+                       "behind the copy; every step's loss is copied to pinned host memory and read by the host one step later",
+                "fp32": "pinned, already normalised fp32 volumes + token ids + masks, double-buffered copy stream; every step's "
+                        "loss is copied to pinned host memory and read by the host one step later"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "CT-CLIP contrastive training step (BASELINE.json configs[1]): production CTViT+BERT-base, "
-                               f"{B} volumes 480x480x240 + {B} reports x 512 ids per rank, fwd+bwd+allreduce+clip+Adam",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if B == 8 else f"per-rank batch {B}",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"CT-CLIP contrastive training step (BASELINE.json configs[{1 if world == 1 else 2}]): "
+                               f"{args.config} CTViT+BERT-base, {B} volumes 480x480x240 + {B} reports x 512 ids per rank, "
+                               "fwd + global-batch InfoNCE + bwd + gradient reduction + clip(0.5) + Adam",
                    "global_batch": world * B, "per_rank_batch": B, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2: 1.77 GB of volumes and >10 GB of activations per step vs 126 MB L2",
-                   "text_tower": "BERT-base forward+backward on libctclip_sm100.so (tcgen05 GEMMs incl. batched per-head QK^T/PV, "
-                                 "native softmax/GELU/LayerNorm/dropout kernels); HF module only holds the parameters"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(video_h.numel() * 4 + ids.numel() * 8 + mask.numel() * 8), "d2h_bytes_per_step": 4,
-                "note": "pinned host volumes + token ids + masks, double-buffered copy stream; every step's loss is copied to pinned host memory and read by the host one step later (last one after the closing sync)"},
+                   "text_tower": "BERT-base forward+backward on libctclip_sm100.so (tcgen05 GEMMs, fused attention core, "
+                                 "native softmax/GELU/LayerNorm/dropout kernels); HF module only holds the parameters",
+                   "host_numa": numa},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": head["ms"], "h2d_bytes_per_step": head["h2d_bytes"],
+                "d2h_bytes_per_step": 4, "mode": e2e_modes[0], "h2d_GBps_slowest_rank": head["h2d_GBps_slowest_rank"],
+                "note": e2e_note[e2e_modes[0]],
+                **({"fp32_volumes": {"value": world * B / (e2e_runs["fp32"]["ms"] * 1e-3), "ms_per_step": e2e_runs["fp32"]["ms"],
+                                     "h2d_bytes_per_step": e2e_runs["fp32"]["h2d_bytes"],
+                                     "h2d_GBps_slowest_rank": e2e_runs["fp32"]["h2d_GBps_slowest_rank"],
+                                     "note": e2e_note["fp32"]}} if "fp32" in e2e_runs and e2e_modes[0] != "fp32" else {})},
         "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
-        "achieved_tflops_step": world * B * TRAIN_GF_PER_VOLUME / (ms_step * 1e-3) / 1e3 / world,
+        "achieved_tflops_step": B * TRAIN_GF_PER_VOLUME / (ms_step * 1e-3) / 1e3,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf_peak if tf_peak else None, "traffic": traffic, "traffic_note": traffic_note,
-                     "kernel": "gemm_bf16_kernel (tcgen05): all launches of one step, algorithmic (un-padded) FLOPs / "
-                               "summed CUDA-event durations", "peak_source": peak_src,
-                     "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None},
+                     "kernel": f"gemm_bf16_kernel (tcgen05/TMEM/TMA): ALL {gemm_n} launches of one step, algorithmic (un-padded) "
+                               "FLOPs / summed CUDA-event durations; per_shape lists the instantiations by time",
+                     "peak_source": peak_src, "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
+                     "dominant": per_shape[0] if per_shape else None, "per_shape": per_shape},
         "clocks": clocks,
-        "loss": losses[-1] if losses else None,
+        "loss": head["loss"],
     }
+    if prep is not None:
+        out["prep"] = prep
+    if zero_shot is not None:
+        out["zero_shot"] = zero_shot
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         t = cpu_reference_step(cfg, 1, threads)

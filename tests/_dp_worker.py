@@ -24,7 +24,7 @@ def train_mode(rank, world):
     from ctpa_clip_b200 import symm
     from ctpa_clip_b200.trainer import CTClipTrainStep
     from oracle import ctclip_oracle as O
-    from tests.test_gpu_model import build
+    from _common import build
     fx = torch.load("tests/golden/ctclip_mid4.pt", weights_only=False)
     cfg = O.MID
     B = fx["batch"]

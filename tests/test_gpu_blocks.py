@@ -11,7 +11,7 @@ from oracle import ctclip_oracle as O  # noqa: E402
 
 
 def _vit(cfg, seed=0):
-    from tests.test_gpu_model import build
+    from _common import build
     sd = O.init_state_dict(cfg, seed)
     m = build(cfg, sd, O.make_text_encoder(cfg, seed)).eval()
     return m.visual_transformer, sd
