@@ -280,8 +280,7 @@ def run_ours(args):
                 c1.record(copy_stream)
                 h2d_events.append((c0, c1))
                 if mode == "raw":                                                  # data_prep on the device, behind the copy
-                    out = preprocess_volumes(stage[i % 2], 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1])
-                    bufs[i % 2].view(out.shape).copy_(out) if out.data_ptr() != bufs[i % 2].data_ptr() else None
+                    preprocess_volumes(stage[i % 2], 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1], out=bufs[i % 2])
                 ready[i % 2].record(copy_stream)
 
         losses = []

@@ -6,8 +6,13 @@
 
 namespace {
 
+constexpr int kSumsqBlocks = 1024;   // fixed grid: the partial sums and their order do not depend on the device or the launch
+
+// Deterministic sum of squares: block b writes ONE partial (fixed strided element order, shuffle tree, fixed warp order) and the
+// second kernel adds the kSumsqBlocks partials in index order. No atomics: every data-parallel rank gets the bit-identical
+// norm from bit-identical (all-reduced) gradients, so the clip factor — and with it the replicas — cannot drift apart.
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ out) {
+sumsq_partial_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ partials) {
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = g[i];
@@ -21,8 +26,22 @@ sumsq_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ o
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i];
-    atomicAdd(out, t);
+    partials[blockIdx.x] = t;
   }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ float sh[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += sh[0];
 }
 
 __global__ void __launch_bounds__(256)
@@ -62,17 +81,18 @@ adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__
 
 }  // namespace
 
-// out[0] += sum(g^2)
-extern "C" int ctclip_sumsq(const float* g, long long n, float* out, void* stream) {
+// out[0] += sum(g^2), deterministically (see above). workspace: device scratch of ctclip_workspace_bytes("sumsq") bytes.
+extern "C" int ctclip_sumsq(const float* g, long long n, float* out, float* workspace, void* stream) {
   if (n <= 0) return CTCLIP_OK;
   if (n % 4 || (reinterpret_cast<uintptr_t>(g) & 15)) return ctclip::fail(CTCLIP_E_ALIGN, "sumsq: n %% 4 and 16-byte alignment required");
+  if (workspace == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "sumsq: workspace of ctclip_workspace_bytes(\"sumsq\") bytes required");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
-  long long blocks = (n / 4 + 255) / 256;
-  const long long cap = (long long)ctclip::sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, out);
-  return ctclip::check_launch("sumsq");
+  sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, workspace);
+  rc = ctclip::check_launch("sumsq(partials)");
+  if (rc) return rc;
+  sumsq_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, kSumsqBlocks, out);
+  return ctclip::check_launch("sumsq(final)");
 }
 
 // one Adam step over flat arenas; `step` is the 1-based step count; norm_sq (device scalar, may be NULL) enables clipping

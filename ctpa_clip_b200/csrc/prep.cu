@@ -458,6 +458,234 @@ prep_hwn_i16_kernel(const PrepParams p, const float* __restrict__ lut, int lut_l
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fast path, v2
+// Same brick decomposition and the same register marching as prep_hwn_i16_kernel, re-laid-out around 128-bit shared-memory
+// traffic and packed arithmetic (the v1 kernel issued ~35 instructions per output voxel, a third of them scalar LDS / STS):
+//  * slots are [j][k] — the depth axis k is contiguous, pitch KP = kn8 + 4 floats (KP / 4 odd: the 16-byte accesses of
+//    eight consecutive columns fall into eight different bank groups). A staging thread converts its 16-byte chunk (8 raw
+//    int16 along k) and writes it back with two STS.128; the w-interpolation of a thread reads its 8 planes of a column
+//    with two LDS.128 per tap instead of eight scalar loads.
+//  * HU normalisation on packed 16-bit integers: clip in the raw domain (VIMNMX.S16x2), one packed add of (intercept + 1024),
+//    int -> float through the 2^23 mantissa trick (PRMT + one packed FADD, no I2F), then the same exact 3-instruction
+//    Newton division as v1 on FMUL2 / FFMA2.
+//  * all three lerp levels are packed along the DEPTH axis (adjacent planes of one column sit in adjacent registers), the
+//    d taps of a thread's run live in registers, and for the production 4:3 depth ratio (three outputs per four input
+//    planes, no plane shared between quads) the emission is straight-line code.
+// A warp owns 6 output depths = an aligned window of 8 input planes; lane = output column (fw <= 32 per CTA, chosen by the
+// host so that the CTA's input columns span <= 32). Same operation order as the generic kernel -> bit-identical results.
+constexpr int V2_OPT = 6, V2_KW = 8, V2_CPR = 2;
+constexpr float kMagic = 8388608.f + 1024.f;   // float(0x4B000000 | u) - kMagic == u - 1024 exactly for 0 <= u < 2^16
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max) {
+  extern __shared__ __align__(16) float tile[];  // [3][jn_max][KP] + slack | d taps [48] | h taps [FOH]
+  const int KP = kn8 + 4;
+  const int slot_elems = jn_max * KP;
+  float4* s_dtap = reinterpret_cast<float4*>(tile + 3 * slot_elems + 16);
+  float4* s_htap = s_dtap + FG * V2_OPT;
+  const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+  constexpr int ftd = FG * V2_OPT;
+  const int n_wt = (p.wwn + fw - 1) / fw;
+  const int oh_base = p.wh0 + blockIdx.x * FOH;
+  const int n_oh = min(FOH, p.wh0 + p.whn - oh_base);
+  const int od_base = p.wd0 + (blockIdx.y / n_wt) * ftd;
+  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * fw;
+  const int nd = min(ftd, p.wd0 + p.wdn - od_base);
+  const int nw = min(fw, p.ww0 + p.wwn - ow_base);
+  const short* in16 = reinterpret_cast<const short*>(p.in) + (long long)blockIdx.z * p.sbatch;
+
+  if (tid < nd) {
+    int a, b; float x, y;
+    taps(p.D, p.oD, od_base + tid, a, b, x, y);
+    s_dtap[tid] = make_float4(x, y, __int_as_float(a), __int_as_float(b));   // (w0, w1, k0, k1): the weights are one LDS.64
+  }
+  if (tid < n_oh) {
+    int a, b; float x, y;
+    taps(p.H, p.oH, oh_base + tid, a, b, x, y);
+    s_htap[tid] = make_float4(__int_as_float(a), x, y, __int_as_float(b));
+  }
+  int k_lo, k_hi, j_lo, j_hi, t0, t1; float f0, f1;
+  taps(p.D, p.oD, od_base, k_lo, t1, f0, f1);
+  taps(p.D, p.oD, od_base + nd - 1, t0, t1, f0, f1);
+  k_hi = min(p.D - 1, max(t1, t0 + 1));
+  taps(p.W, p.oW, ow_base, j_lo, t1, f0, f1);
+  taps(p.W, p.oW, ow_base + nw - 1, t0, j_hi, f0, f1);
+  const int k_lo8 = k_lo & ~7;
+  const int kc_n = (k_hi - k_lo8) / 8 + 1;   // 16-byte chunks per input column
+  const int jn = j_hi - j_lo + 1;
+  const int chunks = kc_n * jn;
+  // this thread's w taps
+  const bool ow_ok = lane < nw;
+  int ja, jb; float fa, fb;
+  taps(p.W, p.oW, ow_base + (ow_ok ? lane : nw - 1), ja, jb, fa, fb);
+  ja -= j_lo; jb -= j_lo;
+  const float2 wa = make_float2(fa, fa), wb = make_float2(fb, fb);
+
+  int cj[V2_CPR], ck[V2_CPR];
+  const short* cptr[V2_CPR];
+#pragma unroll
+  for (int u = 0; u < V2_CPR; ++u) {
+    const int idx = tid + u * 256;
+    ck[u] = idx / jn;
+    cj[u] = idx - ck[u] * jn;
+    cptr[u] = in16 + (long long)(j_lo + cj[u]) * p.sw + k_lo8 + 8 * ck[u];
+  }
+  const bool last_chunk_dup = (k_lo8 + 8 * kc_n == p.D);   // the brick reaches the last plane: duplicate it at k = D
+  auto row_load = [&](int row, uint4 (&pf)[V2_CPR]) {
+    const long long ro = (long long)row * p.sh;
+#pragma unroll
+    for (int u = 0; u < V2_CPR; ++u)
+      if (tid + u * 256 < chunks) pf[u] = __ldg(reinterpret_cast<const uint4*>(cptr[u] + ro));
+  };
+  // raw clip bounds and bias as packed int16 pairs: c + 1024 = clamp(raw, -1000 - icpt, 1000 - icpt) + (icpt + 1024)
+  const uint32_t lo2 = (uint32_t)(uint16_t)(short)(-1000 - icpt) * 0x10001u, hi2 = (uint32_t)(uint16_t)(short)(1000 - icpt) * 0x10001u;
+  const uint32_t bias2 = (uint32_t)(uint16_t)(short)(icpt + 1024) * 0x10001u;
+  auto row_store = [&](int row, const uint4 (&pf)[V2_CPR]) {
+    float* dst = tile + (row % 3) * slot_elems;
+#pragma unroll
+    for (int u = 0; u < V2_CPR; ++u) {
+      if (tid + u * 256 < chunks) {
+        const uint32_t w4[4] = {pf[u].x, pf[u].y, pf[u].z, pf[u].w};
+        float2 y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t c2 = __vadd2(__vmaxs2(__vmins2(w4[e], hi2), lo2), bias2);
+          const float2 m = make_float2(__uint_as_float(prmt(c2, 0x4B000000u, 0x7610u)),
+                                       __uint_as_float(prmt(c2, 0x4B000000u, 0x7632u)));
+          const float2 cf = ptx::fadd2(m, make_float2(-kMagic, -kMagic));          // exact: clip(raw + icpt) as float
+          const float2 k3 = make_float2(0.001f, 0.001f);
+          const float2 q0 = ptx::fmul2(cf, k3);
+          y[e] = ptx::ffma2(ptx::ffma2(q0, make_float2(-1000.f, -1000.f), cf), k3, q0);   // == float(double(c) / 1000.0)
+        }
+        float* d = dst + cj[u] * KP + 8 * ck[u];
+        *reinterpret_cast<float4*>(d) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+        if (last_chunk_dup && ck[u] == kc_n - 1) d[8] = y[3].y;   // P(D) := P(D-1): no select in the march
+      }
+    }
+  };
+
+  __syncthreads();  // taps visible
+  // this warp's run of output depths [zbeg, zend), its aligned window of V2_KW input planes starting at kw0, the d taps
+  const int zbeg = grp * V2_OPT, zend = min(zbeg + V2_OPT, nd);
+  int kw0 = 0;
+  unsigned emask = 0;
+  if (zbeg < zend) {
+    kw0 = __float_as_int(s_dtap[zbeg].z) & ~3;
+    for (int z = zbeg; z < zend; ++z) emask |= 1u << (__float_as_int(s_dtap[z].z) - kw0);
+  }
+  const float4* dtp = s_dtap + zbeg;   // (w0, w1, k0, k1) of this run's outputs: broadcast loads in the march
+  const bool quad43 = (emask == 0x77u);   // 4:3 depth ratio: outputs on planes 0,1,2 and 4,5,6 of the window
+  int ld0 = -1, ld1 = -1, ld2 = -1;  // input row held by each slot
+  auto held = [&](int row) { const int m = row % 3; return (m == 0 ? ld0 : m == 1 ? ld1 : ld2) == row; };
+  auto hold = [&](int row) { const int m = row % 3; if (m == 0) ld0 = row; else if (m == 1) ld1 = row; else ld2 = row; };
+  uint4 pfa[V2_CPR];    // ONE prefetched row in registers; a second new row in the same step (1 in 15 at 512 -> 480) is
+                        // loaded and stored synchronously after it
+  {
+    const float4 ht = s_htap[0];
+    const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
+    row_load(h0, pfa);
+    row_store(h0, pfa); hold(h0);
+    if (h1 != h0) { row_load(h1, pfa); row_store(h1, pfa); hold(h1); }
+  }
+  __syncthreads();
+
+  const int woff_a = ja * KP + (kw0 - k_lo8), woff_b = jb * KP + (kw0 - k_lo8);
+  float2 wA[V2_KW / 2], wB[V2_KW / 2];           // w-interpolated planes (pairs along k) of two input rows
+  int rowA = -1, rowB = -1;
+  auto wrow = [&](int row, float2 (&w)[V2_KW / 2]) {   // planes beyond the run read slack / stale words: never used
+    const float* base = tile + (row % 3) * slot_elems;
+#pragma unroll
+    for (int q = 0; q < V2_KW / 4; ++q) {
+      const float4 a = lds128(base + woff_a + 4 * q), b = lds128(base + woff_b + 4 * q);
+      w[2 * q] = ptx::ffma2(make_float2(a.x, a.y), wa, ptx::fmul2(make_float2(b.x, b.y), wb));
+      w[2 * q + 1] = ptx::ffma2(make_float2(a.z, a.w), wa, ptx::fmul2(make_float2(b.z, b.w), wb));
+    }
+  };
+  const int oplane = p.tH * p.tW;                 // < 2^31 (host-checked): 32-bit element offsets, one IMAD.WIDE per store
+  float* out_t = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
+                 (ow_base + lane - p.ww0 + p.pw0);
+  bool synced_prev = true;   // the barrier after the initial row stores
+  for (int t = 0; t < n_oh; ++t) {
+    const int oh = oh_base + t;
+    const float4 ht = s_htap[t];
+    const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
+    int na = -1, nb = -1;
+    if (t + 1 < n_oh) {
+      const float4 hx = s_htap[t + 1];
+      const int g0 = __float_as_int(hx.x), g1 = __float_as_int(hx.w);
+      if (!held(g0)) na = g0;
+      if (g1 != g0 && !held(g1)) nb = g1;
+      if (na < 0) { na = nb; nb = -1; }
+      if (na >= 0) row_load(na, pfa);
+    }
+    if (zbeg < zend && ow_ok) {                   // lanes beyond the tile's columns only stage
+      float* optr = out_t + (long long)(oh - p.wh0 + p.ph0) * p.tW;
+      const float2 vh0 = make_float2(ht.y, ht.y), vh1 = make_float2(ht.z, ht.z);
+      auto march = [&](const float2 (&x)[V2_KW / 2], const float2 (&y)[V2_KW / 2]) {   // x: row h0, y: row h1
+        float P[V2_KW];
+#pragma unroll
+        for (int q = 0; q < V2_KW / 2; ++q) {
+          const float2 v = ptx::ffma2(x[q], vh0, ptx::fmul2(y[q], vh1));
+          P[2 * q] = v.x; P[2 * q + 1] = v.y;
+        }
+        if (quad43) {
+#pragma unroll
+          for (int i = 0; i < V2_OPT; ++i) {
+            const int kk = (i / 3) * 4 + (i % 3);
+            const float2 tp = *reinterpret_cast<const float2*>(dtp + i);
+            optr[i * oplane] = combine(P[kk], tp.x, P[kk + 1], tp.y);
+          }
+        } else {
+          const float4* wp = dtp;
+          float* op = optr;
+#pragma unroll
+          for (int kk = 0; kk < V2_KW - 1; ++kk) {
+            if (emask & (1u << kk)) {           // warp-uniform
+              const float2 tp = *reinterpret_cast<const float2*>(wp++);
+              *op = combine(P[kk], tp.x, P[kk + 1], tp.y);
+              op += oplane;
+            }
+          }
+        }
+      };
+      // the two register planes swap roles instead of being copied: whichever already holds h0 stays
+      if (rowA == h0) {
+        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
+        if (h1 != h0) march(wA, wB); else march(wA, wA);
+      } else if (rowB == h0) {
+        if (h1 != h0 && rowA != h1) { wrow(h1, wA); rowA = h1; }
+        if (h1 != h0) march(wB, wA); else march(wB, wB);
+      } else {
+        wrow(h0, wA); rowA = h0;
+        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
+        if (h1 != h0) march(wA, wB); else march(wA, wA);
+      }
+    }
+    if (na >= 0 || nb >= 0) {
+      // same slot-reuse argument as prep_hwn_i16_kernel: a new row whose slot is neither h0's nor h1's was last read in an
+      // earlier iteration that ended with the barrier below
+      const int s0 = h0 % 3, s1 = h1 % 3;
+      const bool clash = (na >= 0 && (na % 3 == s0 || na % 3 == s1)) || (nb >= 0 && (nb % 3 == s0 || nb % 3 == s1));
+      if (clash || !synced_prev) __syncthreads();
+      row_store(na, pfa); hold(na);
+      if (nb >= 0) { row_load(nb, pfa); row_store(nb, pfa); hold(nb); }
+      __syncthreads();
+      synced_prev = true;
+    } else {
+      synced_prev = false;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 fill_f32_kernel(float4* __restrict__ x, long long nvec, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
@@ -588,7 +816,76 @@ static int launch_fast_t(const PrepParams& p, dim3 grid, size_t smem, float* lut
 template <int NC>
 static int launch_fast_nc(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s);
 
+// v2 (prep_hwn_i16_v2_kernel): slope 1, integer intercept, every warp run of 6 output depths inside an aligned window of 8
+// input planes, the CTA's input columns within 32; returns 1 when it does not apply. CTCLIP_PREP_V2=0 disables it (A/B).
+static int launch_fast_v2(PrepParams p, int batch, cudaStream_t s) {
+  const char* e = getenv("CTCLIP_PREP_V2");
+  if (e != nullptr && e[0] == '0') return 1;
+  if (!p.in_is_i16 || p.sd != 1 || p.sw != p.D || (p.D % 8) || (p.sh % 8) || (p.sbatch % 8) ||
+      (reinterpret_cast<uintptr_t>(p.in) % 16) || p.D < p.oD)
+    return 1;
+  if (!(p.slope == 1.0 && p.intercept == floor(p.intercept) && fabs(p.intercept) <= 30000.0)) return 1;
+  constexpr int ftd = FG * V2_OPT;
+  // every warp run [b, b + 6): planes k0(first) & ~3 ... must cover k0(z) + 1 of every output of the run, each plane the
+  // lower tap of at most one output (depth down-sampling), k0(z) within the first 7 planes of the window
+  for (int b0 = p.wd0; b0 < p.wd0 + p.wdn; b0 += ftd)
+    for (int g = 0; g < FG; ++g) {
+      const int zb = b0 + g * V2_OPT;
+      const int ze = (zb + V2_OPT < b0 + ftd ? zb + V2_OPT : b0 + ftd) < p.wd0 + p.wdn ? (zb + V2_OPT < b0 + ftd ? zb + V2_OPT : b0 + ftd)
+                                                                                       : p.wd0 + p.wdn;
+      if (zb >= ze) continue;
+      int a0, a1, prev = -1;
+      taps_host(p.D, p.oD, zb, a0, a1);
+      const int w0 = a0 & ~3;
+      for (int z = zb; z < ze; ++z) {
+        taps_host(p.D, p.oD, z, a0, a1);
+        if (a0 <= prev || a0 + 1 > w0 + V2_KW - 1) return 1;
+        prev = a0;
+      }
+    }
+  int kn8 = 8;
+  for (int b = p.wd0; b < p.wd0 + p.wdn; b += ftd) {
+    const int e2 = (b + ftd < p.wd0 + p.wdn ? b + ftd : p.wd0 + p.wdn) - 1;
+    int a0, a1, b0, b1;
+    taps_host(p.D, p.oD, b, a0, a1);
+    taps_host(p.D, p.oD, e2, b0, b1);
+    int hi = b1 > b0 + 1 ? b1 : b0 + 1;
+    if (hi > p.D - 1) hi = p.D - 1;
+    const int n8 = ((hi - (a0 & ~7)) / 8 + 1) * 8;
+    if (n8 > kn8) kn8 = n8;
+  }
+  int fw = 32;
+  while (fw >= 16 && max_span(p.W, p.oW, p.ww0, p.wwn, fw) > 32) --fw;
+  if (fw < 16) return 1;
+  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, fw);
+  if ((kn8 / 8) * jn > V2_CPR * 256) return 1;
+  const int KP = kn8 + 4;
+  // a warp's window may start up to 3 planes before its first plane and always spans 8: stays inside [0, KP + slack)
+  const size_t smem = ((size_t)3 * jn * KP + 16) * sizeof(float) + (size_t)(ftd + FOH) * 16;
+  if (smem > 72 * 1024) return 1;
+  if ((long long)p.tH * p.tW * V2_OPT >= (1LL << 31)) return 1;
+  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + fw - 1) / fw)), (unsigned)batch);
+  const char* oe = getenv("CTCLIP_PREP_V2_OCC");   // resident CTAs per SM the kernel is compiled for (register cap): 2 | 3 | 4
+  const int occ = (oe != nullptr && oe[0] >= '2' && oe[0] <= '4') ? oe[0] - '0' : 3;
+  auto launch = [&](auto kern, size_t& configured) -> int {
+    if (smem > configured) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+      configured = smem;
+    }
+    kern<<<grid, 256, smem, s>>>(p, (int)p.intercept, fw, kn8, jn);
+    return ctclip::check_launch("prep_resample(hwn/i16 v2)");
+  };
+  static size_t conf2 = 0, conf3 = 0, conf4 = 0;
+  if (occ == 2) return launch(prep_hwn_i16_v2_kernel<2>, conf2);
+  if (occ == 4) return launch(prep_hwn_i16_v2_kernel<4>, conf4);
+  return launch(prep_hwn_i16_v2_kernel<3>, conf3);
+}
+
 static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s) {
+  {
+    const int rc = launch_fast_v2(p, batch, s);
+    if (rc <= 0) return rc;
+  }
   const char* e = getenv("CTCLIP_PREP_X2");   // 0: one output column per lane only (A/B and test hook)
   if (!(e != nullptr && e[0] == '0')) {
     const int rc = launch_fast_nc<2>(p, batch, lut_ws, lut_lo, lut_n, s);

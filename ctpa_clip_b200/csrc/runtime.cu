@@ -109,6 +109,7 @@ extern "C" long long ctclip_workspace_bytes(const char* op, const long long* dim
   }
   if (!strcmp(op, "bert_attn_bwd") && need(3)) return dims[0] * dims[1] * dims[2] * f;                        // (batch, heads, seq_len)
   if (!strcmp(op, "prep_resample") && need(0)) return 8192 * f;                                               // exact HU table
+  if (!strcmp(op, "sumsq") && need(0)) return 1024 * f;                                                       // per-block partials
   ctclip::fail(CTCLIP_E_SHAPE, "workspace_bytes: unknown op '%s' or wrong number of dims (%d)", op, ndims);
   return -1;
 }

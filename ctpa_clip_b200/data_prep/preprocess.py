@@ -27,13 +27,14 @@ def resize_array(array, current_spacing, target_spacing):
     return out[None].cpu().numpy()
 
 
-def preprocess_volumes(raw, slope, intercept, xy_spacing, z_spacing, target_spacing=TARGET_SPACING, target_shape=None):
+def preprocess_volumes(raw, slope, intercept, xy_spacing, z_spacing, target_spacing=TARGET_SPACING, target_shape=None,
+                       out=None):
     """process_file arithmetic for a batch of same-shape raw scans (preprocess_train.py:99-109).
     raw: int16 CUDA tensor [b, H, W, N] in NIfTI array order. Returns fp32 [b, D', H', W'] (or target_shape with the
     data.py:155-190 centre-crop / pad(-1) applied)."""
     b, H, W, N = raw.shape
     new_shape = resize_shape((N, H, W), (z_spacing, xy_spacing, xy_spacing), target_spacing)
-    return ops.prep_resample(raw, new_shape, hu=(slope, intercept), layout="hwn", target=target_shape)
+    return ops.prep_resample(raw, new_shape, hu=(slope, intercept), layout="hwn", target=target_shape, out=out)
 
 
 def to_training_volume(vol_dhw, target_shape=TARGET_SHAPE, pad_value=-1.0):

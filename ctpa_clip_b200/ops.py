@@ -462,8 +462,16 @@ def zero_shot_scores(i_hat, t_hat, tau, want_logits=False):
     return (prob, logits) if want_logits else prob
 
 
-def sumsq(g, out):
-    _call("ctclip_sumsq", _ptr(g), _ll(g.numel()), _ptr(out), _stream())
+_SUMSQ_WS = {}
+
+
+def sumsq(g, out, workspace=None):
+    """out[0] += sum(g^2), deterministic (no atomics); workspace: 1024 floats of scratch (one cached per device if None)"""
+    if workspace is None:
+        workspace = _SUMSQ_WS.get(g.device)
+        if workspace is None:
+            workspace = _SUMSQ_WS[g.device] = torch.empty(1024, device=g.device, dtype=torch.float32)
+    _call("ctclip_sumsq", _ptr(g), _ll(g.numel()), _ptr(out), _ptr(workspace), _stream())
 
 
 def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, step, norm_sq=None, max_norm=0.0, zero_grad=True, skipped=None):
@@ -476,8 +484,11 @@ PREP_PRE_OPS = {None: 0, "infer_window": 2, "affine": 3}
 PREP_POST_OPS = {None: 0, "clip_div": 1}
 
 
+_PREP_LUT = {}
+
+
 def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_value=-1.0, force_generic=False,
-                  pre_op=None, post_op=None):
+                  pre_op=None, post_op=None, out=None):
     """Trilinear resample (align_corners=False) of a batch of volumes on the GPU.
     layout "dhw": inp is [b, D, H, W] (fp32, or int16 with hu=(slope, intercept));
     layout "hwn": inp is [b, H, W, N] as stored in a NIfTI array (depth contiguous).
@@ -508,7 +519,10 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
     else:
         raise _lib.CtclipError("prep_resample: input must be int16 or float32")
     tgt = tuple(target) if target is not None else tuple(out_grid)
-    out = torch.empty((b, *tgt), device=inp.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((b, *tgt), device=inp.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != b * tgt[0] * tgt[1] * tgt[2] or not out.is_cuda:
+        raise _lib.CtclipError("prep_resample: out must be a contiguous fp32 CUDA tensor of the destination size")
     d.in_, d.out, d.batch = inp.data_ptr(), out.data_ptr(), b
     d.D, d.H, d.W = D, H, W
     d.stride_d, d.stride_h, d.stride_w, d.stride_batch = sd, sh, sw, D * H * W
@@ -517,7 +531,10 @@ def prep_resample(inp, out_grid, *, hu=None, layout="dhw", target=None, pad_valu
     d.pad_value = pad_value
     d.force_generic = int(force_generic)
     if inp.dtype == torch.int16:
-        lut = torch.empty(8192, device=inp.device, dtype=torch.float32)
+        key = (inp.device, torch.cuda.current_stream().cuda_stream)     # one table per stream: concurrent calls never share it
+        lut = _PREP_LUT.get(key)
+        if lut is None:
+            lut = _PREP_LUT[key] = torch.empty(8192, device=inp.device, dtype=torch.float32)
         d.lut_workspace = lut.data_ptr()
     _call("ctclip_prep_resample", C.byref(d), _stream())
     return out

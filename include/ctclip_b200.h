@@ -262,10 +262,11 @@ int ctclip_cpb_table_bwd(int h, int w, int dim, int heads, const float* W1, cons
 
 /* ------------------------------------------------------------------------------------------------
  * Trainer step (CTCLIPTrainer.py:347-353, optimizer.py:10-24) on flat fp32 arenas: sum of squares for the global-norm
- * clip, then fused clip + Adam + bf16 shadow refresh + gradient zeroing. A non-finite *norm_sq (NaN / Inf gradients, e.g. a
+ * clip (deterministic: fixed grid of per-block partials added in index order, no atomics — bit-identical on every
+ * data-parallel rank), then fused clip + Adam + bf16 shadow refresh + gradient zeroing. A non-finite *norm_sq (NaN / Inf gradients, e.g. a
  * data-parallel peer that timed out) SKIPS the whole update — parameters, moments and gradients stay as they are — and
  * increments *skipped (device int, may be NULL); the host raises on it (CTClipTrainStep.raise_if_skipped). */
-int ctclip_sumsq(const float* g, long long n, float* out, void* stream);
+int ctclip_sumsq(const float* g, long long n, float* out, float* workspace /* ctclip_workspace_bytes("sumsq") */, void* stream);
 int ctclip_adam_step(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, float lr, float beta1,
                      float beta2, float eps, int step, const float* norm_sq, float max_norm, int zero_grad, int* skipped,
                      void* stream);

@@ -111,6 +111,7 @@ def test_workspace_bytes_host_arithmetic():
     assert ws("cpb_table_bwd", 24, 24, 512) == 2 * R * 512 * 4
     assert ws("bert_attn_bwd", 8, 12, 512) == 8 * 12 * 512 * 4
     assert ws("prep_resample") == 8192 * 4
+    assert ws("sumsq") == 1024 * 4
     assert ws("no_such_op", 1) == -1
     assert "unknown op" in _lib.last_error()
 

@@ -335,6 +335,19 @@ def test_adam_with_clipping_matches_torch(ops):
     close(shadow, ref.detach(), 1e-2)
 
 
+def test_sumsq_is_deterministic_and_matches_torch(ops):
+    """the clip norm is a fixed-order two-level sum (no atomics): bit-identical from call to call — and therefore on every
+    data-parallel rank, whose all-reduced gradients are bit-identical — and equal to torch's within fp32 round-off"""
+    g = torch.randn(3_000_004, device="cuda")
+    outs = []
+    for _ in range(4):
+        o = torch.zeros(1, device="cuda")
+        ops.sumsq(g, o)
+        outs.append(o.clone())
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert abs(float(outs[0]) - float((g.double() ** 2).sum())) < 1e-5 * float(outs[0])
+
+
 # ------------------------------------------------------------------------------------------------ data_prep
 def test_resample_bit_exact_vs_golden_and_oracle(ops):
     G = np.load("tests/golden/resample.npz")
@@ -392,10 +405,13 @@ def test_resample_full_size_volume_bit_exact_and_properties(ops):
     ((30, 30, 128), (1.6, 4.0), None, (0.5, 12.5)),               # strong down-sampling on every axis, fractional HU
     ((200, 136, 320), (0.703125, 1.125), None, (1.0, -1024.0)),   # production ratios (512->480-like 15/16, 320->240), two column tiles
     ((96, 144, 160), (0.72, 1.2), (110, 90, 100), (1.0, 0.0)),    # ragged last column tile + crop / pad window
+    ((48, 100, 200), (0.703125, 1.125), None, (1.0, -1024.0)),    # 200 -> 150 planes: ragged last depth brick (150 = 3 x 48 + 6)
+    ((40, 64, 104), (0.703125, 1.125), (70, 30, 50), (1.0, 100.0)),  # 104 -> 78: partial warp runs + crop (d) / crop (h) / crop (w)
 ])
 def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spacing, target, hu, monkeypatch):
-    """the depth-marching int16 (H,W,N) kernels (two output columns per lane, and the one-column variant selected by
-    CTCLIP_PREP_X2=0) and the generic brick kernel must agree bit for bit with the C oracle"""
+    """the depth-marching int16 (H,W,N) kernels — v2 (128-bit shared-memory traffic, packed int16 / fp32x2 arithmetic; compiled
+    for 3, 2 and 4 resident CTAs per SM), v1 with two output columns per lane, v1 with one (CTCLIP_PREP_X2=0) — and the generic
+    brick kernel must agree bit for bit with the C oracle"""
     from ctpa_clip_b200.data_prep.preprocess import resize_shape
     rng = np.random.default_rng(11)
     raw = rng.integers(-2000, 3000, size=shape, dtype=np.int16)
@@ -405,11 +421,14 @@ def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spaci
     H, W, N = shape
     grid = resize_shape((N, H, W), (spacing[1], spacing[0], spacing[0]), (1.5, 0.75, 0.75))
     dev = torch.from_numpy(raw)[None].cuda()
-    for force, x2 in ((False, "1"), (False, "0"), (True, "1")):
+    for force, v2, x2 in ((False, "3", "1"), (False, "2", "1"), (False, "4", "1"), (False, "0", "1"), (False, "0", "0"),
+                          (True, "3", "1")):
+        monkeypatch.setenv("CTCLIP_PREP_V2", "0" if v2 == "0" else "1")
+        monkeypatch.setenv("CTCLIP_PREP_V2_OCC", v2)
         monkeypatch.setenv("CTCLIP_PREP_X2", x2)
         got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
         assert got.shape == want.shape
-        assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force} x2={x2}"
+        assert (got.view(np.int32) == want.view(np.int32)).all(), f"force_generic={force} v2={v2} x2={x2}"
 
 
 # ---- DataLoader conversions on the GPU ---------------------------------------------------------------
