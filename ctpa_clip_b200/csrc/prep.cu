@@ -483,33 +483,68 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-template <int MINB>
+// Input-row pipeline of a CTA (rows are consumed in increasing order without gaps — host-checked: H <= 2 oH):
+//   global --cp.async (LDGSTS), RING rows ahead--> raw ring --convert--> fp32 slots (4; row r lives in slot r & 3) --> wrow
+// Each thread copies, and later reads back, its OWN 16-byte chunks of the raw ring, so the ring needs neither a barrier nor
+// a swizzle; RING - 1 rows (3 x 4 KB per CTA, ~40 KB per SM) stay in flight — the register-prefetch version kept ~6 KB per
+// SM in flight against the ~11 KB that 2.0 TB/s of loads x ~800 ns ask for. With FOUR fp32 slots a new row never lands on a
+// slot the current output row still reads (rows h0, h0+1 in use; h0+2 and h0+3 go to the two other slots), so ONE barrier
+// per converted row — after the store — is enough. All slot / ring / global addresses advance incrementally.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  // .ca (through L1): the lanes of a warp that share a 32-byte sector are served by ONE sector fetch; the .cg (L1 bypass)
+  // form fetched a sector per lane — 2x the L2 -> SM traffic for 16-byte pieces (ncu: 32 sectors per request)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+
+constexpr int V2_RING = 4, V2_SLOTS = 4;
+
+// NC: output columns per lane (lane, lane + fw): the per-row bookkeeping (h taps, row pipeline, barrier, branches — more than
+// a third of the NC = 1 instruction stream) is shared by the column pair. MINB: resident CTAs per SM the register cap allows.
+// RING: true (default) = raw rows through the cp.async shared-memory ring, V2_RING rows ahead; false = raw rows prefetched
+// V2_PFD rows ahead in registers with LDG.128 (A/B arm: measured 4.7 ms against 3.05 ms per 32 scans — the register shifts of
+// the pipeline wait for the loads they move). CPR: 16-byte chunks per thread and row (1 | 2).
+constexpr int V2_PFD = 3;
+template <int NC, int MINB, bool RING, int CPR>
 __global__ void __launch_bounds__(256, MINB)
-prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max) {
-  extern __shared__ __align__(16) float tile[];  // [3][jn_max][KP] + slack | d taps [48] | h taps [FOH]
+prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max, int ring_chunks) {
+  extern __shared__ __align__(16) float tile[];  // [4][jn_max][KP] + slack | d taps [48] | h taps [FOH + 1] | raw ring [4][ring_chunks] x 16 B
   const int KP = kn8 + 4;
   const int slot_elems = jn_max * KP;
-  float4* s_dtap = reinterpret_cast<float4*>(tile + 3 * slot_elems + 16);
+  float4* s_dtap = reinterpret_cast<float4*>(tile + V2_SLOTS * slot_elems + 16);
   float4* s_htap = s_dtap + FG * V2_OPT;
+  uint4* s_ring = reinterpret_cast<uint4*>(s_htap + FOH + 1);
   const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
   constexpr int ftd = FG * V2_OPT;
-  const int n_wt = (p.wwn + fw - 1) / fw;
+  const int ctw = NC * fw;                       // output columns per CTA
+  const int n_wt = (p.wwn + ctw - 1) / ctw;
   const int oh_base = p.wh0 + blockIdx.x * FOH;
   const int n_oh = min(FOH, p.wh0 + p.whn - oh_base);
   const int od_base = p.wd0 + (blockIdx.y / n_wt) * ftd;
-  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * fw;
+  const int ow_base = p.ww0 + (blockIdx.y % n_wt) * ctw;
   const int nd = min(ftd, p.wd0 + p.wdn - od_base);
-  const int nw = min(fw, p.ww0 + p.wwn - ow_base);
+  const int nw = min(ctw, p.ww0 + p.wwn - ow_base);
   const short* in16 = reinterpret_cast<const short*>(p.in) + (long long)blockIdx.z * p.sbatch;
 
   if (tid < nd) {
     int a, b; float x, y;
     taps(p.D, p.oD, od_base + tid, a, b, x, y);
-    s_dtap[tid] = make_float4(x, y, __int_as_float(a), __int_as_float(b));   // (w0, w1, k0, k1): the weights are one LDS.64
+    s_dtap[tid] = make_float4(x, y, __int_as_float(a), __int_as_float(b));   // (w0, w1, k0, k1)
   }
-  if (tid < n_oh) {
+  if (tid <= n_oh) {   // one entry past the end (a copy of the last row): the loop prefetches the NEXT row's taps
     int a, b; float x, y;
-    taps(p.H, p.oH, oh_base + tid, a, b, x, y);
+    taps(p.H, p.oH, oh_base + min(tid, n_oh - 1), a, b, x, y);
     s_htap[tid] = make_float4(__int_as_float(a), x, y, __int_as_float(b));
   }
   int k_lo, k_hi, j_lo, j_hi, t0, t1; float f0, f1;
@@ -522,38 +557,78 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
   const int kc_n = (k_hi - k_lo8) / 8 + 1;   // 16-byte chunks per input column
   const int jn = j_hi - j_lo + 1;
   const int chunks = kc_n * jn;
-  // this thread's w taps
-  const bool ow_ok = lane < nw;
-  int ja, jb; float fa, fb;
-  taps(p.W, p.oW, ow_base + (ow_ok ? lane : nw - 1), ja, jb, fa, fb);
-  ja -= j_lo; jb -= j_lo;
-  const float2 wa = make_float2(fa, fa), wb = make_float2(fb, fb);
+  int h_first, h_last;
+  taps(p.H, p.oH, oh_base, h_first, t1, f0, f1);
+  taps(p.H, p.oH, oh_base + n_oh - 1, t0, h_last, f0, f1);
 
-  int cj[V2_CPR], ck[V2_CPR];
-  const short* cptr[V2_CPR];
-#pragma unroll
-  for (int u = 0; u < V2_CPR; ++u) {
-    const int idx = tid + u * 256;
-    ck[u] = idx / jn;
-    cj[u] = idx - ck[u] * jn;
-    cptr[u] = in16 + (long long)(j_lo + cj[u]) * p.sw + k_lo8 + 8 * ck[u];
-  }
+  // this thread's staging chunks: global address in the row being prefetched, byte offset inside an fp32 slot
   const bool last_chunk_dup = (k_lo8 + 8 * kc_n == p.D);   // the brick reaches the last plane: duplicate it at k = D
-  auto row_load = [&](int row, uint4 (&pf)[V2_CPR]) {
-    const long long ro = (long long)row * p.sh;
+  const short* gsrc[CPR];
+  uint32_t cdst[CPR];
+  bool cuse[CPR], cdup[CPR];
+  const uint32_t tile_u32 = ptx::smem_u32(tile);
+  // chunk -> (column cj, depth chunk ck). Lanes run along the CONTIGUOUS depth axis: with 8 chunks per column a quarter-warp
+  // takes chunks 0-3 (or 4-7) of two adjacent columns, so a warp's cp.async reads 4 columns x 128 contiguous bytes (16 full
+  // sectors; one lane per column read 16 of every 32-byte sector and cost 32 LSU wavefronts per instruction), and its two
+  // STS.128 per chunk fall into eight different bank groups (column pitch KP = 17 x 16 B).
 #pragma unroll
-    for (int u = 0; u < V2_CPR; ++u)
-      if (tid + u * 256 < chunks) pf[u] = __ldg(reinterpret_cast<const uint4*>(cptr[u] + ro));
+  for (int u = 0; u < CPR; ++u) {
+    const int idx = tid + u * 256;
+    int ck, cj;
+    if (kc_n == 8) {
+      const int r = idx & 15;
+      cj = 2 * (idx >> 4) + ((r >> 2) & 1);
+      ck = (r & 3) + 4 * (r >> 3);
+    } else {
+      cj = idx / kc_n;
+      ck = idx - cj * kc_n;
+    }
+    cuse[u] = cj < jn;
+    cdup[u] = cuse[u] && last_chunk_dup && ck == kc_n - 1;
+    gsrc[u] = in16 + (long long)h_first * p.sh + (long long)(j_lo + cj) * p.sw + k_lo8 + 8 * ck;
+    cdst[u] = tile_u32 + (uint32_t)(cj * KP + 8 * ck) * 4u;
+  }
+  const uint32_t slot_bytes = (uint32_t)slot_elems * 4u, ring_bytes = (uint32_t)ring_chunks * 16u;   // ring_bytes: 4096 or 8192
+  const uint32_t ring_mask = V2_RING * ring_bytes - 1;
+  const uint32_t ring_u32 = ptx::smem_u32(s_ring) + tid * 16;
+  uint32_t ring_wr = 0, ring_rd = 0;            // byte offsets of the slots of the next row to prefetch / to take
+  int pf_left = h_last - h_first + 1;           // rows still to prefetch
+  int conv_hi = h_first - 1;                    // highest row converted so far
+  uint32_t cv_slot = (uint32_t)(h_first & (V2_SLOTS - 1)) * slot_bytes;   // fp32 slot of row conv_hi + 1
+  uint4 pfr[RING ? 1 : V2_PFD][CPR];           // register pipeline: pfr[0] is the next row to convert
+  auto prefetch_next = [&]() {
+    if constexpr (RING) {
+      if (pf_left > 0) {
+#pragma unroll
+        for (int u = 0; u < CPR; ++u)
+          if (cuse[u]) { cp_async16(ring_u32 + ring_wr + u * 4096u, gsrc[u]); gsrc[u] += p.sh; }
+      }
+      cp_async_commit();                        // one group per row, empty beyond the brick's last row
+      ring_wr = (ring_wr + ring_bytes) & ring_mask;
+    } else {
+#pragma unroll
+      for (int d = 0; d + 1 < V2_PFD; ++d)
+#pragma unroll
+        for (int u = 0; u < CPR; ++u) pfr[d][u] = pfr[d + 1][u];
+      if (pf_left > 0) {
+#pragma unroll
+        for (int u = 0; u < CPR; ++u)
+          if (cuse[u]) { pfr[V2_PFD - 1][u] = __ldg(reinterpret_cast<const uint4*>(gsrc[u])); gsrc[u] += p.sh; }
+      }
+    }
+    --pf_left;
   };
   // raw clip bounds and bias as packed int16 pairs: c + 1024 = clamp(raw, -1000 - icpt, 1000 - icpt) + (icpt + 1024)
   const uint32_t lo2 = (uint32_t)(uint16_t)(short)(-1000 - icpt) * 0x10001u, hi2 = (uint32_t)(uint16_t)(short)(1000 - icpt) * 0x10001u;
   const uint32_t bias2 = (uint32_t)(uint16_t)(short)(icpt + 1024) * 0x10001u;
-  auto row_store = [&](int row, const uint4 (&pf)[V2_CPR]) {
-    float* dst = tile + (row % 3) * slot_elems;
+  auto convert_next = [&]() {                   // raw row conv_hi + 1: ring -> HU-normalised fp32 slot; refill its ring slot
+    if constexpr (RING) cp_async_wait<V2_RING - 1>();
 #pragma unroll
-    for (int u = 0; u < V2_CPR; ++u) {
-      if (tid + u * 256 < chunks) {
-        const uint32_t w4[4] = {pf[u].x, pf[u].y, pf[u].z, pf[u].w};
+    for (int u = 0; u < CPR; ++u) {
+      if (cuse[u]) {
+        uint4 pf;
+        if constexpr (RING) pf = lds128u(ring_u32 + ring_rd + u * 4096u); else pf = pfr[0][u];
+        const uint32_t w4[4] = {pf.x, pf.y, pf.z, pf.w};
         float2 y[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -565,125 +640,156 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
           const float2 q0 = ptx::fmul2(cf, k3);
           y[e] = ptx::ffma2(ptx::ffma2(q0, make_float2(-1000.f, -1000.f), cf), k3, q0);   // == float(double(c) / 1000.0)
         }
-        float* d = dst + cj[u] * KP + 8 * ck[u];
-        *reinterpret_cast<float4*>(d) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
-        *reinterpret_cast<float4*>(d + 4) = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
-        if (last_chunk_dup && ck[u] == kc_n - 1) d[8] = y[3].y;   // P(D) := P(D-1): no select in the march
+        const uint32_t d = cdst[u] + cv_slot;
+        sts128(d, y[0].x, y[0].y, y[1].x, y[1].y);
+        sts128(d + 16, y[2].x, y[2].y, y[3].x, y[3].y);
+        if (cdup[u]) sts32(d + 32, y[3].y);     // P(D) := P(D-1): no select in the march
       }
     }
+    ++conv_hi;
+    cv_slot += slot_bytes;
+    if (cv_slot == V2_SLOTS * slot_bytes) cv_slot = 0;
+    ring_rd = (ring_rd + ring_bytes) & ring_mask;
+    prefetch_next();
   };
 
   __syncthreads();  // taps visible
-  // this warp's run of output depths [zbeg, zend), its aligned window of V2_KW input planes starting at kw0, the d taps
+  // this warp's run of output depths [zbeg, zend), its aligned window of V2_KW input planes starting at kw0, its d taps
   const int zbeg = grp * V2_OPT, zend = min(zbeg + V2_OPT, nd);
   int kw0 = 0;
   unsigned emask = 0;
+  constexpr bool kTapsInRegs = (NC == 1 && MINB == 2);   // elsewhere registers are tight: the d taps are broadcast LDS.64 per output row
+  float2 dt[V2_OPT];
+#pragma unroll
+  for (int i = 0; i < V2_OPT; ++i) dt[i] = make_float2(0.f, 0.f);
   if (zbeg < zend) {
     kw0 = __float_as_int(s_dtap[zbeg].z) & ~3;
-    for (int z = zbeg; z < zend; ++z) emask |= 1u << (__float_as_int(s_dtap[z].z) - kw0);
+#pragma unroll
+    for (int i = 0; i < V2_OPT; ++i)
+      if (zbeg + i < zend) {
+        const float4 tp = s_dtap[zbeg + i];
+        emask |= 1u << (__float_as_int(tp.z) - kw0);
+        if (kTapsInRegs) dt[i] = make_float2(tp.x, tp.y);
+      }
   }
-  const float4* dtp = s_dtap + zbeg;   // (w0, w1, k0, k1) of this run's outputs: broadcast loads in the march
+  const float4* dtp = s_dtap + zbeg;
   const bool quad43 = (emask == 0x77u);   // 4:3 depth ratio: outputs on planes 0,1,2 and 4,5,6 of the window
-  int ld0 = -1, ld1 = -1, ld2 = -1;  // input row held by each slot
-  auto held = [&](int row) { const int m = row % 3; return (m == 0 ? ld0 : m == 1 ? ld1 : ld2) == row; };
-  auto hold = [&](int row) { const int m = row % 3; if (m == 0) ld0 = row; else if (m == 1) ld1 = row; else ld2 = row; };
-  uint4 pfa[V2_CPR];    // ONE prefetched row in registers; a second new row in the same step (1 in 15 at 512 -> 480) is
-                        // loaded and stored synchronously after it
+  // this thread's columns and their w taps
+  bool ow_ok[NC];
+  uint32_t woff_a[NC], woff_b[NC];
+  float2 wa[NC], wb[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = lane + c * fw;
+    ow_ok[c] = lane < fw && col < nw;
+    int ja, jb; float fa, fb;
+    taps(p.W, p.oW, ow_base + (ow_ok[c] ? col : nw - 1), ja, jb, fa, fb);
+    woff_a[c] = tile_u32 + (uint32_t)((ja - j_lo) * KP + (kw0 - k_lo8)) * 4u;
+    woff_b[c] = tile_u32 + (uint32_t)((jb - j_lo) * KP + (kw0 - k_lo8)) * 4u;
+    wa[c] = make_float2(fa, fa); wb[c] = make_float2(fb, fb);
+  }
+  const bool active = zbeg < zend && ow_ok[0];   // lanes beyond the tile's columns / warps beyond its depths only stage
+
+#pragma unroll
+  for (int r = 0; r < (RING ? V2_RING : V2_PFD); ++r) prefetch_next();
   {
-    const float4 ht = s_htap[0];
-    const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
-    row_load(h0, pfa);
-    row_store(h0, pfa); hold(h0);
-    if (h1 != h0) { row_load(h1, pfa); row_store(h1, pfa); hold(h1); }
+    const int h1_0 = __float_as_int(s_htap[0].w);
+    do { convert_next(); } while (conv_hi < h1_0);
   }
   __syncthreads();
 
-  const int woff_a = ja * KP + (kw0 - k_lo8), woff_b = jb * KP + (kw0 - k_lo8);
-  float2 wA[V2_KW / 2], wB[V2_KW / 2];           // w-interpolated planes (pairs along k) of two input rows
-  int rowA = -1, rowB = -1;
-  auto wrow = [&](int row, float2 (&w)[V2_KW / 2]) {   // planes beyond the run read slack / stale words: never used
-    const float* base = tile + (row % 3) * slot_elems;
+  // w-interpolated planes (pairs along k) of two input rows per column; X / Y swap roles from one output row to the next, so
+  // that the upper row of one output row is the lower row of the next without moving a register
+  float2 wX[NC][V2_KW / 2], wY[NC][V2_KW / 2];
+  int rowX = -1, rowY = -1;
+  auto wrow = [&](int row, float2 (&w)[NC][V2_KW / 2]) {   // planes beyond the run read slack / stale words: never used
+    const uint32_t so = (uint32_t)(row & (V2_SLOTS - 1)) * slot_bytes;
 #pragma unroll
-    for (int q = 0; q < V2_KW / 4; ++q) {
-      const float4 a = lds128(base + woff_a + 4 * q), b = lds128(base + woff_b + 4 * q);
-      w[2 * q] = ptx::ffma2(make_float2(a.x, a.y), wa, ptx::fmul2(make_float2(b.x, b.y), wb));
-      w[2 * q + 1] = ptx::ffma2(make_float2(a.z, a.w), wa, ptx::fmul2(make_float2(b.z, b.w), wb));
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+      for (int q = 0; q < V2_KW / 4; ++q) {
+        const uint4 a = lds128u(woff_a[c] + so + 16 * q), b = lds128u(woff_b[c] + so + 16 * q);
+        w[c][2 * q] = ptx::ffma2(make_float2(__uint_as_float(a.x), __uint_as_float(a.y)), wa[c],
+                                 ptx::fmul2(make_float2(__uint_as_float(b.x), __uint_as_float(b.y)), wb[c]));
+        w[c][2 * q + 1] = ptx::ffma2(make_float2(__uint_as_float(a.z), __uint_as_float(a.w)), wa[c],
+                                     ptx::fmul2(make_float2(__uint_as_float(b.z), __uint_as_float(b.w)), wb[c]));
+      }
     }
   };
-  const int oplane = p.tH * p.tW;                 // < 2^31 (host-checked): 32-bit element offsets, one IMAD.WIDE per store
-  float* out_t = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
-                 (ow_base + lane - p.ww0 + p.pw0);
-  bool synced_prev = true;   // the barrier after the initial row stores
-  for (int t = 0; t < n_oh; ++t) {
-    const int oh = oh_base + t;
-    const float4 ht = s_htap[t];
+  const int oplane = p.tH * p.tW;                 // < 2^31 / 6 (host-checked): 32-bit element offsets
+  float* optr = p.out + (long long)blockIdx.z * p.obatch + (long long)(od_base + zbeg - p.wd0 + p.pd0) * oplane +
+                (long long)(oh_base - p.wh0 + p.ph0) * p.tW + (ow_base + lane - p.ww0 + p.pw0);
+  float4 ht = s_htap[0];
+  // one output row: lo / hi are the register planes that hold (or receive) rows h0 / h1
+  auto out_row = [&](int t, float2 (&lo)[NC][V2_KW / 2], int& row_lo, float2 (&hi)[NC][V2_KW / 2], int& row_hi) {
     const int h0 = __float_as_int(ht.x), h1 = __float_as_int(ht.w);
-    int na = -1, nb = -1;
-    if (t + 1 < n_oh) {
-      const float4 hx = s_htap[t + 1];
-      const int g0 = __float_as_int(hx.x), g1 = __float_as_int(hx.w);
-      if (!held(g0)) na = g0;
-      if (g1 != g0 && !held(g1)) nb = g1;
-      if (na < 0) { na = nb; nb = -1; }
-      if (na >= 0) row_load(na, pfa);
-    }
-    if (zbeg < zend && ow_ok) {                   // lanes beyond the tile's columns only stage
-      float* optr = out_t + (long long)(oh - p.wh0 + p.ph0) * p.tW;
-      const float2 vh0 = make_float2(ht.y, ht.y), vh1 = make_float2(ht.z, ht.z);
-      auto march = [&](const float2 (&x)[V2_KW / 2], const float2 (&y)[V2_KW / 2]) {   // x: row h0, y: row h1
+    const float2 vh0 = make_float2(ht.y, ht.y), vh1 = make_float2(ht.z, ht.z);
+    ht = s_htap[t + 1];                           // next row's taps: the load is in flight during this row's arithmetic
+    if (active) {
+      if constexpr (!kTapsInRegs) {
+#pragma unroll
+        for (int i = 0; i < V2_OPT; ++i) dt[i] = *reinterpret_cast<const float2*>(dtp + i);   // entries past the run: unused
+      }
+      if (row_lo != h0) { wrow(h0, lo); row_lo = h0; }
+      if (row_hi != h1) {
+        if (h1 != h0) {
+          wrow(h1, hi);
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int q = 0; q < V2_KW / 2; ++q) hi[c][q] = lo[c][q];
+        }
+        row_hi = h1;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
         float P[V2_KW];
 #pragma unroll
         for (int q = 0; q < V2_KW / 2; ++q) {
-          const float2 v = ptx::ffma2(x[q], vh0, ptx::fmul2(y[q], vh1));
+          const float2 v = ptx::ffma2(lo[c][q], vh0, ptx::fmul2(hi[c][q], vh1));
           P[2 * q] = v.x; P[2 * q + 1] = v.y;
         }
-        if (quad43) {
+        if (c == 0 || ow_ok[c]) {
+          float* oc = optr + c * fw;
+          if (quad43) {
 #pragma unroll
-          for (int i = 0; i < V2_OPT; ++i) {
-            const int kk = (i / 3) * 4 + (i % 3);
-            const float2 tp = *reinterpret_cast<const float2*>(dtp + i);
-            optr[i * oplane] = combine(P[kk], tp.x, P[kk + 1], tp.y);
-          }
-        } else {
-          const float4* wp = dtp;
-          float* op = optr;
+            for (int i = 0; i < V2_OPT; ++i) {
+              const int kk = (i / 3) * 4 + (i % 3);
+              oc[i * oplane] = combine(P[kk], dt[i].x, P[kk + 1], dt[i].y);
+            }
+          } else {
+            int i = 0;
 #pragma unroll
-          for (int kk = 0; kk < V2_KW - 1; ++kk) {
-            if (emask & (1u << kk)) {           // warp-uniform
-              const float2 tp = *reinterpret_cast<const float2*>(wp++);
-              *op = combine(P[kk], tp.x, P[kk + 1], tp.y);
-              op += oplane;
+            for (int kk = 0; kk < V2_KW - 1; ++kk) {
+              if (emask & (1u << kk)) {           // warp-uniform; the i-th output of the run
+                float2 tp = dt[0];
+#pragma unroll
+                for (int s2 = 1; s2 < V2_OPT; ++s2)
+                  if (i == s2) tp = dt[s2];
+                oc[i * oplane] = combine(P[kk], tp.x, P[kk + 1], tp.y);
+                ++i;
+              }
             }
           }
         }
-      };
-      // the two register planes swap roles instead of being copied: whichever already holds h0 stays
-      if (rowA == h0) {
-        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
-        if (h1 != h0) march(wA, wB); else march(wA, wA);
-      } else if (rowB == h0) {
-        if (h1 != h0 && rowA != h1) { wrow(h1, wA); rowA = h1; }
-        if (h1 != h0) march(wB, wA); else march(wB, wB);
-      } else {
-        wrow(h0, wA); rowA = h0;
-        if (h1 != h0 && rowB != h1) { wrow(h1, wB); rowB = h1; }
-        if (h1 != h0) march(wA, wB); else march(wA, wA);
       }
+      optr += p.tW;
     }
-    if (na >= 0 || nb >= 0) {
-      // same slot-reuse argument as prep_hwn_i16_kernel: a new row whose slot is neither h0's nor h1's was last read in an
-      // earlier iteration that ended with the barrier below
-      const int s0 = h0 % 3, s1 = h1 % 3;
-      const bool clash = (na >= 0 && (na % 3 == s0 || na % 3 == s1)) || (nb >= 0 && (nb % 3 == s0 || nb % 3 == s1));
-      if (clash || !synced_prev) __syncthreads();
-      row_store(na, pfa); hold(na);
-      if (nb >= 0) { row_load(nb, pfa); row_store(nb, pfa); hold(nb); }
+    // rows of the next output row that are not converted yet (CTA-uniform): store, then ONE barrier
+    const int g1 = __float_as_int(ht.w);
+    if (g1 > conv_hi) {
+      do { convert_next(); } while (conv_hi < g1);
       __syncthreads();
-      synced_prev = true;
-    } else {
-      synced_prev = false;
     }
+  };
+  int t = 0;
+  for (; t + 1 < n_oh; t += 2) {
+    out_row(t, wX, rowX, wY, rowY);
+    out_row(t + 1, wY, rowY, wX, rowX);
   }
+  if (t < n_oh) out_row(t, wX, rowX, wY, rowY);
+  if constexpr (RING) cp_async_wait<0>();   // nothing of this CTA is in flight when it exits
 }
 
 __global__ void __launch_bounds__(256)
@@ -857,28 +963,42 @@ static int launch_fast_v2(PrepParams p, int batch, cudaStream_t s) {
   int fw = 32;
   while (fw >= 16 && max_span(p.W, p.oW, p.ww0, p.wwn, fw) > 32) --fw;
   if (fw < 16) return 1;
-  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, fw);
-  if ((kn8 / 8) * jn > V2_CPR * 256) return 1;
+  const char* ne = getenv("CTCLIP_PREP_V2_NC");    // output columns per lane: 1 (default) | 2 (A/B: at the 128-register cap it spills)
+  int nc = (ne != nullptr && ne[0] == '2') ? 2 : 1;
+  auto chunk_slots = [&](int cols) { return (kn8 / 8) * ((cols + 1) & ~1); };   // columns are dealt to the threads in pairs
+  if (nc == 2 && chunk_slots(max_span(p.W, p.oW, p.ww0, p.wwn, 2 * fw)) > V2_CPR * 256) nc = 1;
+  const int jn = max_span(p.W, p.oW, p.ww0, p.wwn, nc * fw);
+  if (chunk_slots(jn) > V2_CPR * 256) return 1;
   const int KP = kn8 + 4;
   // a warp's window may start up to 3 planes before its first plane and always spans 8: stays inside [0, KP + slack)
-  const size_t smem = ((size_t)3 * jn * KP + 16) * sizeof(float) + (size_t)(ftd + FOH) * 16;
-  if (smem > 72 * 1024) return 1;
+  // the row pipeline consumes input rows in increasing order without gaps: every row between the first and the last of a
+  // brick is a tap of some output row, which holds whenever the height is not down-sampled by more than 2
+  if ((long long)p.H > 2LL * p.oH) return 1;
+  const int ring_chunks = ((chunk_slots(jn) + 255) / 256) * 256;   // 16-byte chunks of one raw row, whole 256-thread passes
+  const char* re = getenv("CTCLIP_PREP_V2_RING");  // default: raw rows through the cp.async ring; 0: register prefetch (A/B)
+  const bool ring = !(re != nullptr && re[0] == '0');
+  const size_t smem = ((size_t)V2_SLOTS * jn * KP + 16) * sizeof(float) + (size_t)(ftd + FOH + 1) * 16 +
+                      (size_t)V2_RING * ring_chunks * 16;
+  if (smem > 112 * 1024) return 1;
   if ((long long)p.tH * p.tW * V2_OPT >= (1LL << 31)) return 1;
-  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + fw - 1) / fw)), (unsigned)batch);
-  const char* oe = getenv("CTCLIP_PREP_V2_OCC");   // resident CTAs per SM the kernel is compiled for (register cap): 2 | 3 | 4
-  const int occ = (oe != nullptr && oe[0] >= '2' && oe[0] <= '4') ? oe[0] - '0' : 3;
+  dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + nc * fw - 1) / (nc * fw))),
+            (unsigned)batch);
+  const char* oe = getenv("CTCLIP_PREP_V2_OCC");   // resident CTAs per SM the kernel is compiled for (register cap): 2 | 3
+  const int occ = (oe != nullptr && oe[0] == '3') ? 3 : 2;
   auto launch = [&](auto kern, size_t& configured) -> int {
     if (smem > configured) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
       configured = smem;
     }
-    kern<<<grid, 256, smem, s>>>(p, (int)p.intercept, fw, kn8, jn);
+    kern<<<grid, 256, smem, s>>>(p, (int)p.intercept, fw, kn8, jn, ring_chunks);
     return ctclip::check_launch("prep_resample(hwn/i16 v2)");
   };
-  static size_t conf2 = 0, conf3 = 0, conf4 = 0;
-  if (occ == 2) return launch(prep_hwn_i16_v2_kernel<2>, conf2);
-  if (occ == 4) return launch(prep_hwn_i16_v2_kernel<4>, conf4);
-  return launch(prep_hwn_i16_v2_kernel<3>, conf3);
+  static size_t conf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (nc == 2) return ring ? launch(prep_hwn_i16_v2_kernel<2, 2, true, 2>, conf[0]) : launch(prep_hwn_i16_v2_kernel<2, 2, false, 2>, conf[1]);
+  if (ring_chunks > 256)   // two chunks per thread and row
+    return ring ? launch(prep_hwn_i16_v2_kernel<1, 2, true, 2>, conf[2]) : launch(prep_hwn_i16_v2_kernel<1, 2, false, 2>, conf[3]);
+  if (ring) return launch(prep_hwn_i16_v2_kernel<1, 2, true, 1>, conf[4]);
+  return occ == 3 ? launch(prep_hwn_i16_v2_kernel<1, 3, false, 1>, conf[5]) : launch(prep_hwn_i16_v2_kernel<1, 2, false, 1>, conf[6]);
 }
 
 static int launch_fast(PrepParams p, int batch, float* lut_ws, int lut_lo, int lut_n, cudaStream_t s) {

@@ -409,9 +409,9 @@ def test_resample_full_size_volume_bit_exact_and_properties(ops):
     ((40, 64, 104), (0.703125, 1.125), (70, 30, 50), (1.0, 100.0)),  # 104 -> 78: partial warp runs + crop (d) / crop (h) / crop (w)
 ])
 def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spacing, target, hu, monkeypatch):
-    """the depth-marching int16 (H,W,N) kernels — v2 (128-bit shared-memory traffic, packed int16 / fp32x2 arithmetic; compiled
-    for 3, 2 and 4 resident CTAs per SM), v1 with two output columns per lane, v1 with one (CTCLIP_PREP_X2=0) — and the generic
-    brick kernel must agree bit for bit with the C oracle"""
+    """the depth-marching int16 (H,W,N) kernels — v2 (cp.async row ring, 128-bit shared-memory traffic, packed int16 / fp32x2
+    arithmetic; two / one output columns per lane, 2 / 3 CTAs per SM), v1 with two output columns per lane, v1 with one
+    (CTCLIP_PREP_X2=0) — and the generic brick kernel must agree bit for bit with the C oracle"""
     from ctpa_clip_b200.data_prep.preprocess import resize_shape
     rng = np.random.default_rng(11)
     raw = rng.integers(-2000, 3000, size=shape, dtype=np.int16)
@@ -421,10 +421,13 @@ def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spaci
     H, W, N = shape
     grid = resize_shape((N, H, W), (spacing[1], spacing[0], spacing[0]), (1.5, 0.75, 0.75))
     dev = torch.from_numpy(raw)[None].cuda()
-    for force, v2, x2 in ((False, "3", "1"), (False, "2", "1"), (False, "4", "1"), (False, "0", "1"), (False, "0", "0"),
-                          (True, "3", "1")):
+    # v2 = "<columns per lane><CTAs per SM><raw rows through the cp.async ring>" or "0" (v1 kernels)
+    for force, v2, x2 in ((False, "120", "1"), (False, "121", "1"), (False, "130", "1"), (False, "220", "1"), (False, "221", "1"),
+                          (False, "0", "1"), (False, "0", "0"), (True, "120", "1")):
         monkeypatch.setenv("CTCLIP_PREP_V2", "0" if v2 == "0" else "1")
-        monkeypatch.setenv("CTCLIP_PREP_V2_OCC", v2)
+        monkeypatch.setenv("CTCLIP_PREP_V2_NC", v2[0])
+        monkeypatch.setenv("CTCLIP_PREP_V2_OCC", v2[1:2] or "2")
+        monkeypatch.setenv("CTCLIP_PREP_V2_RING", v2[2:3] or "0")
         monkeypatch.setenv("CTCLIP_PREP_X2", x2)
         got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
         assert got.shape == want.shape
