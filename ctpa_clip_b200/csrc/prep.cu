@@ -512,13 +512,17 @@ constexpr int V2_RING = 4, V2_SLOTS = 4;
 
 // NC: output columns per lane (lane, lane + fw): the per-row bookkeeping (h taps, row pipeline, barrier, branches — more than
 // a third of the NC = 1 instruction stream) is shared by the column pair. MINB: resident CTAs per SM the register cap allows.
-// RING: true (default) = raw rows through the cp.async shared-memory ring, V2_RING rows ahead; false = raw rows prefetched
-// V2_PFD rows ahead in registers with LDG.128 (A/B arm: measured 4.7 ms against 3.05 ms per 32 scans — the register shifts of
-// the pipeline wait for the loads they move). CPR: 16-byte chunks per thread and row (1 | 2).
-constexpr int V2_PFD = 3;
-template <int NC, int MINB, bool RING, int CPR>
+// TMA: true (CTCLIP_PREP_V2_TMA=1, when the brick's raw rows fit a 64-plane x 32 * NC-column box) = ONE thread fetches each raw row with a
+// 4-D `cp.async.bulk.tensor` (SWIZZLE_128B, one 128-byte line per input column) into the ring, completion on an mbarrier per
+// slot, refill right after the CTA barrier that follows the row's conversion; false = every thread copies its own 16-byte
+// chunks with cp.async (LDGSTS). ncu on the LDGSTS ring: ~18 LSU wavefronts per 512-byte warp request (one per returning
+// sector) in a kernel whose LSU data pipe is its busiest unit — TMA writes shared memory without the LSU.
+// A register-prefetch pipeline (LDG.128 three rows ahead) was measured too: 4.7 ms against 3.05 ms per 32 scans (the register
+// shifts of the pipeline wait for the loads they move). CPR: 16-byte chunks per thread and row (1 | 2).
+template <int NC, int MINB, bool TMA, int CPR>
 __global__ void __launch_bounds__(256, MINB)
-prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max, int ring_chunks) {
+prep_hwn_i16_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PrepParams p, int icpt, int fw, int kn8, int jn_max,
+                       int ring_chunks) {
   extern __shared__ __align__(16) float tile[];  // [4][jn_max][KP] + slack | d taps [48] | h taps [FOH + 1] | raw ring [4][ring_chunks] x 16 B
   const int KP = kn8 + 4;
   const int slot_elems = jn_max * KP;
@@ -564,7 +568,7 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
   // this thread's staging chunks: global address in the row being prefetched, byte offset inside an fp32 slot
   const bool last_chunk_dup = (k_lo8 + 8 * kc_n == p.D);   // the brick reaches the last plane: duplicate it at k = D
   const short* gsrc[CPR];
-  uint32_t cdst[CPR];
+  uint32_t cdst[CPR], csrc[CPR];
   bool cuse[CPR], cdup[CPR];
   const uint32_t tile_u32 = ptx::smem_u32(tile);
   // chunk -> (column cj, depth chunk ck). Lanes run along the CONTIGUOUS depth axis: with 8 chunks per column a quarter-warp
@@ -587,47 +591,49 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
     cdup[u] = cuse[u] && last_chunk_dup && ck == kc_n - 1;
     gsrc[u] = in16 + (long long)h_first * p.sh + (long long)(j_lo + cj) * p.sw + k_lo8 + 8 * ck;
     cdst[u] = tile_u32 + (uint32_t)(cj * KP + 8 * ck) * 4u;
+    csrc[u] = TMA ? (uint32_t)(cj * 128 + ((ck ^ (cj & 7)) << 4)) : (uint32_t)u * 4096u;   // chunk offset inside a ring slot
   }
   const uint32_t slot_bytes = (uint32_t)slot_elems * 4u, ring_bytes = (uint32_t)ring_chunks * 16u;   // ring_bytes: 4096 or 8192
   const uint32_t ring_mask = V2_RING * ring_bytes - 1;
-  const uint32_t ring_u32 = ptx::smem_u32(s_ring) + tid * 16;
+  // TMA ring: 1024-byte aligned (128-byte swizzle atom), row of column cj at cj * 128, chunk ck at ((ck ^ (cj & 7)) << 4)
+  const uint32_t ring_al = (ptx::smem_u32(s_ring) + 1023u) & ~1023u;
+  uint8_t* ring_ptr = reinterpret_cast<uint8_t*>(tile) + (ring_al - ptx::smem_u32(tile));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring_ptr + V2_RING * ring_bytes);
+  const uint32_t ring_u32 = TMA ? ring_al : ptx::smem_u32(s_ring) + tid * 16;
   uint32_t ring_wr = 0, ring_rd = 0;            // byte offsets of the slots of the next row to prefetch / to take
-  int pf_left = h_last - h_first + 1;           // rows still to prefetch
+  int pf_left = h_last - h_first + 1;           // (cp.async) rows still to prefetch
+  int pf_row = h_first;                         // (TMA) next row to fetch
+  uint32_t rd_parity = 0;                       // (TMA) phase of the slot being taken
   int conv_hi = h_first - 1;                    // highest row converted so far
   uint32_t cv_slot = (uint32_t)(h_first & (V2_SLOTS - 1)) * slot_bytes;   // fp32 slot of row conv_hi + 1
-  uint4 pfr[RING ? 1 : V2_PFD][CPR];           // register pipeline: pfr[0] is the next row to convert
-  auto prefetch_next = [&]() {
-    if constexpr (RING) {
-      if (pf_left > 0) {
+  auto prefetch_next = [&]() {                  // cp.async flavour: every thread, right after it consumed its chunks of a row
+    if (pf_left > 0) {
 #pragma unroll
-        for (int u = 0; u < CPR; ++u)
-          if (cuse[u]) { cp_async16(ring_u32 + ring_wr + u * 4096u, gsrc[u]); gsrc[u] += p.sh; }
-      }
-      cp_async_commit();                        // one group per row, empty beyond the brick's last row
-      ring_wr = (ring_wr + ring_bytes) & ring_mask;
-    } else {
-#pragma unroll
-      for (int d = 0; d + 1 < V2_PFD; ++d)
-#pragma unroll
-        for (int u = 0; u < CPR; ++u) pfr[d][u] = pfr[d + 1][u];
-      if (pf_left > 0) {
-#pragma unroll
-        for (int u = 0; u < CPR; ++u)
-          if (cuse[u]) { pfr[V2_PFD - 1][u] = __ldg(reinterpret_cast<const uint4*>(gsrc[u])); gsrc[u] += p.sh; }
-      }
+      for (int u = 0; u < CPR; ++u)
+        if (cuse[u]) { cp_async16(ring_u32 + ring_wr + csrc[u], gsrc[u]); gsrc[u] += p.sh; }
     }
+    cp_async_commit();                          // one group per row, empty beyond the brick's last row
+    ring_wr = (ring_wr + ring_bytes) & ring_mask;
     --pf_left;
+  };
+  auto tma_refill = [&]() {                     // TMA flavour: thread 0, after the barrier that ends the reads of the freed slots
+    while (pf_row <= h_last && pf_row <= conv_hi + V2_RING) {
+      uint64_t* bar = full_bar + (ring_wr / ring_bytes);
+      ptx::mbar_expect_tx(bar, ring_bytes);
+      ptx::tma_load_4d(ring_ptr + ring_wr, &tmap, bar, k_lo8, j_lo, pf_row, (int)blockIdx.z);
+      ring_wr = (ring_wr + ring_bytes) & ring_mask;
+      ++pf_row;
+    }
   };
   // raw clip bounds and bias as packed int16 pairs: c + 1024 = clamp(raw, -1000 - icpt, 1000 - icpt) + (icpt + 1024)
   const uint32_t lo2 = (uint32_t)(uint16_t)(short)(-1000 - icpt) * 0x10001u, hi2 = (uint32_t)(uint16_t)(short)(1000 - icpt) * 0x10001u;
   const uint32_t bias2 = (uint32_t)(uint16_t)(short)(icpt + 1024) * 0x10001u;
   auto convert_next = [&]() {                   // raw row conv_hi + 1: ring -> HU-normalised fp32 slot; refill its ring slot
-    if constexpr (RING) cp_async_wait<V2_RING - 1>();
+    if constexpr (TMA) ptx::mbar_wait(full_bar + (ring_rd / ring_bytes), rd_parity); else cp_async_wait<V2_RING - 1>();
 #pragma unroll
     for (int u = 0; u < CPR; ++u) {
       if (cuse[u]) {
-        uint4 pf;
-        if constexpr (RING) pf = lds128u(ring_u32 + ring_rd + u * 4096u); else pf = pfr[0][u];
+        const uint4 pf = lds128u(ring_u32 + ring_rd + csrc[u]);
         const uint32_t w4[4] = {pf.x, pf.y, pf.z, pf.w};
         float2 y[4];
 #pragma unroll
@@ -650,10 +656,18 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
     cv_slot += slot_bytes;
     if (cv_slot == V2_SLOTS * slot_bytes) cv_slot = 0;
     ring_rd = (ring_rd + ring_bytes) & ring_mask;
-    prefetch_next();
+    if constexpr (TMA) { if (ring_rd == 0) rd_parity ^= 1u; } else { prefetch_next(); }
   };
 
-  __syncthreads();  // taps visible
+  if constexpr (TMA) {
+    if (tid == 0) {
+      ptx::prefetch_tmap(&tmap);
+#pragma unroll
+      for (int r = 0; r < V2_RING; ++r) ptx::mbar_init(full_bar + r, 1);
+      ptx::fence_barrier_init();
+    }
+  }
+  __syncthreads();  // taps (and the ring barriers) visible
   // this warp's run of output depths [zbeg, zend), its aligned window of V2_KW input planes starting at kw0, its d taps
   const int zbeg = grp * V2_OPT, zend = min(zbeg + V2_OPT, nd);
   int kw0 = 0;
@@ -690,13 +704,18 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
   }
   const bool active = zbeg < zend && ow_ok[0];   // lanes beyond the tile's columns / warps beyond its depths only stage
 
+  if constexpr (TMA) {
+    if (tid == 0) tma_refill();                 // rows h_first .. h_first + 3 (barriers were initialised before the tap barrier)
+  } else {
 #pragma unroll
-  for (int r = 0; r < (RING ? V2_RING : V2_PFD); ++r) prefetch_next();
+    for (int r = 0; r < V2_RING; ++r) prefetch_next();
+  }
   {
     const int h1_0 = __float_as_int(s_htap[0].w);
     do { convert_next(); } while (conv_hi < h1_0);
   }
   __syncthreads();
+  if constexpr (TMA) { if (tid == 0) tma_refill(); }
 
   // w-interpolated planes (pairs along k) of two input rows per column; X / Y swap roles from one output row to the next, so
   // that the upper row of one output row is the lower row of the next without moving a register
@@ -781,6 +800,7 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
     if (g1 > conv_hi) {
       do { convert_next(); } while (conv_hi < g1);
       __syncthreads();
+      if constexpr (TMA) { if (tid == 0) tma_refill(); }   // the slots just read are free: fetch the rows 4 ahead
     }
   };
   int t = 0;
@@ -789,7 +809,7 @@ prep_hwn_i16_v2_kernel(const PrepParams p, int icpt, int fw, int kn8, int jn_max
     out_row(t + 1, wY, rowY, wX, rowX);
   }
   if (t < n_oh) out_row(t, wX, rowX, wY, rowY);
-  if constexpr (RING) cp_async_wait<0>();   // nothing of this CTA is in flight when it exits
+  if constexpr (!TMA) cp_async_wait<0>();   // nothing of this CTA is in flight when it exits (TMA: every fetched row was awaited)
 }
 
 __global__ void __launch_bounds__(256)
@@ -975,10 +995,24 @@ static int launch_fast_v2(PrepParams p, int batch, cudaStream_t s) {
   // brick is a tap of some output row, which holds whenever the height is not down-sampled by more than 2
   if ((long long)p.H > 2LL * p.oH) return 1;
   const int ring_chunks = ((chunk_slots(jn) + 255) / 256) * 256;   // 16-byte chunks of one raw row, whole 256-thread passes
-  const char* re = getenv("CTCLIP_PREP_V2_RING");  // default: raw rows through the cp.async ring; 0: register prefetch (A/B)
-  const bool ring = !(re != nullptr && re[0] == '0');
+  // raw rows by cp.async (default) or, CTCLIP_PREP_V2_TMA=1, by one TMA box per row when the brick fits it. Measured on the
+  // production shape (32 scans): cp.async 3.05-3.25 ms, TMA 3.45 ms — with the LSU no longer the limiter (dependency
+  // latency at 16 warps per SM is), the single refilling thread behind the barrier costs more than the LSU wavefronts it saves
+  const char* te = getenv("CTCLIP_PREP_V2_TMA");
+  const bool tma = (te != nullptr && te[0] == '1') && kn8 <= 64 && jn <= 32 * nc && ring_chunks * 16 == 128 * 32 * nc;
   const size_t smem = ((size_t)V2_SLOTS * jn * KP + 16) * sizeof(float) + (size_t)(ftd + FOH + 1) * 16 +
-                      (size_t)V2_RING * ring_chunks * 16;
+                      (size_t)V2_RING * ring_chunks * 16 + (tma ? 1024 + 64 : 0);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (tma) {   // raw scans as a 4-D tensor (depth, width, height, batch) of 16-bit words; box = 64 planes x 32 * nc columns of ONE row
+    const cuuint64_t dims[4] = {(cuuint64_t)p.D, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.sw * 2, (cuuint64_t)p.sh * 2, (cuuint64_t)p.sbatch * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(32 * nc), 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (ctclip::encode_tmap(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(p.in), dims, strides, box, estr,
+                            CU_TENSOR_MAP_SWIZZLE_128B) != CTCLIP_OK)
+      return 1;
+  }
   if (smem > 112 * 1024) return 1;
   if ((long long)p.tH * p.tW * V2_OPT >= (1LL << 31)) return 1;
   dim3 grid((unsigned)((p.whn + FOH - 1) / FOH), (unsigned)(((p.wdn + ftd - 1) / ftd) * ((p.wwn + nc * fw - 1) / (nc * fw))),
@@ -990,14 +1024,13 @@ static int launch_fast_v2(PrepParams p, int batch, cudaStream_t s) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
       configured = smem;
     }
-    kern<<<grid, 256, smem, s>>>(p, (int)p.intercept, fw, kn8, jn, ring_chunks);
+    kern<<<grid, 256, smem, s>>>(tmap, p, (int)p.intercept, fw, kn8, jn, ring_chunks);
     return ctclip::check_launch("prep_resample(hwn/i16 v2)");
   };
   static size_t conf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (nc == 2) return ring ? launch(prep_hwn_i16_v2_kernel<2, 2, true, 2>, conf[0]) : launch(prep_hwn_i16_v2_kernel<2, 2, false, 2>, conf[1]);
-  if (ring_chunks > 256)   // two chunks per thread and row
-    return ring ? launch(prep_hwn_i16_v2_kernel<1, 2, true, 2>, conf[2]) : launch(prep_hwn_i16_v2_kernel<1, 2, false, 2>, conf[3]);
-  if (ring) return launch(prep_hwn_i16_v2_kernel<1, 2, true, 1>, conf[4]);
+  if (nc == 2) return tma ? launch(prep_hwn_i16_v2_kernel<2, 2, true, 2>, conf[0]) : launch(prep_hwn_i16_v2_kernel<2, 2, false, 2>, conf[1]);
+  if (ring_chunks > 256) return launch(prep_hwn_i16_v2_kernel<1, 2, false, 2>, conf[2]);   // two chunks per thread and row
+  if (tma) return occ == 3 ? launch(prep_hwn_i16_v2_kernel<1, 3, true, 1>, conf[3]) : launch(prep_hwn_i16_v2_kernel<1, 2, true, 1>, conf[4]);
   return occ == 3 ? launch(prep_hwn_i16_v2_kernel<1, 3, false, 1>, conf[5]) : launch(prep_hwn_i16_v2_kernel<1, 2, false, 1>, conf[6]);
 }
 

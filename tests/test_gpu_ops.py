@@ -421,13 +421,13 @@ def test_resample_marching_fast_path_equals_generic_and_oracle(ops, shape, spaci
     H, W, N = shape
     grid = resize_shape((N, H, W), (spacing[1], spacing[0], spacing[0]), (1.5, 0.75, 0.75))
     dev = torch.from_numpy(raw)[None].cuda()
-    # v2 = "<columns per lane><CTAs per SM><raw rows through the cp.async ring>" or "0" (v1 kernels)
-    for force, v2, x2 in ((False, "120", "1"), (False, "121", "1"), (False, "130", "1"), (False, "220", "1"), (False, "221", "1"),
-                          (False, "0", "1"), (False, "0", "0"), (True, "120", "1")):
+    # v2 = "<columns per lane><CTAs per SM><raw rows by TMA (1) or cp.async (0)>" or "0" (v1 kernels)
+    for force, v2, x2 in ((False, "121", "1"), (False, "120", "1"), (False, "131", "1"), (False, "221", "1"), (False, "220", "1"),
+                          (False, "0", "1"), (False, "0", "0"), (True, "121", "1")):
         monkeypatch.setenv("CTCLIP_PREP_V2", "0" if v2 == "0" else "1")
         monkeypatch.setenv("CTCLIP_PREP_V2_NC", v2[0])
         monkeypatch.setenv("CTCLIP_PREP_V2_OCC", v2[1:2] or "2")
-        monkeypatch.setenv("CTCLIP_PREP_V2_RING", v2[2:3] or "0")
+        monkeypatch.setenv("CTCLIP_PREP_V2_TMA", v2[2:3] or "0")
         monkeypatch.setenv("CTCLIP_PREP_X2", x2)
         got = ops.prep_resample(dev, grid, hu=hu, layout="hwn", target=target, force_generic=force)[0].cpu().numpy()
         assert got.shape == want.shape

@@ -20,8 +20,8 @@ base = torch.randint(-1024, 3071, (4, 512, 512, 320), generator=g, dtype=torch.i
 raw = base.repeat((n + 3) // 4, 1, 1, 1)[:n].contiguous()
 out = torch.empty((n, 240, 480, 480), device="cuda")
 BYTES = 512 * 512 * 320 * 2 + 240 * 480 * 480 * 4
-variants = [(f"v2 nc{c} occ{o} ring{r}", {"CTCLIP_PREP_V2": "1", "CTCLIP_PREP_V2_NC": c, "CTCLIP_PREP_V2_OCC": o, "CTCLIP_PREP_V2_RING": r})
-            for c, o, r in (("1", "2", "1"), ("1", "2", "0"), ("2", "2", "1"))] + [
+variants = [(f"v2 nc{c} occ{o} tma{t}", {"CTCLIP_PREP_V2": "1", "CTCLIP_PREP_V2_NC": c, "CTCLIP_PREP_V2_OCC": o, "CTCLIP_PREP_V2_TMA": t})
+            for c, o, t in (("1", "2", "1"), ("1", "2", "0"), ("1", "3", "1"), ("2", "2", "1"))] + [
     ("v1 x2", {"CTCLIP_PREP_V2": "0", "CTCLIP_PREP_X2": "1"})]
 ref = None
 for name, env in variants:
