@@ -371,7 +371,7 @@ def run_ours(args):
                             f"scans to 240x480x480 fp32 ({nb} per GPU), inputs resident (12.4 GB per 32 scans >> L2)",
                 "ms": prep_ms, "volumes_per_s": nb * world / (prep_ms * 1e-3), "GBps_per_gpu": gbs, "peak_GBps": hbm_peak,
                 "frac": gbs / hbm_peak, "algorithmic_bytes_per_volume": PREP_BYTES_PER_VOLUME,
-                "out_shape": list(out.shape), "kernel": "prep_hwn_i16_kernel (bit-exact vs the C oracle / the reference's resize_array)"}
+                "out_shape": list(out.shape), "kernel": "prep_hwn_i16_v2_kernel (bit-exact with the reference's resize_array; tests/test_gpu_ops.py)"}
         del raw_d, out
         torch.cuda.empty_cache()
 

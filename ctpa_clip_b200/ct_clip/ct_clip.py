@@ -76,10 +76,13 @@ class LinearFunction(torch.autograd.Function):
                     # the 294912 -> 512 projection) and form the global-batch gradient locally, instead of all-reducing
                     # the N x K fp32 product (604 MB) — SURVEY 7.2-6 / 8(e). Every rank ends with the identical sum.
                     ws = dist.get_world_size()
-                    dy_all = torch.empty((ws * dyb.shape[0], dyb.shape[1]), device=dyb.device, dtype=dyb.dtype)
-                    x_all = torch.empty((ws * xb.shape[0], xb.shape[1]), device=xb.device, dtype=xb.dtype)
-                    dist.all_gather_into_tensor(dy_all, dyb.contiguous())
-                    dist.all_gather_into_tensor(x_all, xb.contiguous())
+                    bl, n, kk = dyb.shape[0], dyb.shape[1], xb.shape[1]
+                    packed = torch.empty((bl, n + kk), device=dyb.device, dtype=dyb.dtype)   # [dL | E] rows: ONE all-gather
+                    packed[:, :n] = dyb
+                    packed[:, n:] = xb
+                    gathered = torch.empty((ws * bl, n + kk), device=dyb.device, dtype=dyb.dtype)
+                    dist.all_gather_into_tensor(gathered, packed)
+                    dy_all, x_all = gathered[:, :n], gathered[:, n:]        # strided views: the GEMM takes a row pitch
                     ops.gemm(dy_all, x_all, a_t=True, b_t=True, out=w.grad, resid=w.grad)
                     if ctx.ready is not None:
                         ctx.ready([w], reduced=True)     # already the sum over ranks: no all-reduce for this span

@@ -146,7 +146,9 @@ class CTViT(nn.Module):
         self.last_indices = None
         self.last_pooled_bf16 = None
         self.force_indices = None
-        self.ema_reduce = None  # optional callable(bins, embed_sum) -> None, e.g. an NVLink all-reduce across ranks
+        self.ema_reduce = None  # optional callable(bins, embed_sum) -> work handle | None: cross-rank sum (async all-reduce)
+        self.grad_ready = None  # optional callable(list of parameters): their .grad is final (direct-gradient mode, per layer)
+        self._ema_pending = None
 
     # ---------------------------------------------------------------- reference surface
     @property
@@ -186,6 +188,7 @@ class CTViT(nn.Module):
         return {n: p.shape for n, p in self.named_parameters()}
 
     def weights(self) -> engine.EncoderWeights:
+        self.finish_ema()
         key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
             (b.data_ptr(), b._version) for b in self.buffers())
         if self._wcache is None or key != self._wkey:
@@ -197,11 +200,29 @@ class CTViT(nn.Module):
     def invalidate_weights(self):
         self._wcache = None
 
+    def finish_ema(self):
+        """apply a pending (cross-rank reduced) EMA codebook update; no-op when nothing is pending"""
+        pending = self.__dict__.get("_ema_pending")
+        if pending is None:
+            return
+        self._ema_pending = None
+        work, bins, esum = pending
+        if work is not None:
+            work.wait()
+        cb = self.vq._codebook
+        ops.vq_ema_update(cb.embed[0], cb.cluster_size[0], bins, esum, self.vq.decay)
+        self._wcache = None  # the codebook operands are derived caches
+
     def _ema_update(self, tokens, inv, idx):
         cb = self.vq._codebook
+        self.finish_ema()
         bins, esum = ops.vq_ema(cb.embed[0], cb.cluster_size[0], tokens, inv, idx, self.vq.decay)
         if self.ema_reduce is not None:
-            self.ema_reduce(bins, esum)
+            # data parallel: the statistics are summed across ranks ASYNCHRONOUSLY (the callable returns a work handle); the
+            # codebook itself is only needed by the next forward, so the update is applied by finish_ema() — which the trainer
+            # calls with the gradient reduction — instead of stalling this forward on a 16.8 MB all-reduce
+            self._ema_pending = (self.ema_reduce(bins, esum), bins, esum)
+            return
         ops.vq_ema_update(cb.embed[0], cb.cluster_size[0], bins, esum, self.vq.decay)
         self._wcache = None  # the codebook operands are derived caches
 

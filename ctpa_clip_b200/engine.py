@@ -174,11 +174,12 @@ class GradStore:
     at the end and handed to autograd. Direct mode (CTClipTrainStep): when the kernel layout IS the parameter layout the
     accumulator is the parameter's existing .grad (flat arena, zeroed by the optimiser kernel) and autograd gets None."""
 
-    def __init__(self, device, params=None, direct=False):
+    def __init__(self, device, params=None, direct=False, ready=None):
         self.device = device
         self.g = {}
         self.params = params or {}
         self.direct = direct
+        self.ready = ready if direct else None    # callable(list of parameters): their .grad in the arena is final
 
     def direct_grad(self, name, shape=None):
         """the parameter's own .grad if direct accumulation is possible for `name` (optionally: in this shape)"""
@@ -206,6 +207,10 @@ class GradStore:
         return t
 
 
+LAYER_PARAM_NAMES = ("0.dsconv.bias", "1.q_scale", "1.k_scale", "1.norm.gamma", "1.to_q.weight", "1.to_kv.weight",
+                     "1.to_out.weight", "3.0.weight", "3.0.bias", "3.1.weight", "3.4.weight")
+
+
 def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal, tab, rowmax, dtab, gs: GradStore, prefix,
                    dim):
     """gradient of one [PEG, attention, feed-forward] layer; g = dL/dx3 fp32 [T, dim] (g_bf: its bf16 copy, written by
@@ -224,9 +229,17 @@ def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal,
     dh1 = ops.geglu_bwd(c.h1, du)
     dxf = ops.gemm(dh1, L.w1p, b_t=True)                  # [T, dim] bf16: only LayerNorm's backward reads it
     # one GEMM over both padded halves [x rows | gate rows] (two half-size GEMMs into the parameter's own gradient would
-    # read xf twice and fill the SMs worse); un-padded and handed to autograd at the end
-    dw1 = gs.fresh(prefix + "3.1.weight", (2 * L.ffp, dim))
+    # read xf twice and fill the SMs worse); un-padded into the parameter's gradient right away in direct mode (so the layer's
+    # whole gradient span is final when the layer is), else handed to autograd at the end
+    dw1_direct = gs.direct_grad(prefix + "3.1.weight", (2 * L.ffi, dim))
+    if dw1_direct is not None:
+        dw1 = torch.zeros((2 * L.ffp, dim), device=g.device, dtype=torch.float32)
+    else:
+        dw1 = gs.fresh(prefix + "3.1.weight", (2 * L.ffp, dim))
     ops.gemm(dh1, c.xf, a_t=True, b_t=True, out=dw1, accumulate=True, splits=0)
+    if dw1_direct is not None:
+        dw1_direct[: L.ffi] += dw1[: L.ffi]
+        dw1_direct[L.ffi:] += dw1[L.ffp: L.ffp + L.ffi]
     dg = gs.zeros(prefix + "3.0.weight", (dim,))
     db = gs.zeros(prefix + "3.0.bias", (dim,))
     g2, g2_bf = ops.layernorm_bwd(dxf, c.x2, L.ff_g, add_in=g, dgamma=dg, dbeta=db, want_bf16=True)
@@ -252,14 +265,20 @@ def layer_backward(g, g_bf, c: LayerCtx, L: LayerWeights, grid, heads, temporal,
     dw27 = gs.zeros(prefix + "0.dsconv.weight", (27, dim))
     dpb = gs.zeros(prefix + "0.dsconv.bias", (dim,))
     ops.peg_bwd_weight(c.x, g1, dw27, dpb, grid, temporal)
-    return ops.peg_bwd_data(g1, L.w27, grid, temporal, want_bf16=True)
+    out = ops.peg_bwd_data(g1, L.w27, grid, temporal, want_bf16=True)
+    if gs.ready is not None:   # every gradient this layer wrote straight into the arena is final: its all-reduce may start
+        done = [gs.params[prefix + n] for n in LAYER_PARAM_NAMES if gs.direct_grad(prefix + n) is not None]
+        if done:
+            gs.ready(done)
+    return out
 
 
 def encoder_backward(vit, W: EncoderWeights, ctx: EncoderCtx, g_tokens):
     """backward of encoder_forward; g_tokens = dL/d(tokens) fp32 [T, dim]. Returns {reference param name: grad}."""
     dim = W.dim
     dev = g_tokens.device
-    gs = GradStore(dev, params=dict(vit.named_parameters()), direct=getattr(vit, "direct_grad", False))
+    gs = GradStore(dev, params=dict(vit.named_parameters()), direct=getattr(vit, "direct_grad", False),
+                   ready=getattr(vit, "grad_ready", None))
     grid = ctx.grid
     v = ""
     # temporal transformer

@@ -358,8 +358,9 @@ def pool_bwd(dpool, batch, t, hw, dim):
 def vq_ema(embed, cluster_size, x, inv_norm, idx, decay=0.8):
     """in-place train-mode EMA update of (embed [C,D], cluster_size [C]); returns (bins, embed_sum) for cross-rank reduction"""
     codes, dim = embed.shape
-    bins = torch.zeros(codes, device=embed.device, dtype=torch.float32)
-    esum = torch.zeros((codes, dim), device=embed.device, dtype=torch.float32)
+    # ONE buffer [bins | embed_sum]: a single collective reduces both across data-parallel ranks (bins.storage is the buffer)
+    buf = torch.zeros(codes * (dim + 1), device=embed.device, dtype=torch.float32)
+    bins, esum = buf[:codes], buf[codes:].view(codes, dim)
     _call("ctclip_vq_ema_accum", _ptr(x), _ptr(inv_norm), _ptr(idx), _ll(x.shape[0]), dim, _ptr(bins), _ptr(esum), _stream())
     return bins, esum
 

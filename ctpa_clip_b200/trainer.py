@@ -110,9 +110,12 @@ class CTClipTrainStep:
             vit = model.visual_transformer
 
             def ema_reduce(bins, esum):
-                dist.all_reduce(bins)
-                dist.all_reduce(esum)
+                # bins and embed_sum are two views of ONE buffer (ops.vq_ema): one asynchronous all-reduce for both
+                buf = torch.as_strided(bins, (bins.numel() + esum.numel(),), (1,))
+                return dist.all_reduce(buf, async_op=True)
             vit.ema_reduce = ema_reduce
+            # gradients of a finished image-tower layer start their all-reduce while the earlier layers still back-propagate
+            vit.grad_ready = self._on_grads_ready
             # Overlap: the latent-projection and text-tower gradients are final long before the image tower's backward ends
             # (its 294912 -> 512 projection is the FIRST thing the backward computes, the text tower runs next); their
             # all-reduce (1.04 of the 1.13 GB) starts the moment the kernels that wrote them are enqueued.
@@ -188,6 +191,7 @@ class CTClipTrainStep:
 
     def reduce_gradients(self):
         """sum over ranks: every rank back-propagated its own rows of the global-batch loss"""
+        self.model.visual_transformer.finish_ema()    # the (all-reduced) EMA codebook update of this step's forward
         if not self.distributed:
             return
         g = self.arena.grad
