@@ -71,7 +71,9 @@ def train_mode(rank, world):
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert torch.equal(lo, hi), "replicas diverged after one optimiser step"
     tr.raise_if_skipped()
-    mode = symm.mode() if symm.get_exchange(b, cfg["dim_latent"]) is not None else "nccl(fallback)"
+    mode = symm.mode()
+    if mode == "peer" and symm.get_exchange(b, cfg["dim_latent"]) is None:
+        mode = "nccl (peer mapping failed: fallback)"
     return f"loss {float(loss):.6f} (reference {float(fx['loss_train']):.6f}), {n} gradients, worst {worst}, exchange={mode}"
 
 
