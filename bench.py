@@ -247,7 +247,7 @@ def run_ours(args):
     #   and hands the step its (B, 1, 240, 480, 480) fp32 volumes — the reference's own order of work (data.py:138-192
     #   resamples inside the DataLoader, on the CPU) and 24 % fewer PCIe bytes than shipping 221 MB fp32 volumes.
     # mode "fp32": already normalised fp32 volumes in pinned memory (round-1 definition), kept as the comparison.
-    copy_stream = torch.cuda.Stream()
+    copy_stream, prep_stream = torch.cuda.Stream(), torch.cuda.Stream()
     ids_h, mask_h = ids.pin_memory(), mask.pin_memory()
 
     def run_e2e(mode):
@@ -266,22 +266,42 @@ def run_ours(args):
         texts = [BatchEncoding({"input_ids": a, "attention_mask": b}) for a, b in tbufs]
         h2d_events = []
 
+        prep_done = [torch.cuda.Event(), torch.cuda.Event()]      # (raw mode) the prep kernel has consumed stage[i % 2]
+        for e in prep_done:
+            e.record()
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i % 2])
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                c0.record(copy_stream)
                 if mode == "raw":
+                    copy_stream.wait_event(prep_done[i % 2])                       # stage[i % 2] is free again
+                    c0.record(copy_stream)
                     stage[i % 2].copy_(host[i % 2], non_blocking=True)             # this step's raw scans ...
                 else:
+                    copy_stream.wait_event(consumed[i % 2])
+                    c0.record(copy_stream)
                     bufs[i % 2].copy_(host[i % 2], non_blocking=True)
-                tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                    # ... token ids / attention mask
-                tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
+                if mode != "raw":
+                    tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                # ... token ids / attention mask
+                    tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
                 c1.record(copy_stream)
                 h2d_events.append((c0, c1))
-                if mode == "raw":                                                  # data_prep on the device, behind the copy
+                if mode == "raw":
+                    copied[i % 2].record(copy_stream)
+                else:
+                    ready[i % 2].record(copy_stream)
+            if mode == "raw":
+                # data_prep on the device behind the copy, on its OWN stream: while it waits for SMs between the step's
+                # persistent kernels, the copy engine already moves the next step's scans (on the copy stream it stalled them)
+                with torch.cuda.stream(prep_stream):
+                    prep_stream.wait_event(copied[i % 2])
+                    prep_stream.wait_event(consumed[i % 2])                        # the step that last read bufs / tbufs[i % 2] is done
+                    tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                # token ids / attention mask (64 KB)
+                    tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
                     preprocess_volumes(stage[i % 2], 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1], out=bufs[i % 2])
-                ready[i % 2].record(copy_stream)
+                    prep_done[i % 2].record(prep_stream)
+                    ready[i % 2].record(prep_stream)
 
         losses = []
         k = [0]                                   # running step index: step k reads bufs[k % 2], prefetches step k + 1

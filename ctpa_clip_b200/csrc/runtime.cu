@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "ctclip_internal.h"
 
@@ -55,15 +56,27 @@ int require_sm100() {
   return CTCLIP_OK;
 }
 
+// SMs the persistent kernels size their grids for: all of them, or the budget set by ctclip_set_sm_budget / CTCLIP_SM_BUDGET
+// (data-parallel training: a static persistent schedule over 148 CTAs runs a second wave for every SM a concurrent NCCL
+// kernel holds; sizing the grids a few SMs short removes that tail).
+static std::atomic<int> g_sm_budget{-1};
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
-  int n = 148;
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (dev >= 0 && dev < 64) cached[dev] = n;
-  return n;
+  int n = (dev >= 0 && dev < 64) ? cached[dev] : 0;
+  if (n <= 0) {
+    n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+  }
+  int b = g_sm_budget.load(std::memory_order_relaxed);
+  if (b < 0) {
+    const char* e = getenv("CTCLIP_SM_BUDGET");
+    b = e != nullptr ? atoi(e) : 0;
+    g_sm_budget.store(b, std::memory_order_relaxed);
+  }
+  return (b > 0 && b < n) ? b : n;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -83,6 +96,12 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* bas
 }  // namespace ctclip
 
 extern "C" int ctclip_version(void) { return 100; }
+
+extern "C" int ctclip_set_sm_budget(int sms) {
+  if (sms < 0) return ctclip::fail(CTCLIP_E_SHAPE, "set_sm_budget: negative budget");
+  ctclip::g_sm_budget.store(sms, std::memory_order_relaxed);   // 0 = all SMs
+  return CTCLIP_OK;
+}
 
 extern "C" int ctclip_last_error(char* buf, size_t n) {
   if (buf == nullptr || n == 0) return (int)strlen(g_err);

@@ -35,10 +35,14 @@ int ctclip_version(void);
 int ctclip_last_error(char* buf, size_t n);
 /* bytes of the caller-owned workspace of an entry point: op in {"clip_loss" (B, d), "clip_loss_allgather" (b_local, d, world),
  * "cpb_table_fwd" (h, w, dim) [the `acts` buffer], "cpb_table_bwd" (h, w, dim), "bert_attn_bwd" (batch, heads, seq_len),
- * "prep_resample" () [lut_workspace]}; -1 for an unknown op / wrong ndims. Pure host arithmetic. */
+ * "prep_resample" () [lut_workspace], "sumsq" ()}; -1 for an unknown op / wrong ndims. Pure host arithmetic. */
 long long ctclip_workspace_bytes(const char* op, const long long* dims, int ndims);
 /* number of kernels launched by this process through the library since load (bench.py: gpu_launches) */
 long long ctclip_launch_count(void);
+/* SMs the persistent kernels (GEMM, attention, ...) size their grids for: 0 = all (default; env CTCLIP_SM_BUDGET). Data-parallel
+ * training leaves a few SMs to the NCCL kernels that overlap the backward pass: a static persistent schedule over every SM
+ * would run a second wave for each SM a communication kernel holds. Process-wide; takes effect at the next launch. */
+int ctclip_set_sm_budget(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] (op)= alpha * sum_k A(m,k) B(n,k) (+ bias[n]) (+ resid[m,n])      tcgen05 / TMEM / TMA
