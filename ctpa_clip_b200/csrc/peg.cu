@@ -8,6 +8,7 @@
 #include "ptx.cuh"
 #include "ctclip_internal.h"
 #include <type_traits>
+#include <cstdlib>
 
 namespace {
 
@@ -279,8 +280,28 @@ peg_tiled_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
 // MODE 0: y = x + conv(x) + bias; MODE 1: dx = dy + conv^T(dy) (marches downwards, spatial taps mirrored);
 // MODE 2: dw27 / dbias accumulation (x planes march, three dy rows roll).
 constexpr int MTW = 4, MTH = 8, MCH = 64;
+// STAGE (default): the (MTH + 2) x (MTW + 2) x 64-channel neighbourhood of an input plane travels global -> shared memory with
+// cp.async, two planes ahead of the one being consumed (three-slot ring, ONE barrier per plane), and the warps read their
+// three rows from shared memory. ncu on the direct-load version: 5-6.7 long-scoreboard stall cycles per issued instruction
+// at 16 warps / SM (128 registers) — the 18 LDG.64 of a plane are consumed right after they are issued — 35-41 % DRAM.
+constexpr int PEG_STAGES = 3;
+constexpr int PEG_TILE_POS = (MTH + 2) * (MTW + 2);            // positions of one staged plane tile
+constexpr int PEG_TILE_BYTES = PEG_TILE_POS * MCH * 4;         // 15360
+constexpr int PEG_CHUNKS = PEG_TILE_BYTES / 16;                // 960 16-byte chunks: <= 4 per thread
 
-template <int MODE>
+__device__ __forceinline__ void peg_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void peg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void peg_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float2 peg_lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
+template <int MODE, bool STAGE>
 __global__ void __launch_bounds__(256, 2)
 peg_march_kernel(const float* __restrict__ in, const float* __restrict__ in2, float* __restrict__ out,
                  __nv_bfloat16* __restrict__ out_bf16, const float* __restrict__ w27, const float* __restrict__ bias,
@@ -334,6 +355,38 @@ peg_march_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
 #pragma unroll
     for (int ow = 0; ow < MTW; ++ow) acc[s][ow] = make_float2(0.f, 0.f);
 
+  // ---- staging: this thread's <= 4 chunks of a plane tile (same offsets for every plane)
+  extern __shared__ __align__(16) uint8_t peg_smem[];
+  const uint32_t ring = ptx::smem_u32(peg_smem);
+  unsigned g_off[4];     // byte offset of the chunk inside plane 0 (row / column clamped into the grid)
+  uint32_t s_off[4];     // byte offset inside a ring slot
+  bool c_use[4];
+  if constexpr (STAGE) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = threadIdx.x + u * 256;
+      c_use[u] = c < PEG_CHUNKS;
+      const int pos = min(c, PEG_CHUNKS - 1) >> 4, q = c & 15;      // 16 chunks = the 64 channels of one position
+      const int r = pos / (MTW + 2), x = pos - r * (MTW + 2);
+      g_off[u] = (unsigned)((min(max(h0 + r - 1, 0), H - 1) * sh + min(max(w0 + x - 1, 0), W - 1) * sw) * dim +
+                            blockIdx.y * MCH + 4 * q) * 4u;
+      s_off[u] = (uint32_t)(pos * MCH * 4 + q * 16);
+    }
+  }
+  auto stage_plane = [&](int p, int slot) {        // plane p (already a valid plane index) -> ring slot
+    const char* pb = base + p * pstride;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c_use[u]) peg_cp_async16(ring + slot * PEG_TILE_BYTES + s_off[u], pb + g_off[u]);
+  };
+  if constexpr (STAGE) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {                  // planes of steps 0 and 1
+      if (s < T) stage_plane(flip ? T - 1 - s : s, s);
+      peg_cp_commit();
+    }
+  }
+
   if (MODE == 2 && row_ok) {  // dy rows of planes 0 and 1
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -346,6 +399,14 @@ peg_march_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
     constexpr int PH = decltype(phc)::value;
     const int p = flip ? T - 1 - step : step;
     const char* pb = base + p * pstride;
+    uint32_t srow = 0;
+    if constexpr (STAGE) {
+      peg_cp_wait<1>();                             // this thread's chunks of plane `step` have landed (step + 1 may be pending)
+      __syncthreads();                              // ... everybody's; and every warp is done reading slot (step - 1) % 3
+      if (step + 2 < T) stage_plane(flip ? T - 3 - step : step + 2, (step + 2) % PEG_STAGES);
+      peg_cp_commit();
+      srow = ring + (step % PEG_STAGES) * PEG_TILE_BYTES + (uint32_t)(warp * (MTW + 2)) * (MCH * 4) + lane * 8;
+    }
     if (MODE == 2) {
       // dy row of plane p + 2 replaces the slot that held plane p - 1
       const char* b2 = base2 + (p + 2) * pstride;
@@ -361,7 +422,10 @@ peg_march_kernel(const float* __restrict__ in, const float* __restrict__ in2, fl
       float2 v[MTW + 2];
       const char* rp = pb + roff[kh];
 #pragma unroll
-      for (int x = 0; x < MTW + 2; ++x) v[x] = __ldg(reinterpret_cast<const float2*>(rp + coff[x]));
+      for (int x = 0; x < MTW + 2; ++x) {
+        if constexpr (STAGE) v[x] = peg_lds64(srow + (uint32_t)((kh * (MTW + 2) + x) * (MCH * 4)));
+        else v[x] = __ldg(reinterpret_cast<const float2*>(rp + coff[x]));
+      }
       if (!left_ok) v[0] = make_float2(0.f, 0.f);
       if (!right_ok) v[MTW + 1] = make_float2(0.f, 0.f);
       if (MODE != 2 && kh == 1) {  // residual: the centre tap of the plane that completes at this step
@@ -452,8 +516,21 @@ int launch_tiled(const float* in, const float* in2, float* out, void* out_bf16, 
   if (affine_strides(t, h, w, temporal, st, sh, sw) && (long long)t * h * w * dim < (1ll << 31) && w % MTW == 0 &&
       dim % MCH == 0) {
     dim3 grid((unsigned)(((h + MTH - 1) / MTH) * (w / MTW)), (unsigned)(dim / MCH), (unsigned)batch);
-    peg_march_kernel<MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(in, in2, out, (__nv_bfloat16*)out_bf16, w27, bias, dw27,
-                                                                  dbias, t, h, w, st, sh, sw, dim);
+    const char* e = getenv("CTCLIP_PEG_STAGE");    // 0: direct global loads (A/B arm)
+    if (!(e != nullptr && e[0] == '0')) {
+      constexpr int smem = PEG_STAGES * PEG_TILE_BYTES;
+      static bool configured = false;              // per MODE instantiation
+      if (!configured) {
+        if (cudaFuncSetAttribute(peg_march_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+          return ctclip::fail(CTCLIP_E_CUDA, "%s: cudaFuncSetAttribute", what);
+        configured = true;
+      }
+      peg_march_kernel<MODE, true><<<grid, 256, smem, (cudaStream_t)stream>>>(in, in2, out, (__nv_bfloat16*)out_bf16, w27, bias,
+                                                                              dw27, dbias, t, h, w, st, sh, sw, dim);
+    } else {
+      peg_march_kernel<MODE, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, in2, out, (__nv_bfloat16*)out_bf16, w27, bias,
+                                                                            dw27, dbias, t, h, w, st, sh, sw, dim);
+    }
     return ctclip::check_launch(what);
   }
   PegGrid g{t, h, w, temporal};

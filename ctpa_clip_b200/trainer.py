@@ -119,6 +119,7 @@ class CTClipTrainStep:
             # Overlap: the latent-projection and text-tower gradients are final long before the image tower's backward ends
             # (its 294912 -> 512 projection is the FIRST thing the backward computes, the text tower runs next); their
             # all-reduce (1.04 of the 1.13 GB) starts the moment the kernels that wrote them are enqueued.
+            self.overlap = os.environ.get("CTCLIP_DP_OVERLAP", "1") != "0"   # 0: ONE gradient all-reduce pass after backward (A/B)
             model.grad_ready = self._on_grads_ready
             # the 294912 -> 512 projection's gradient (604 of the 1130 MB) is rank-B_glob: its bf16 factors are all-gathered
             # (4.7 MB per rank) and multiplied locally instead of all-reducing the product (CTCLIP_FACTOR_GATHER=0: all-reduce)
@@ -166,6 +167,8 @@ class CTClipTrainStep:
     def _on_grads_ready(self, params, reduced=False):
         """called from inside backward (direct-gradient mode): these parameters' .grad in the arena is final;
         reduced=True: it already is the sum over ranks (factor gather), so the span is only excluded from the all-reduce"""
+        if not self.overlap and not reduced:
+            return                                 # everything is reduced after backward (reduce_gradients)
         spans = sorted(self.arena.span[id(p)] for p in params if id(p) in self.arena.span)
         merged = []
         for off, n in spans:
