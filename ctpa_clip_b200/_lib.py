@@ -32,6 +32,8 @@ class GemmDesc(C.Structure):
         ("a_stride_h", C.c_longlong), ("a_stride_b", C.c_longlong),
         ("b_stride_h", C.c_longlong), ("b_stride_b", C.c_longlong),
         ("c_stride_h", C.c_longlong), ("c_stride_b", C.c_longlong),
+        ("geglu_u", C.c_void_p), ("ld_u", C.c_longlong),
+        ("geglu_h", C.c_void_p), ("ld_h", C.c_longlong),
     ]
 
 

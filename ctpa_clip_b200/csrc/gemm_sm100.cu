@@ -51,6 +51,11 @@ struct GemmKernelParams {
   long long ldr;
   float alpha;
   float4* top2;  // non-null: per (row, n-tile) best two (value, column) instead of storing C
+  // GEGLU epilogues (N = 2 Nh, tiles are 128-column slabs of the x half and of the gate half):
+  //   forward : B rows [x | gate]; accumulator columns [0,128) = x slab, [128,256) = gate slab; C <- h, geglu_u <- x gelu(gate)
+  int geglu_nh;                 // Nh (> 0: one of the GEGLU modes)
+  __nv_bfloat16* geglu_u; long long ld_u;
+  int dbg;                      // CTCLIP_GEGLU_DBG (ablations: 1 no gelu math, 2 no u store, 4 no h store)
   // batched mode (BERT attention): Z = zh_n * zb_n independent problems, z = b * zh_n + h
   int zh_n, z_n;
   int a_hpos, b_hpos;          // 1: tensor-map coordinates are (c0, h, row, b); 2: (c0, row, h, b)
@@ -254,6 +259,56 @@ __device__ __forceinline__ void epi_store_f32x32(const GemmKernelParams& p, uint
   __syncwarp();
 }
 
+// GEGLU forward (attention.py:39-42): this warp's 32 rows x 32 columns of the x slab (xr) and of the gate slab (gr).
+// h = [x | gate] and u = x * gelu(gate) leave as bf16 through the staging tile (row = [x 64 B | gate 64 B], 16-byte chunks
+// XOR-swizzled with the row; 4 lanes x 16 B per row and array, 8 rows per instruction). u is computed from the ROUNDED x and
+// gate, i.e. exactly what geglu_fwd_kernel computes from the stored h.
+__device__ __forceinline__ void epi_geglu_fwd(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
+                                              const uint32_t (&xr)[32], const uint32_t (&gr)[32], int lane) {
+  uint32_t ub[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t xb[4], gb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xb[k] = pack_bf16(__uint_as_float(xr[8 * c4 + 2 * k]), __uint_as_float(xr[8 * c4 + 2 * k + 1]));
+      gb[k] = pack_bf16(__uint_as_float(gr[8 * c4 + 2 * k]), __uint_as_float(gr[8 * c4 + 2 * k + 1]));
+      ub[4 * c4 + k] = (p.dbg & 1) ? xb[k]
+                                   : pack_bf16(bf16_lo(xb[k]) * gelu_fast(bf16_lo(gb[k])), bf16_hi(xb[k]) * gelu_fast(bf16_hi(gb[k])));
+    }
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+    *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c4) ^ (lane & 7)) << 4)) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+  }
+  __syncwarp();
+  const int c4 = lane & 3;
+  const bool col_ok = col0 + c4 * 8 < p.geglu_nh;     // Nh is a multiple of 8: whole 16-byte pieces
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(p.C) + col0 + c4 * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i = it * 8 + (lane >> 2);
+    const uint4 xv = *reinterpret_cast<const uint4*>(stg + i * 128 + ((c4 ^ (i & 7)) << 4));
+    const uint4 gv = *reinterpret_cast<const uint4*>(stg + i * 128 + (((4 + c4) ^ (i & 7)) << 4));
+    if (row0 + i < p.M && col_ok && !(p.dbg & 4)) {
+      *reinterpret_cast<uint4*>(hb + (long long)(row0 + i) * p.ldc) = xv;
+      *reinterpret_cast<uint4*>(hb + (long long)(row0 + i) * p.ldc + p.geglu_nh) = gv;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+        make_uint4(ub[4 * q], ub[4 * q + 1], ub[4 * q + 2], ub[4 * q + 3]);
+  __syncwarp();
+  __nv_bfloat16* ubp = p.geglu_u + col0 + c4 * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i = it * 8 + (lane >> 2);
+    const uint4 uv = *reinterpret_cast<const uint4*>(stg + i * 128 + ((c4 ^ (i & 7)) << 4));
+    if (row0 + i < p.M && col_ok && !(p.dbg & 2)) *reinterpret_cast<uint4*>(ubp + (long long)(row0 + i) * p.ld_u) = uv;
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- kernel
 // PAIR: two CTAs of a cluster (same TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2 — CTA r owns rows
 // [128 r, 128 r + 128) of A and of the accumulator and stages HALF of the B tile (rows [BN/2 r, ...)), which cuts the
@@ -339,7 +394,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         };
         constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows this CTA stages
-        const int b_row0 = n_t * BN + (PAIR ? cta_rank * kBRows : 0);
+        // GEGLU forward: the tile's B rows are a 128-row slab of the x half and the matching slab of the gate half
+        const int b_row0 = p.geglu_u != nullptr ? n_t * 128 + (PAIR && cta_rank ? p.geglu_nh : 0)
+                                                : n_t * BN + (PAIR ? cta_rank * kBRows : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -356,7 +413,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmap_a, p.a_hpos, m_t * BM + j * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
+            if (!PAIR && p.geglu_u != nullptr) {    // 128-row boxes: x slab, then gate slab
+              load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
+              load(sb + 128 * 128, &tmap_b, p.b_hpos, kb * BK, p.geglu_nh + b_row0);
+            } else {
+              load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < kBRows / 64; ++j) load(sb + j * (BK * 128), &tmap_b, p.b_hpos, b_row0 + j * 64, kb * BK);
@@ -495,6 +557,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             p.top2[(long long)row * p.n_tiles + n_t] = make_float4(t1, __int_as_float(j1), t2, __int_as_float(j2));
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");   // the pair's tile is free for the next work unit
+      } else if (p.geglu_u != nullptr) {
+        // GEGLU forward: this warp owns slab columns [64 ch, 64 ch + 64) of BOTH slabs (x at TMEM column lc, gate at 128 + lc)
+        if constexpr (BN == 256) {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const int lc = ch * 64 + c * 32;
+            const int gc = n_t * 128 + lc;           // column of x inside h; the gate column is Nh + gc
+            if (gc >= p.geglu_nh) break;             // warp-uniform
+            uint32_t xr[32], gr[32];
+            tmem_ld_32x32(taddr + lc, xr);
+            tmem_ld_32x32(taddr + 128 + lc, gr);
+            tmem_wait_ld();
+            epi_geglu_fwd(pz, stg, m_t * BM + ew * 32, gc, xr, gr, lane);
+          }
+        }
       } else if (fast_mode == 1 && n_t * BN + (ch + 1) * kHalf <= p.N) {
         // bf16 plain: 64 columns per round; the next round's TMEM loads fly while this round is stored
         const int cbase = n_t * BN + ch * kHalf;
@@ -647,11 +724,24 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   int rc = ctclip::require_sm100();
   if (rc) return rc;
 
-  const int BN = (d->N <= 128) ? 128 : 256;
+  const bool geglu_fwd = d->geglu_u != nullptr;
+  if (geglu_fwd) {
+    if (d->geglu_h != nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: geglu_u and geglu_h are exclusive");
+    if ((d->N % 16) || d->b_mn_major || d->c_is_f32 || d->bias || d->resid || d->atomic || d->top2_out || d->splits > 1 ||
+        d->alpha != 1.f || d->batch_h > 1 || d->batch_b > 1 || d->C == nullptr)
+      return ctclip::fail(CTCLIP_E_SHAPE, "gemm: the GEGLU forward epilogue needs N = 2 Nh with Nh %% 8 == 0, a K-major B, "
+                                          "bf16 C and no bias / resid / atomic / top2 / split-K / alpha / batch");
+    if ((d->ldc % 8) || (d->ld_u % 8) || (reinterpret_cast<uintptr_t>(d->C) & 15) || (reinterpret_cast<uintptr_t>(d->geglu_u) & 15))
+      return ctclip::fail(CTCLIP_E_ALIGN, "gemm: GEGLU outputs need 16-byte aligned rows");
+  }
+  const int BN = (d->N <= 128 && !geglu_fwd) ? 128 : 256;
   GemmKernelParams kp{};
   kp.M = d->M; kp.N = d->N; kp.K = d->K;
   kp.m_tiles = (d->M + BM - 1) / BM;
-  kp.n_tiles = (d->N + BN - 1) / BN;
+  kp.n_tiles = geglu_fwd ? (d->N / 2 + 127) / 128 : (d->N + BN - 1) / BN;
+  kp.geglu_nh = geglu_fwd ? d->N / 2 : 0;
+  kp.geglu_u = reinterpret_cast<__nv_bfloat16*>(d->geglu_u); kp.ld_u = d->ld_u;
+  { const char* e = getenv("CTCLIP_GEGLU_DBG"); kp.dbg = e ? atoi(e) : 0; }
   kp.kb_total = (d->K + BK - 1) / BK;
   int splits = d->splits;
   const int tiles = kp.m_tiles * kp.n_tiles;
@@ -701,7 +791,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   rc = encode_operand_map(&ta, &kp.a_hpos, d->A, d->a_mn_major != 0, d->M, d->K, d->lda, BM, zh_n, zb_n, d->a_stride_h,
                           d->a_stride_b);
   if (rc) return rc;
-  rc = encode_operand_map(&tb, &kp.b_hpos, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, pair ? BN / 2 : BN, zh_n, zb_n,
+  rc = encode_operand_map(&tb, &kp.b_hpos, d->B, d->b_mn_major != 0, d->N, d->K, d->ldb, (pair || geglu_fwd) ? BN / 2 : BN, zh_n, zb_n,
                           d->b_stride_h, d->b_stride_b);
   if (rc) return rc;
 

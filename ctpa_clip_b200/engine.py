@@ -9,10 +9,16 @@ and returns gradients keyed by the reference's parameter names. `EncodeFunction`
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
 from .shadow import bf16_of
+
+
+# GEGLU inside the FF1 GEMM's epilogue / the FF2 dgrad GEMM's epilogue (CTCLIP_FUSE_GEGLU=0: separate row-wise kernels, A/B)
+FUSE_GEGLU = os.environ.get("CTCLIP_FUSE_GEGLU", "1") != "0"
 
 
 def ff_pad(n: int) -> int:
@@ -108,8 +114,11 @@ def layer_forward(x, L: LayerWeights, grid, heads, temporal, tab, rowmax, save: 
     o, lse = ops.attn_fwd(q, kv, grid, heads, temporal, L.q_scale, L.k_scale, tab, rowmax)   # :145-180
     x2 = ops.gemm(o, L.wout, out_dtype=torch.float32, resid=x1)                              # :181 + residual :326
     xf, _, _ = ops.layernorm_fwd(x2, L.ff_g, L.ff_b)                                         # :47
-    h1 = ops.gemm(xf, L.w1p)                                                                 # :48
-    u = ops.geglu_fwd(h1)                                                                    # :39-42
+    if FUSE_GEGLU:
+        h1, u = ops.gemm_geglu(xf, L.w1p)                                                    # :48 with GEGLU (:39-42) in the epilogue
+    else:
+        h1 = ops.gemm(xf, L.w1p)                                                             # :48
+        u = ops.geglu_fwd(h1)                                                                # :39-42
     x3 = ops.gemm(u, L.w2p, out_dtype=torch.float32, resid=x2)                               # :51 + residual :331
     c = None
     if save:

@@ -116,6 +116,31 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_t: bool = False, b_t: bool = Fal
     return out
 
 
+def gemm_geglu(a: torch.Tensor, w: torch.Tensor, *, tag: str = ""):
+    """FeedForward's first Linear with GEGLU in the epilogue (attention.py:39-48): a [M, K] bf16, w [2 Nh, K] bf16 =
+    [x rows | gate rows]. Returns (h [M, 2 Nh] bf16 = [x | gate], kept for the backward, u [M, Nh] bf16 = x * gelu(gate)) —
+    bit-identical to geglu_fwd(gemm(a, w)) without re-reading h."""
+    _req(a, torch.bfloat16, "gemm_geglu.a")
+    _req(w, torch.bfloat16, "gemm_geglu.w")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if N % 16:
+        raise _lib.CtclipError("gemm_geglu: 2 Nh must be a multiple of 16")
+    h = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    u = torch.empty((M, N // 2), device=a.device, dtype=torch.bfloat16)
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn_major = a.data_ptr(), a.stride(0), 0
+    d.B, d.ldb, d.b_mn_major = w.data_ptr(), w.stride(0), 0
+    d.C, d.ldc, d.c_is_f32 = h.data_ptr(), h.stride(0), 0
+    d.alpha, d.splits = 1.0, 1
+    d.geglu_u, d.ld_u = u.data_ptr(), u.stride(0)
+    with _Span("gemm:" + (tag or f"{M}x{N}x{K}+geglu"), 2.0 * M * N * K):
+        _lib.check(_lib.lib().ctclip_gemm_bf16(C.byref(d), _stream()), "ctclip_gemm_bf16(geglu)")
+    return h, u
+
+
 def _call(name: str, *args):
     fn = getattr(_lib.lib(), name)
     with _Span(name.replace("ctclip_", "")):

@@ -70,6 +70,14 @@ typedef struct ctclip_gemm_desc {
    * M, N, K are per-problem extents: tiles never read a neighbouring problem (TMA zero fill). 0 / 1 = not batched. */
   int batch_h, batch_b;
   long long a_stride_h, a_stride_b, b_stride_h, b_stride_b, c_stride_h, c_stride_b;
+  /* GEGLU epilogues of the FeedForward block (attention.py:39-52); N = 2 * Nh, bf16 C, no bias / resid / split-K.
+   * geglu_u != NULL (forward, FF1): B is [2 Nh][ldb] = [x rows | gate rows]; C [M][N] receives h = [x | gate] and
+   *   geglu_u [M][ld_u] receives x * gelu(gate), computed from the bf16-rounded h (bit-identical to ctclip_geglu_fwd on C).
+   * geglu_h != NULL (backward, FF2 dgrad): the product is du [M][Nh] (B has Nh rows / columns, K = dim) and is not stored;
+   *   geglu_h [M][ld_h] is the forward's h; C [M][2 Nh] receives dh = [du * gelu(gate) | du * x * gelu'(gate)]
+   *   (bit-identical to ctclip_geglu_bwd on the bf16-rounded du). */
+  void* geglu_u; long long ld_u;
+  const void* geglu_h; long long ld_h;
 } ctclip_gemm_desc;
 /* N-tile width the kernel will use for a given N (128 or 256): sizes the top2_out buffer */
 int ctclip_gemm_tile_n(int N);

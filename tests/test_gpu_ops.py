@@ -86,6 +86,23 @@ def test_gemm_cta_pair_layouts(ops, a_t, b_t, shape):
     close(out, ref + 1, 1e-4)
 
 
+@pytest.mark.parametrize("shape", [(200, 176, 64), (128, 8, 64), (2000, 1368, 512), (19000, 1368, 512), (333, 520, 200)])
+def test_gemm_geglu_forward_epilogue_is_bit_identical_to_the_unfused_pair(ops, shape):
+    """FF1 with GEGLU in the epilogue (attention.py:39-48): h = [x | gate] equals the plain GEMM's output and u equals
+    geglu_fwd(h) bit for bit, on non-pair tiles, CTA-pair tiles (K >= 512, >= 148 tiles), ragged M and a ragged last slab."""
+    M, Nh, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + Nh + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(2 * Nh, K, device="cuda", generator=g) * 0.08).bfloat16()
+    h_ref = ops.gemm(A, W)
+    u_ref = ops.geglu_fwd(h_ref)
+    h, u = ops.gemm_geglu(A, W)
+    assert torch.equal(h, h_ref)
+    assert torch.equal(u, u_ref)
+    ref = A.float() @ W.float().t()
+    close(u, ref[:, :Nh] * F.gelu(ref[:, Nh:]), 2e-2)
+
+
 def test_gemm_rejects_bad_alignment(ops):
     from ctpa_clip_b200._lib import CtclipError
     A = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
