@@ -43,6 +43,14 @@ struct AttnParams {
   int num_blocks;           // sequence blocks per head; a CTA (fixed head) walks blocks blockIdx.x / heads, + gridDim.x / heads, ...
 };
 
+// Row pitch of the relative-position bias table inside shared memory: the smallest S >= 2 gw - 1 with S = gw (mod 32). The
+// lanes of a warp are consecutive query positions p = qy * gw + qx, and they read table word A_i - B_j with
+// A_i = (qy + gh - 1) S + qx + gw - 1: with this pitch A_i = p + const (mod 32), so the 32 lanes always hit 32 different banks
+// (with the natural pitch 2 gw - 1 = 47 lanes of neighbouring grid rows collide: 35 % of the backward kernel's shared-memory
+// wavefronts were bank conflicts of the bias loads and of the dbias read-modify-writes).
+__host__ __device__ __forceinline__ int tab_pitch(int gw) { return gw + 32 * ((gw - 1 + 31) / 32); }
+__host__ __device__ __forceinline__ int tab_words(int gh, int gw) { return (2 * gh - 2) * tab_pitch(gw) + 2 * gw - 1; }
+
 __device__ __forceinline__ long long row_token(const AttnParams& p, int blk, int r, bool& valid) {
   const int sl = r / p.nst, pos = r - sl * p.nst;
   const long long seq = (long long)blk * p.ns + sl;
@@ -168,8 +176,10 @@ attn_fwd_kernel(const AttnParams p) {
   float* sL = reinterpret_cast<float*>(sB + p.r_pad);   // [2][128] partial row sums of the two column halves
   float* sScale = sL + 256;                             // [64]: q_scale*8*log2e , k_scale
   float* sTab = sScale + 64;
-  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
-  float* sRowMax = sTab + tab_n;
+  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;   // words of the table in global memory
+  const int tab_s = has_bias ? tab_words(p.gh, p.gw) : 0;              // words of the padded copy in shared memory
+  const int tpitch = tab_pitch(p.gw), tw = 2 * p.gw - 1;
+  float* sRowMax = sTab + tab_s;
   uint64_t* bars = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(sRowMax + (has_bias ? p.n : 0)) + 15) & ~uintptr_t(15));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
@@ -188,12 +198,13 @@ attn_fwd_kernel(const AttnParams p) {
     sScale[tid] = p.q_scale[tid] * (kScale * kLog2e);
     sScale[DH + tid] = p.k_scale[tid];
   }
-  for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
+  for (int i = tid; i < tab_n; i += blockDim.x)
+    sTab[(i / tw) * tpitch + i % tw] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
   if (has_bias)
     for (int i = tid; i < p.n; i += blockDim.x) sRowMax[i] = p.bias_rowmax[(long long)head * p.n + i] * kLog2e;
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     const int kp = r % p.n;
-    sB[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));   // byte offset of key r inside the bias table
+    sB[r] = -4 * ((kp / p.gw) * tpitch + (kp % p.gw));   // byte offset of key r inside the (padded) bias table
   }
   tc_fence_before();
   __syncthreads();
@@ -269,7 +280,7 @@ attn_fwd_kernel(const AttnParams p) {
     const int my_seq = r / p.nst;
     const int my_pos = r - my_seq * p.nst;
     const int key_lo = my_seq * p.nst, key_hi = min(R, key_lo + p.n);   // keys of this row's own sequence
-    const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
+    const int a_i = (my_pos / p.gw + p.gh - 1) * tpitch + (my_pos % p.gw) + p.gw - 1;
     const float m_i = cmax + ((has_bias && valid) ? sRowMax[my_pos] : 0.f);
     float l = 0.f;
     fence_proxy_async_smem();
@@ -440,7 +451,10 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   const int nchunks = (R + BKC - 1) / BKC;
   const int ntiles = (R + QT - 1) / QT;
   const bool has_bias = p.bias_table != nullptr;
-  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
+  const int tab_n = has_bias ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;   // words of the table in global memory
+  const int tab_s = has_bias ? tab_words(p.gh, p.gw) : 0;              // words of a padded copy in shared memory
+  const int tpitch = tab_pitch(p.gw), tw = 2 * p.gw - 1;
+  const int r_lse = (R + 31) & ~31;                                    // rows that own an lse / delta slot
 
   constexpr uint32_t TILE_B = QT * DH * 2;         // bytes of one Q~ / dO tile buffer
   uint8_t* sQt = smem;                             // 3 x (128 x 32)  Q~ tile ring
@@ -449,14 +463,14 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   uint8_t* sV = sK + BKC * DH * 2;                 // 128 x 32
   uint8_t* sP = sV + BKC * DH * 2;                 // 128 x 128
   uint8_t* sdS = sP + QT * BKC * 2;                // 128 x 128
-  int* sBn = reinterpret_cast<int*>(sdS + QT * BKC * 2);  // [r_pad] -4 * B_j: byte offset of key j inside the bias table
-  float* sLse = reinterpret_cast<float*>(sBn + p.r_pad);
-  float* sDelta = sLse + p.r_pad;
-  float* sScale = sDelta + p.r_pad;                // [64]
+  short* sBn = reinterpret_cast<short*>(sdS + QT * BKC * 2);  // [r_pad] -4 * B_j: byte offset of key j inside the bias table
+  float* sLse = reinterpret_cast<float*>(sBn + p.r_pad);       // (16-bit: the padded table is < 32 KB; r_pad is a multiple of 128)
+  float* sDelta = sLse + r_lse;
+  float* sScale = sDelta + r_lse;                  // [64]
   float* sRed = sScale + 64;                       // [64]
-  float* sTab = sRed + 64;                         // [tab_n] bias * log2e
-  float* sdTab = sTab + tab_n;                     // [8][tab_n] per-warp private dbias accumulators
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sdTab + 8 * tab_n) + 15) & ~uintptr_t(15));
+  float* sTab = sRed + 64;                         // [tab_s] bias * log2e, rows at the conflict-free pitch
+  float* sdTab = sTab + tab_s;                     // [8][tab_s] per-warp private dbias accumulators
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sdTab + 8 * tab_s) + 15) & ~uintptr_t(15));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
   if (tid == 0) {
@@ -474,11 +488,12 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     sScale[DH + tid] = p.k_scale[tid];
   }
   if (tid < 64) sRed[tid] = 0.f;
-  for (int i = tid; i < tab_n; i += blockDim.x) sTab[i] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
-  for (int i = tid; i < 8 * tab_n; i += blockDim.x) sdTab[i] = 0.f;
+  for (int i = tid; i < tab_n; i += blockDim.x)
+    sTab[(i / tw) * tpitch + i % tw] = p.bias_table[(long long)head * tab_n + i] * kLog2e;
+  for (int i = tid; i < 8 * tab_s; i += blockDim.x) sdTab[i] = 0.f;
   for (int r = tid; r < p.r_pad; r += blockDim.x) {
     const int kp = r % p.n;
-    sBn[r] = -4 * ((kp / p.gw) * (2 * p.gw - 1) + (kp % p.gw));
+    sBn[r] = (short)(-4 * ((kp / p.gw) * tpitch + (kp % p.gw)));
   }
   tc_fence_before();
   __syncthreads();
@@ -491,7 +506,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   constexpr uint32_t idesc_q = make_idesc_bf16(QT, DH, false, true);     // [128 q] x [32], K = 128 keys
   constexpr uint32_t P_RS = (BKC / 8) * 128;                             // row-group stride of the P / dS tiles
   constexpr uint32_t KH_B = BKH * DH * 2;                                // bytes of 64 key rows of sK / sV
-  float* my_dtab = sdTab + warp * tab_n;
+  float* my_dtab = sdTab + warp * tab_s;
   uint32_t ph_a = 0, ph_b = 0, ph_m = 0;
   bool mma_pending = false;
   float acc_qs[DH], acc_ks[DH];
@@ -503,7 +518,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   // accumulators are set up (and flushed) once per CTA
   for (int blk = blockIdx.x / p.heads; blk < p.num_blocks; blk += gridDim.x / p.heads) {
   // ---- lse and delta = rowsum(dO * O) for the whole block
-  for (int r = tid; r < p.r_pad; r += blockDim.x) {
+  for (int r = tid; r < r_lse; r += blockDim.x) {
     bool valid = false;
     const long long tok = (r < R) ? row_token(p, blk, r, valid) : 0;
     if (valid) {
@@ -618,8 +633,8 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       const int my_seq = r / p.nst;
       const int my_pos = r - my_seq * p.nst;
       const int key_lo = my_seq * p.nst, key_hi = min(R, key_lo + p.n);
-      const int a_i = (my_pos / p.gw + p.gh - 1) * (2 * p.gw - 1) + (my_pos % p.gw) + p.gw - 1;
-      const float lse_i = sLse[r], delta_i = sDelta[r];
+      const int a_i = (my_pos / p.gw + p.gh - 1) * tpitch + (my_pos % p.gw) + p.gw - 1;
+      const float lse_i = r < r_lse ? sLse[r] : INFINITY, delta_i = r < r_lse ? sDelta[r] : 0.f;   // rows >= R: p = exp2(-inf) = 0
       // next tile's rows -> ring slot nbuf (last read by the MMAs of step n-2, retired before step n-1 wrote P / dS)
       if (i + 1 < ntiles) {
         store_tile_row(nbuf);
@@ -662,15 +677,16 @@ attn_bwd_kernel(const AttnBwdParams bp) {
           // hits what lane l-1 hit at key j), which is ordered by the in-order LSU pipe of a converged warp: the
           // accesses are volatile (no compiler reordering) and unconditional (invalid rows / keys add an exact 0).
           volatile char* dtb = reinterpret_cast<volatile char*>(my_dtab + a_i);
-          const int2* nb0 = reinterpret_cast<const int2*>(sBn + k0);
-          const int2* nb1 = reinterpret_cast<const int2*>(sBn + k1);
+          const int* nb0 = reinterpret_cast<const int*>(sBn + k0);     // two 16-bit key offsets per word
+          const int* nb1 = reinterpret_cast<const int*>(sBn + k1);
           if (k0 >= key_hi) {               // both sub-pieces beyond the sequence (warp-uniform): nothing to do
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk0[j] = dk0[j] = 0u;
           } else if (k1 + 16 <= key_hi) {   // both sub-pieces fully valid: no per-key predicates, two chains interleaved
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const int2 na = nb0[j >> 1], nb = nb1[j >> 1];
+              const int wa = nb0[j >> 1], wb = nb1[j >> 1];
+              const int2 na = make_int2((int)(short)wa, wa >> 16), nb = make_int2((int)(short)wb, wb >> 16);
               const float pa0 = ex2_approx((__uint_as_float(s0[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + na.x));
               const float pb0 = ex2_approx((__uint_as_float(s1[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x));
               const float pa1 = ex2_approx((__uint_as_float(s0[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + na.y));
@@ -698,12 +714,13 @@ attn_bwd_kernel(const AttnBwdParams bp) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const int kq = q ? k1 : k0;
-              const int2* nbp = q ? nb1 : nb0;
+              const int* nbp = q ? nb1 : nb0;
               const uint32_t* sq = q ? s1 : s0;
               const uint32_t* dq_ = q ? dp1 : dp0;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const int2 nb = nbp[j >> 1];
+                const int wn = nbp[j >> 1];
+                const int2 nb = make_int2((int)(short)wn, wn >> 16);
                 const float x0 = (__uint_as_float(sq[j]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.x);
                 const float x1 = (__uint_as_float(sq[j + 1]) - lse_i) + *reinterpret_cast<const float*>(tabb + nb.y);
                 const float p0 = (kq + j < key_hi) ? ex2_approx(x0) : 0.f;
@@ -899,9 +916,10 @@ attn_bwd_kernel(const AttnBwdParams bp) {
   }
   if (has_bias && bp.dbias_table != nullptr)
     for (int i = tid; i < tab_n; i += blockDim.x) {
+      const int si = (i / tw) * tpitch + i % tw;
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += sdTab[w * tab_n + i];
+      for (int w = 0; w < 8; ++w) t += sdTab[w * tab_s + si];
       atomicAdd(bp.dbias_table + (long long)head * tab_n + i, t);
     }
   if (warp == 0) {
@@ -1307,13 +1325,14 @@ unsigned short_grid(const AttnParams& p, int ctas_per_sm) {
 }
 
 size_t bwd_smem_bytes(const AttnParams& p) {
-  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) : 0;
-  return (size_t)QT * DH * 2 * 6 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 4 * 3 +
-         (size_t)tab_n * 4 * 9 + 128 * 4 + 64 + 16;
+  const int tab_s = (p.bias_table != nullptr) ? tab_words(p.gh, p.gw) : 0;
+  const int r_lse = (p.ns * p.nst + 31) & ~31;
+  return (size_t)QT * DH * 2 * 6 + (size_t)BKC * DH * 2 * 2 + (size_t)QT * BKC * 2 * 2 + (size_t)p.r_pad * 2 +
+         (size_t)r_lse * 4 * 2 + (size_t)tab_s * 4 * 9 + 128 * 4 + 64 + 16;
 }
 
 size_t fwd_smem_bytes(const AttnParams& p) {
-  const int tab_n = (p.bias_table != nullptr) ? (2 * p.gh - 1) * (2 * p.gw - 1) + p.n : 0;
+  const int tab_n = (p.bias_table != nullptr) ? tab_words(p.gh, p.gw) + p.n : 0;
   const size_t kv_rows = (size_t)((p.ns * p.nst + KC - 1) / KC) * KC;
   return kv_rows * DH * 2 * 2 + QT * DH * 2 + QT * KC * 2 + (size_t)tab_n * 4 + 64 * 4 + 256 * 4 +
          (size_t)p.r_pad * 4 + 64 + 16;
