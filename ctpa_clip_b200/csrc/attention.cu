@@ -597,6 +597,34 @@ attn_bwd_kernel(const AttnBwdParams bp) {
     const long long ktok = (kr < R) ? row_token(p, blk, kr, kvalid) : 0;
     float kraw[DH];
     float kinv = 0.f;
+    // Global latency off the chunk-start critical path: the first tile's rows were requested two steps ago (see the step
+    // loop) or are requested here BEFORE the K / V rows are waited for, and the lines the next chunk start / the next
+    // sequence block will need are pulled into L2 now (no registers held).
+    if (c == 0 || ntiles < 2) prefetch_tile_row(0);
+    {
+      const int nblk = blk + gridDim.x / p.heads;
+      const bool next_chunk = c + 1 < nchunks;
+      if (next_chunk || nblk < p.num_blocks) {
+        const int nr = next_chunk ? kr + BKC : rowt;
+        bool nvalid = false;
+        const long long ntok = (nr < R) ? row_token(p, next_chunk ? blk : nblk, nr, nvalid) : 0;
+        if (nvalid) {
+          const __nv_bfloat16* a = p.kv + ntok * p.ldkv + (half ? p.inner : 0) + head * DH;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
+      if (!next_chunk && nblk < p.num_blocks) {   // last chunk: the next block's dO / O rows (delta prologue) and lse
+        for (int r = tid; r < R; r += blockDim.x) {
+          bool nvalid = false;
+          const long long ntok = row_token(p, nblk, r, nvalid);
+          if (nvalid) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(bp.d_o + ntok * p.ldo + head * DH));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.o + ntok * p.ldo + head * DH));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.q + ntok * p.ldq + head * DH));
+          }
+        }
+      }
+    }
     if (half == 0) {
       if (kvalid) {
         kinv = load_head_row(p.kv + ktok * p.ldkv + head * DH, kraw);
@@ -616,7 +644,6 @@ attn_bwd_kernel(const AttnBwdParams bp) {
         store_zero_row_cm(sV, rowt);
       }
     }
-    prefetch_tile_row(0);
     store_tile_row(gstep % 3);
     if (ntiles > 1) prefetch_tile_row(1);
     fence_proxy_async_smem();
@@ -639,6 +666,7 @@ attn_bwd_kernel(const AttnBwdParams bp) {
       if (i + 1 < ntiles) {
         store_tile_row(nbuf);
         if (i + 2 < ntiles) prefetch_tile_row(i + 2);
+        else if (c + 1 < nchunks) prefetch_tile_row(0);   // first tile of the next chunk: in registers across the chunk's last step
       }
       uint32_t pk[32], dk[32];
 #pragma unroll
