@@ -51,11 +51,9 @@ struct GemmKernelParams {
   long long ldr;
   float alpha;
   float4* top2;  // non-null: per (row, n-tile) best two (value, column) instead of storing C
-  // GEGLU epilogues (N = 2 Nh, tiles are 128-column slabs of the x half and of the gate half):
-  //   forward : B rows [x | gate]; accumulator columns [0,128) = x slab, [128,256) = gate slab; C <- h, geglu_u <- x gelu(gate)
-  int geglu_nh;                 // Nh (> 0: one of the GEGLU modes)
-  __nv_bfloat16* geglu_u; long long ld_u;
-  int dbg;                      // CTCLIP_GEGLU_DBG (ablations: 1 no gelu math, 2 no u store, 4 no h store)
+  // GEGLU forward epilogue (template EPI = 1; N = 2 Nh, tiles are 128-column slabs of the x half and of the gate half):
+  //   B rows [x | gate]; accumulator columns [0,128) = x slab, [128,256) = gate slab; C <- h = [x | gate], u <- x gelu(gate).
+  //   No fields of its own (a larger struct cost the other instantiations registers): Nh = N / 2, u = top2, ld_u = ldr.
   // batched mode (BERT attention): Z = zh_n * zb_n independent problems, z = b * zh_n + h
   int zh_n, z_n;
   int a_hpos, b_hpos;          // 1: tensor-map coordinates are (c0, h, row, b); 2: (c0, row, h, b)
@@ -265,6 +263,8 @@ __device__ __forceinline__ void epi_store_f32x32(const GemmKernelParams& p, uint
 // gate, i.e. exactly what geglu_fwd_kernel computes from the stored h.
 __device__ __forceinline__ void epi_geglu_fwd(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
                                               const uint32_t (&xr)[32], const uint32_t (&gr)[32], int lane) {
+  const int nh = p.N >> 1;
+  __nv_bfloat16* u_out = reinterpret_cast<__nv_bfloat16*>(p.top2);
   uint32_t ub[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
@@ -273,24 +273,23 @@ __device__ __forceinline__ void epi_geglu_fwd(const GemmKernelParams& p, uint8_t
     for (int k = 0; k < 4; ++k) {
       xb[k] = pack_bf16(__uint_as_float(xr[8 * c4 + 2 * k]), __uint_as_float(xr[8 * c4 + 2 * k + 1]));
       gb[k] = pack_bf16(__uint_as_float(gr[8 * c4 + 2 * k]), __uint_as_float(gr[8 * c4 + 2 * k + 1]));
-      ub[4 * c4 + k] = (p.dbg & 1) ? xb[k]
-                                   : pack_bf16(bf16_lo(xb[k]) * gelu_fast(bf16_lo(gb[k])), bf16_hi(xb[k]) * gelu_fast(bf16_hi(gb[k])));
+      ub[4 * c4 + k] = pack_bf16(bf16_lo(xb[k]) * gelu_fast(bf16_lo(gb[k])), bf16_hi(xb[k]) * gelu_fast(bf16_hi(gb[k])));
     }
     *reinterpret_cast<uint4*>(stg + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
     *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c4) ^ (lane & 7)) << 4)) = make_uint4(gb[0], gb[1], gb[2], gb[3]);
   }
   __syncwarp();
   const int c4 = lane & 3;
-  const bool col_ok = col0 + c4 * 8 < p.geglu_nh;     // Nh is a multiple of 8: whole 16-byte pieces
+  const bool col_ok = col0 + c4 * 8 < nh;     // Nh is a multiple of 8: whole 16-byte pieces
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(p.C) + col0 + c4 * 8;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int i = it * 8 + (lane >> 2);
     const uint4 xv = *reinterpret_cast<const uint4*>(stg + i * 128 + ((c4 ^ (i & 7)) << 4));
     const uint4 gv = *reinterpret_cast<const uint4*>(stg + i * 128 + (((4 + c4) ^ (i & 7)) << 4));
-    if (row0 + i < p.M && col_ok && !(p.dbg & 4)) {
+    if (row0 + i < p.M && col_ok) {
       *reinterpret_cast<uint4*>(hb + (long long)(row0 + i) * p.ldc) = xv;
-      *reinterpret_cast<uint4*>(hb + (long long)(row0 + i) * p.ldc + p.geglu_nh) = gv;
+      *reinterpret_cast<uint4*>(hb + (long long)(row0 + i) * p.ldc + nh) = gv;
     }
   }
   __syncwarp();
@@ -299,23 +298,25 @@ __device__ __forceinline__ void epi_geglu_fwd(const GemmKernelParams& p, uint8_t
     *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
         make_uint4(ub[4 * q], ub[4 * q + 1], ub[4 * q + 2], ub[4 * q + 3]);
   __syncwarp();
-  __nv_bfloat16* ubp = p.geglu_u + col0 + c4 * 8;
+  __nv_bfloat16* ubp = u_out + col0 + c4 * 8;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int i = it * 8 + (lane >> 2);
     const uint4 uv = *reinterpret_cast<const uint4*>(stg + i * 128 + ((c4 ^ (i & 7)) << 4));
-    if (row0 + i < p.M && col_ok && !(p.dbg & 2)) *reinterpret_cast<uint4*>(ubp + (long long)(row0 + i) * p.ld_u) = uv;
+    if (row0 + i < p.M && col_ok) *reinterpret_cast<uint4*>(ubp + (long long)(row0 + i) * p.ldr) = uv;
   }
   __syncwarp();
 }
 
 // ---------------------------------------------------------------- kernel
+// EPI = 1: GEGLU forward epilogue (a separate instantiation: its code must not cost the other epilogues registers — adding it as
+// a run-time branch pushed their spills from < 100 to ~900 bytes and the fp32 + residual GEMMs lost 15 %).
 // PAIR: two CTAs of a cluster (same TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2 — CTA r owns rows
 // [128 r, 128 r + 128) of A and of the accumulator and stages HALF of the B tile (rows [BN/2 r, ...)), which cuts the
 // shared-memory fill per k-block from 48 KB to 32 KB (6 stages instead of 4). Only the leader issues MMAs; both CTAs' TMA
 // loads are counted on the leader's full barriers, MMA completion is multicast to both CTAs' empty / accumulator-full
 // barriers, and both epilogues release the accumulator on the leader's barrier.
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
@@ -395,8 +396,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         };
         constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows this CTA stages
         // GEGLU forward: the tile's B rows are a 128-row slab of the x half and the matching slab of the gate half
-        const int b_row0 = p.geglu_u != nullptr ? n_t * 128 + (PAIR && cta_rank ? p.geglu_nh : 0)
-                                                : n_t * BN + (PAIR ? cta_rank * kBRows : 0);
+        const int b_row0 = EPI == 1 ? n_t * 128 + (PAIR && cta_rank ? (p.N >> 1) : 0) : n_t * BN + (PAIR ? cta_rank * kBRows : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -413,12 +413,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmap_a, p.a_hpos, m_t * BM + j * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            if (!PAIR && p.geglu_u != nullptr) {    // 128-row boxes: x slab, then gate slab
-              load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
-              load(sb + 128 * 128, &tmap_b, p.b_hpos, kb * BK, p.geglu_nh + b_row0);
-            } else {
-              load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
-            }
+            load(sb, &tmap_b, p.b_hpos, kb * BK, b_row0);
+            if constexpr (EPI == 1 && !PAIR) load(sb + 128 * 128, &tmap_b, p.b_hpos, kb * BK, (p.N >> 1) + b_row0);   // gate slab
           } else {
 #pragma unroll
             for (int j = 0; j < kBRows / 64; ++j) load(sb + j * (BK * 128), &tmap_b, p.b_hpos, b_row0 + j * 64, kb * BK);
@@ -516,7 +512,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m_t * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-      if (p.top2 != nullptr) {
+      if constexpr (EPI == 1) {
+        // GEGLU forward: this warp owns slab columns [64 ch, 64 ch + 64) of BOTH slabs (x at TMEM column lc, gate at 128 + lc)
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int lc = ch * 64 + c * 32;
+          const int gc = n_t * 128 + lc;           // column of x inside h; the gate column is Nh + gc
+          if (gc >= (p.N >> 1)) break;             // warp-uniform
+          uint32_t xr[32], gr[32];
+          tmem_ld_32x32(taddr + lc, xr);
+          tmem_ld_32x32(taddr + 128 + lc, gr);
+          tmem_wait_ld();
+          epi_geglu_fwd(pz, stg, m_t * BM + ew * 32, gc, xr, gr, lane);
+        }
+      } else if (p.top2 != nullptr) {
         // VQ assignment epilogue: running best-two over this tile's columns (ties keep the lower column). The two warps of
         // a lane quadrant scan one half of the columns each; the upper half hands its pair to the lower one through the
         // staging tile (named barrier of the two warps), which merges and writes one float4 per row.
@@ -557,21 +566,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             p.top2[(long long)row * p.n_tiles + n_t] = make_float4(t1, __int_as_float(j1), t2, __int_as_float(j2));
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory");   // the pair's tile is free for the next work unit
-      } else if (p.geglu_u != nullptr) {
-        // GEGLU forward: this warp owns slab columns [64 ch, 64 ch + 64) of BOTH slabs (x at TMEM column lc, gate at 128 + lc)
-        if constexpr (BN == 256) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            const int lc = ch * 64 + c * 32;
-            const int gc = n_t * 128 + lc;           // column of x inside h; the gate column is Nh + gc
-            if (gc >= p.geglu_nh) break;             // warp-uniform
-            uint32_t xr[32], gr[32];
-            tmem_ld_32x32(taddr + lc, xr);
-            tmem_ld_32x32(taddr + 128 + lc, gr);
-            tmem_wait_ld();
-            epi_geglu_fwd(pz, stg, m_t * BM + ew * 32, gc, xr, gr, lane);
-          }
-        }
       } else if (fast_mode == 1 && n_t * BN + (ch + 1) * kHalf <= p.N) {
         // bf16 plain: 64 columns per round; the next round's TMEM loads fly while this round is stored
         const int cbase = n_t * BN + ch * kHalf;
@@ -670,11 +664,11 @@ int encode_operand_map(CUtensorMap* map, int* hpos, const void* ptr, bool mn_maj
                              estr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, int EPI = 0>
 int launch(const ctclip_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta, const CUtensorMap& tb,
            int grid, cudaStream_t stream) {
   using L = SmemLayout<BN, PAIR>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, PAIR>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, PAIR, EPI>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -725,11 +719,11 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   if (rc) return rc;
 
   const bool geglu_fwd = d->geglu_u != nullptr;
+  if (d->geglu_h != nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: the GEGLU backward epilogue (geglu_h) is not implemented");
   if (geglu_fwd) {
-    if (d->geglu_h != nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: geglu_u and geglu_h are exclusive");
-    if ((d->N % 16) || d->b_mn_major || d->c_is_f32 || d->bias || d->resid || d->atomic || d->top2_out || d->splits > 1 ||
-        d->alpha != 1.f || d->batch_h > 1 || d->batch_b > 1 || d->C == nullptr)
-      return ctclip::fail(CTCLIP_E_SHAPE, "gemm: the GEGLU forward epilogue needs N = 2 Nh with Nh %% 8 == 0, a K-major B, "
+    if ((d->N % 16) || d->a_mn_major || d->b_mn_major || d->c_is_f32 || d->bias || d->resid || d->atomic || d->top2_out ||
+        d->splits > 1 || d->alpha != 1.f || d->batch_h > 1 || d->batch_b > 1 || d->C == nullptr)
+      return ctclip::fail(CTCLIP_E_SHAPE, "gemm: the GEGLU forward epilogue needs N = 2 Nh with Nh %% 8 == 0, K-major A and B, "
                                           "bf16 C and no bias / resid / atomic / top2 / split-K / alpha / batch");
     if ((d->ldc % 8) || (d->ld_u % 8) || (reinterpret_cast<uintptr_t>(d->C) & 15) || (reinterpret_cast<uintptr_t>(d->geglu_u) & 15))
       return ctclip::fail(CTCLIP_E_ALIGN, "gemm: GEGLU outputs need 16-byte aligned rows");
@@ -739,9 +733,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   kp.M = d->M; kp.N = d->N; kp.K = d->K;
   kp.m_tiles = (d->M + BM - 1) / BM;
   kp.n_tiles = geglu_fwd ? (d->N / 2 + 127) / 128 : (d->N + BN - 1) / BN;
-  kp.geglu_nh = geglu_fwd ? d->N / 2 : 0;
-  kp.geglu_u = reinterpret_cast<__nv_bfloat16*>(d->geglu_u); kp.ld_u = d->ld_u;
-  { const char* e = getenv("CTCLIP_GEGLU_DBG"); kp.dbg = e ? atoi(e) : 0; }
+
   kp.kb_total = (d->K + BK - 1) / BK;
   int splits = d->splits;
   const int tiles = kp.m_tiles * kp.n_tiles;
@@ -771,6 +763,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   kp.bias = d->bias; kp.resid = d->resid; kp.ldr = d->ldr;
   kp.alpha = d->alpha;
   kp.top2 = reinterpret_cast<float4*>(d->top2_out);
+  if (geglu_fwd) { kp.top2 = reinterpret_cast<float4*>(d->geglu_u); kp.ldr = d->ld_u; }   // EPI = 1 reads them as (u, ld_u)
   if (kp.top2 != nullptr && kp.splits > 1) return ctclip::fail(CTCLIP_E_SHAPE, "gemm: top2 epilogue cannot be split-K");
   if (kp.splits > 1 && (d->bias || d->resid))
     return ctclip::fail(CTCLIP_E_SHAPE, "gemm: bias/resid not supported with split-K");
@@ -801,6 +794,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
     if (clusters > units) clusters = units;
     const int grid = 2 * clusters;
     const int sel = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+    if (geglu_fwd) return launch<256, false, false, true, 1>(d, kp, ta, tb, grid, stream);
     switch (sel) {
       case 0: return launch<256, false, false, true>(d, kp, ta, tb, grid, stream);
       case 1: return launch<256, false, true, true>(d, kp, ta, tb, grid, stream);
@@ -811,6 +805,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   const int num_work = tiles * kp.splits * kp.z_n;
   const int grid = num_work < sms ? num_work : sms;
   const int sel = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+  if (geglu_fwd) return launch<256, false, false, false, 1>(d, kp, ta, tb, grid, stream);
   switch (sel) {
     case 0: return launch<128, false, false, false>(d, kp, ta, tb, grid, stream);
     case 1: return launch<128, false, true, false>(d, kp, ta, tb, grid, stream);
