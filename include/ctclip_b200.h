@@ -70,12 +70,13 @@ typedef struct ctclip_gemm_desc {
    * M, N, K are per-problem extents: tiles never read a neighbouring problem (TMA zero fill). 0 / 1 = not batched. */
   int batch_h, batch_b;
   long long a_stride_h, a_stride_b, b_stride_h, b_stride_b, c_stride_h, c_stride_b;
-  /* GEGLU epilogues of the FeedForward block (attention.py:39-52); N = 2 * Nh, bf16 C, no bias / resid / split-K.
-   * geglu_u != NULL (forward, FF1): B is [2 Nh][ldb] = [x rows | gate rows]; C [M][N] receives h = [x | gate] and
-   *   geglu_u [M][ld_u] receives x * gelu(gate), computed from the bf16-rounded h (bit-identical to ctclip_geglu_fwd on C).
-   * geglu_h != NULL (backward, FF2 dgrad): the product is du [M][Nh] (B has Nh rows / columns, K = dim) and is not stored;
-   *   geglu_h [M][ld_h] is the forward's h; C [M][2 Nh] receives dh = [du * gelu(gate) | du * x * gelu'(gate)]
-   *   (bit-identical to ctclip_geglu_bwd on the bf16-rounded du). */
+  /* GEGLU epilogue of the FeedForward block's first Linear (attention.py:39-48); N = 2 * Nh, bf16 C, K-major A and B, no
+   * bias / resid / split-K. geglu_u != NULL: B is [2 Nh][ldb] = [x rows | gate rows]; C [M][N] receives h = [x | gate] (kept
+   * for the backward) and geglu_u [M][ld_u] receives x * gelu(gate), computed from the bf16-rounded h (bit-identical to
+   * ctclip_geglu_fwd on C) without re-reading h from HBM.
+   * geglu_h / ld_h: reserved for the backward counterpart (GEGLU backward in the FF2 dgrad epilogue). It was built and is
+   * bit-identical, but the h loads in the epilogue make it slower than the two-kernel path (491 vs 192 + 250 us per layer),
+   * so the library rejects a non-NULL geglu_h. */
   void* geglu_u; long long ld_u;
   const void* geglu_h; long long ld_h;
 } ctclip_gemm_desc;
