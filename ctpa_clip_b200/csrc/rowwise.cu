@@ -216,6 +216,150 @@ layernorm_bwd_kernel(const void* __restrict__ dy_v, const float* __restrict__ x,
   }
 }
 
+// ------------------------------------------------------------------------------------------ LayerNorm bwd, dim = 512
+// The image tower's case ([110592, 512] rows, 44 % of the LayerNorm time of a step). Same arithmetic, in the same order, as
+// layernorm_bwd_kernel<4, ...> (bit-identical dx); the difference is how the rows reach the lanes: every warp owns a two-stage
+// shared-memory ring and requests the NEXT row's x, dy and add_in with cp.async (16-byte pieces, no registers held) while it
+// works on the current one, so 16 warps / SM keep ~160 KB of reads in flight instead of what fits the register file.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool DY_BF16>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd512_kernel(const void* __restrict__ dy_v, const float* __restrict__ x, long long rows,
+                        const float* __restrict__ gamma, float eps, const float* __restrict__ add_in,
+                        float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta) {
+  constexpr int DIM = 512, NV = 4;
+  constexpr int DYB = DY_BF16 ? 1024 : 2048;
+  constexpr int STAGE = 4096 + DYB;                 // [x 2 KB | add_in 2 KB | dy]
+  extern __shared__ __align__(16) uint8_t sm512[];
+  float* red = reinterpret_cast<float*>(sm512);     // [2][512]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = sm512 + 2 * DIM * 4 + warp * 2 * STAGE;
+  const long long warp_global = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (int i = threadIdx.x; i < 2 * DIM; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 acc_g[NV], acc_b[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc_g[j] = acc_b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto issue = [&](long long row, int st) {
+    uint8_t* b = ring + st * STAGE;
+    const float* xr = x + row * DIM;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) cp_async16(b + (lane + 32 * j) * 16, xr + (lane + 32 * j) * 4);
+    if (add_in != nullptr) {
+      const float* ar = add_in + row * DIM;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) cp_async16(b + 2048 + (lane + 32 * j) * 16, ar + (lane + 32 * j) * 4);
+    }
+    if (DY_BF16) {
+      const __nv_bfloat16* dr = reinterpret_cast<const __nv_bfloat16*>(dy_v) + row * DIM;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) cp_async16(b + 4096 + (lane + 32 * j) * 16, dr + (lane + 32 * j) * 8);
+    } else {
+      const float* dr = reinterpret_cast<const float*>(dy_v) + row * DIM;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) cp_async16(b + 4096 + (lane + 32 * j) * 16, dr + (lane + 32 * j) * 4);
+    }
+  };
+
+  int st = 0;
+  if (warp_global < rows) issue(warp_global, 0);
+  cp_async_commit();
+  for (long long row = warp_global; row < rows; row += nwarps, st ^= 1) {
+    if (row + nwarps < rows) issue(row + nwarps, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();      // this row's group has landed (the newest one may still be in flight)
+    __syncwarp();            // ... for every lane's pieces
+    const uint8_t* b = ring + st * STAGE;
+    float4 v[NV], d[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = *reinterpret_cast<const float4*>(b + i * 16);
+      if (DY_BF16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(b + 4096 + i * 8);
+        d[j] = make_float4(ptx::bf16_lo(u.x), ptx::bf16_hi(u.x), ptx::bf16_lo(u.y), ptx::bf16_hi(u.y));
+      } else {
+        d[j] = *reinterpret_cast<const float4*>(b + 4096 + i * 16);
+      }
+    }
+    const float x0 = __shfl_sync(0xffffffffu, v[0].x, 0);
+    float s1 = 0.f, s2 = 0.f, sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + 32 * j;
+      v[j].x -= x0; v[j].y -= x0; v[j].z -= x0; v[j].w -= x0;
+      s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      s2 += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float gx = d[j].x * gm.x, gy = d[j].y * gm.y, gz = d[j].z * gm.z, gw = d[j].w * gm.w;
+      sg += (gx + gy) + (gz + gw);
+      sgx += (gx * v[j].x + gy * v[j].y) + (gz * v[j].z + gw * v[j].w);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+      sg += __shfl_xor_sync(0xffffffffu, sg, m);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, m);
+    }
+    asm volatile("" ::: "memory");
+    const float inv_dim = 1.f / DIM;
+    const float m0 = s1 * inv_dim;                                     // mean - x0
+    const float rstd = rsqrtf(fmaxf(s2 * inv_dim - m0 * m0, 0.f) + eps);
+    const float mg = sg * inv_dim, mgx = rstd * (sgx - m0 * sg) * inv_dim;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + 32 * j;
+      v[j].x = (v[j].x - m0) * rstd; v[j].y = (v[j].y - m0) * rstd;
+      v[j].z = (v[j].z - m0) * rstd; v[j].w = (v[j].w - m0) * rstd;
+      acc_g[j].x += d[j].x * v[j].x; acc_g[j].y += d[j].y * v[j].y;
+      acc_g[j].z += d[j].z * v[j].z; acc_g[j].w += d[j].w * v[j].w;
+      acc_b[j].x += d[j].x; acc_b[j].y += d[j].y; acc_b[j].z += d[j].z; acc_b[j].w += d[j].w;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      float4 o;
+      o.x = rstd * (d[j].x * gm.x - mg - v[j].x * mgx);
+      o.y = rstd * (d[j].y * gm.y - mg - v[j].y * mgx);
+      o.z = rstd * (d[j].z * gm.z - mg - v[j].z * mgx);
+      o.w = rstd * (d[j].w * gm.w - mg - v[j].w * mgx);
+      if (add_in != nullptr) {
+        const float4 a = *reinterpret_cast<const float4*>(b + 2048 + i * 16);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (dx_out != nullptr) reinterpret_cast<float4*>(dx_out + row * DIM)[i] = o;
+      if (dx_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = ptx::pack_bf16(o.x, o.y);
+        pk.y = ptx::pack_bf16(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * DIM)[i] = pk;
+      }
+    }
+    __syncwarp();            // every lane is done with this stage before the next iteration's cp.async refills it
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    atomicAdd(&red[4 * i + 0], acc_g[j].x); atomicAdd(&red[4 * i + 1], acc_g[j].y);
+    atomicAdd(&red[4 * i + 2], acc_g[j].z); atomicAdd(&red[4 * i + 3], acc_g[j].w);
+    atomicAdd(&red[DIM + 4 * i + 0], acc_b[j].x); atomicAdd(&red[DIM + 4 * i + 1], acc_b[j].y);
+    atomicAdd(&red[DIM + 4 * i + 2], acc_b[j].z); atomicAdd(&red[DIM + 4 * i + 3], acc_b[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DIM; i += blockDim.x) {
+    if (dgamma != nullptr) atomicAdd(dgamma + i, red[i]);
+    if (dbeta != nullptr) atomicAdd(dbeta + i, red[DIM + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ GEGLU
 // h: [rows][2*ld_half] bf16 = [x | gate];  u: [rows][ld_half] bf16 = x * gelu(gate)
 __global__ void __launch_bounds__(256)
@@ -326,6 +470,32 @@ extern "C" int ctclip_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
   const size_t sm = 2 * dim * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* db = (__nv_bfloat16*)dx_bf16;
+  {
+    // dim 512, 16-byte aligned rows: the cp.async ring kernel (CTCLIP_LN_BWD_RING=0: the register-staged kernel, A/B)
+    const char* e = getenv("CTCLIP_LN_BWD_RING");    // read per call: the test compares both kernels in one process
+    const int ring = (e != nullptr && e[0] == '0') ? 0 : 1;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add_in) |
+                         reinterpret_cast<uintptr_t>(dx_out) | reinterpret_cast<uintptr_t>(dx_bf16);
+    if (ring && dim == 512 && (al & 15) == 0) {
+      long long nb = (rows + 63) / 64;
+      const long long cap2 = (long long)ctclip::sm_count() * 2;
+      if (nb > cap2) nb = cap2;
+      cudaStream_t s2 = (cudaStream_t)stream;
+      __nv_bfloat16* db2 = (__nv_bfloat16*)dx_bf16;
+      if (dy_is_bf16) {
+        constexpr int kSm = 2 * 512 * 4 + 8 * 2 * (4096 + 1024);
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(layernorm_bwd512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm); cfg = true; }
+        layernorm_bwd512_kernel<true><<<(int)nb, 256, kSm, s2>>>(dy, x, rows, gamma, eps, add_in, dx_out, db2, dgamma, dbeta);
+      } else {
+        constexpr int kSm = 2 * 512 * 4 + 8 * 2 * (4096 + 2048);
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(layernorm_bwd512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm); cfg = true; }
+        layernorm_bwd512_kernel<false><<<(int)nb, 256, kSm, s2>>>(dy, x, rows, gamma, eps, add_in, dx_out, db2, dgamma, dbeta);
+      }
+      return ctclip::check_launch("layernorm_bwd(512)");
+    }
+  }
   static int ahead = -1;   // CTCLIP_LN_BWD_L2_AHEAD=0: no L2 prefetches (A/B)
   if (ahead < 0) {
     const char* e = getenv("CTCLIP_LN_BWD_L2_AHEAD");
