@@ -308,9 +308,42 @@ __device__ __forceinline__ void epi_geglu_fwd(const GemmKernelParams& p, uint8_t
   __syncwarp();
 }
 
+// fp32 + residual with the residual tile of the chunk ALREADY in registers (EPI = 3: loaded one chunk ahead by the caller, so
+// that the global-load latency overlaps the previous chunk's transposition and stores instead of sitting on the critical path
+// of every chunk). rr[it] = residual float4 of row (row0 + it * 4 + (lane >> 3)), columns col0 + 4 * (lane & 7) ...
+__device__ __forceinline__ void epi_load_resid(const GemmKernelParams& p, int row0, int col0, int lane, float4 (&rr)[8]) {
+  const float* rb = p.resid + col0 + (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int grow = row0 + it * 4 + (lane >> 3);
+    rr[it] = (grow < p.M) ? *reinterpret_cast<const float4*>(rb + (long long)grow * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void epi_store_f32x32_rr(const GemmKernelParams& p, uint8_t* stg, int row0, int col0,
+                                                    const uint32_t (&a)[32], const float4 (&rr)[8], int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+        make_uint4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+  __syncwarp();
+  const int g = lane & 7;
+  float* cb = reinterpret_cast<float*>(p.C) + col0 + g * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int i = it * 4 + (lane >> 3);
+    float4 x = *reinterpret_cast<const float4*>(stg + i * 128 + ((g ^ (i & 7)) << 4));
+    x.x += rr[it].x; x.y += rr[it].y; x.z += rr[it].z; x.w += rr[it].w;
+    if (row0 + i < p.M) *reinterpret_cast<float4*>(cb + (long long)(row0 + i) * p.ldc) = x;
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- kernel
 // EPI = 1: GEGLU forward epilogue (a separate instantiation: its code must not cost the other epilogues registers — adding it as
 // a run-time branch pushed their spills from < 100 to ~900 bytes and the fp32 + residual GEMMs lost 15 %).
+// EPI = 3: fp32 + residual with the residual rows held one chunk ahead in registers (whole-chunk N only; the residual may not
+//          alias C rows that a LATER chunk of the same warp reads... it never does: a chunk's residual is read before any store
+//          of that chunk, and chunks touch disjoint columns).
 // PAIR: two CTAs of a cluster (same TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2 — CTA r owns rows
 // [128 r, 128 r + 128) of A and of the accumulator and stages HALF of the B tile (rows [BN/2 r, ...)), which cuts the
 // shared-memory fill per k-block from 48 KB to 32 KB (6 stages instead of 4). Only the leader issues MMAs; both CTAs' TMA
@@ -512,7 +545,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m_t * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-      if constexpr (EPI == 1) {
+      if constexpr (EPI == 3) {
+        const int cbase = n_t * BN + ch * kHalf;
+        const int row0 = m_t * BM + ew * 32;
+        uint32_t r[32];
+        float4 rr0[8];
+        // (chunk 0 was requested before the accumulator wait)
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          if (c == 0) epi_load_resid(pz, row0, cbase, lane, rr0);
+          tmem_ld_32x32(taddr + ch * kHalf + c * 32, r);
+          float4 rn[8];
+          if (c + 1 < kChunks) epi_load_resid(pz, row0, cbase + (c + 1) * 32, lane, rn);
+          tmem_wait_ld();
+          epi_store_f32x32_rr(pz, stg, row0, cbase + c * 32, r, rr0, lane);
+          if (c + 1 < kChunks) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rr0[it] = rn[it];
+          }
+        }
+      } else if constexpr (EPI == 1) {
         // GEGLU forward: this warp owns slab columns [64 ch, 64 ch + 64) of BOTH slabs (x at TMEM column lc, gate at 128 + lc)
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -788,6 +840,17 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
                           d->b_stride_h, d->b_stride_b);
   if (rc) return rc;
 
+  // fp32 + residual, whole 256-column tiles, K-major operands: the register-prefetching instantiation (CTCLIP_GEMM_RESID_AHEAD=0: off)
+  bool resid_ahead = false;
+  {
+    const char* e = getenv("CTCLIP_GEMM_RESID_AHEAD");
+    const bool on = !(e != nullptr && e[0] == '0');
+    resid_ahead = on && d->resid != nullptr && d->c_is_f32 && d->bias == nullptr && !d->atomic && d->alpha == 1.f && kp.z_n == 1 &&
+                  kp.top2 == nullptr && !geglu_fwd && BN == 256 && d->N % 256 == 0 && !d->a_mn_major && !d->b_mn_major &&
+                  (reinterpret_cast<uintptr_t>(d->C) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 &&
+                  (d->ldc % 4) == 0 && (d->ldr % 4) == 0;
+  }
+
   if (pair) {
     const int units = ((kp.m_tiles + 1) / 2) * kp.n_tiles * kp.splits * kp.z_n;
     int clusters = sms / 2;
@@ -795,6 +858,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
     const int grid = 2 * clusters;
     const int sel = (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
     if (geglu_fwd) return launch<256, false, false, true, 1>(d, kp, ta, tb, grid, stream);
+    if (resid_ahead) return launch<256, false, false, true, 3>(d, kp, ta, tb, grid, stream);
     switch (sel) {
       case 0: return launch<256, false, false, true>(d, kp, ta, tb, grid, stream);
       case 1: return launch<256, false, true, true>(d, kp, ta, tb, grid, stream);
@@ -806,6 +870,7 @@ extern "C" int ctclip_gemm_bf16(const ctclip_gemm_desc* d, void* stream_v) {
   const int grid = num_work < sms ? num_work : sms;
   const int sel = (BN == 256 ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   if (geglu_fwd) return launch<256, false, false, false, 1>(d, kp, ta, tb, grid, stream);
+  if (resid_ahead) return launch<256, false, false, false, 3>(d, kp, ta, tb, grid, stream);
   switch (sel) {
     case 0: return launch<128, false, false, false>(d, kp, ta, tb, grid, stream);
     case 1: return launch<128, false, true, false>(d, kp, ta, tb, grid, stream);
