@@ -525,7 +525,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         pz.C = p.c_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.C) + off)
                           : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off);
       }
-      if (fast_mode == 3 || fast_mode == 5) {
+      if (EPI != 3 && (fast_mode == 3 || fast_mode == 5)) {
         // The residual rows of the NEXT work unit start their way from HBM into L2 now (no registers held): one tile
         // epilogue later the loads below are L2 hits, so the few loads a warp keeps in flight no longer bound the bandwidth
         auto prefetch_resid = [&](int wq) {

@@ -39,6 +39,10 @@ dy = torch.randn(T, D, device=dev, generator=g)
 gam = torch.ones(D, device=dev)
 dg = torch.zeros(D, device=dev)
 ops.layernorm_bwd(dy, x, gam, add_in=dy, dgamma=dg, want_bf16=True)
+ops.layernorm_bwd(dy.bfloat16(), x, gam, add_in=dy, dgamma=dg, want_bf16=True)      # the in-step variant: bf16 dy + residual gradient
+h1f, u = ops.gemm_geglu(xf, w1)                                   # ff1 forward with the GEGLU epilogue (EPI = 1)
+w2 = torch.randn(512, 1368, device=dev, generator=g).bfloat16()
+x3 = ops.gemm(u, w2, out_dtype=torch.float32, resid=x)            # ff2 + residual (EPI = 3, K = 1368)
 torch.cuda.synchronize()
 print("done")
 # data_prep fast path (one production scan) and the generic brick kernel
