@@ -462,7 +462,10 @@ extern "C" int ctclip_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
   if (dy == nullptr || x == nullptr || gamma == nullptr) return ctclip::fail(CTCLIP_E_SHAPE, "layernorm_bwd: null pointer");
   int rc = ctclip::require_sm100();
   if (rc) return rc;
-  long long blocks = (rows + 63) / 64;  // each warp walks >= 8 rows so the column reductions amortise
+  // each warp walks >= 8 rows so the column reductions amortise — unless that leaves SMs empty: the BERT tower's [4096, 768]
+  // calls got 64 CTAs for 148 SMs (22 us per call, 25 calls per step); two rows per warp fill the chip
+  long long blocks = (rows + 63) / 64;
+  if (blocks < (long long)ctclip::sm_count() * 2) blocks = (rows + 15) / 16;
   // one resident wave (3 CTAs / SM at <= 80 registers for dim <= 512): the column-sum flush happens once per CTA
   const long long cap = (long long)ctclip::sm_count() * 3;
   if (blocks > cap) blocks = cap;
