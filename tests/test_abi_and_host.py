@@ -136,3 +136,23 @@ def test_package_configs_equal_the_oracles():
     src = (ROOT / "bench.py").read_text()
     ours = src[src.index("def run_ours"):src.index('if __name__ == "__main__"')]
     assert not re.search(r"^\s*(import|from)\s+oracle", ours, flags=re.M), "product arm must not import oracle/"
+
+
+def test_bias_table_pitch_is_conflict_free():
+    """csrc/attention.cu tab_pitch(): the relative-position bias table rows sit at pitch S = gw + 32 * ceil((gw - 1) / 32) in
+    shared memory. Lanes of a warp are 32 consecutive query positions p = qy * gw + qx reading word (qy + gh - 1) * S + qx +
+    gw - 1 - B_j: for every grid and every start position the 32 words must fall into 32 different banks, every index must stay
+    inside the padded table, and S must hold a whole table row."""
+    def pitch(gw):
+        return gw + 32 * ((gw - 1 + 31) // 32)
+    for gh, gw in [(24, 24), (13, 11), (6, 6), (4, 4), (5, 5), (3, 4), (40, 33), (2, 64), (7, 1)]:
+        S = pitch(gw)
+        assert S >= 2 * gw - 1 and S % 32 == gw % 32
+        words = (2 * gh - 2) * S + 2 * gw - 1
+        n = gh * gw
+        a = [((p // gw) + gh - 1) * S + (p % gw) + gw - 1 for p in range(n)]
+        b = [(k // gw) * S + (k % gw) for k in range(n)]
+        assert min(a) - max(b) == 0 and max(a) - min(b) == words - 1
+        for start in range(0, max(1, n - 31)):
+            lanes = a[start:start + 32]
+            assert len({x % 32 for x in lanes}) == len(lanes), (gh, gw, start)
