@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--config", default="production")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-op device-time breakdown of one step to this file")
-    ap.add_argument("--e2e-mode", default="both", choices=["both", "raw", "fp32"],
+    ap.add_argument("--e2e-mode", default="both", choices=["both", "raw12", "raw", "fp32"],
                     help="end-to-end input: raw int16 scans + on-device data_prep (headline), pre-normalised fp32 volumes, or both")
     ap.add_argument("--no-extras", action="store_true", help="skip the data_prep (configs[3]) and zero-shot (configs[4]) legs")
     return ap.parse_args()
@@ -250,71 +250,92 @@ def run_ours(args):
     copy_stream, prep_stream = torch.cuda.Stream(), torch.cuda.Stream()
     ids_h, mask_h = ids.pin_memory(), mask.pin_memory()
 
+    RING = 3      # input ring depth: a copy may finish up to two steps late without stalling the step (8 ranks share the host)
+    LAG = 2       # the host consumes a step's loss two steps later (it may run two steps ahead of the device)
+
     def run_e2e(mode):
+        raw_like = mode in ("raw", "raw12")
+        stage16 = None
         if mode == "raw":
             raw = synth_raw_scans(B, seed=200 + rank)
             host = [raw.pin_memory(), raw.clone().pin_memory()]
-            stage = [torch.empty(host[0].shape, device=dev, dtype=torch.int16) for _ in range(2)]
+            stage = [torch.empty(host[0].shape, device=dev, dtype=torch.int16) for _ in range(RING)]
             del raw
+        elif mode == "raw12":
+            # the same scans in the 12-bit transfer format (two voxels per three bytes, data_prep/pack12.py): 126 MB per scan
+            # on the wire; ctclip_unpack12 restores the int16 array on the device in front of the data_prep kernel
+            # Synthetic scans: uniformly random bytes ARE the packed form of uniformly random 12-bit voxels (stored 0 .. 4095,
+            # i.e. raw -1024 .. 3071 with offset 1024 — the distribution synth_raw_scans draws), so no host packing pass is needed
+            n_vox = B * RAW_SHAPE[0] * RAW_SHAPE[1] * RAW_SHAPE[2]
+            gq = torch.Generator().manual_seed(200 + rank)
+            packed = torch.randint(0, 256, (n_vox * 3 // 2,), generator=gq, dtype=torch.uint8)
+            host = [packed.pin_memory(), packed.clone().pin_memory()]
+            stage = [torch.empty(host[0].shape, device=dev, dtype=torch.uint8) for _ in range(RING)]
+            stage16 = torch.empty((B, *RAW_SHAPE), device=dev, dtype=torch.int16)
+            del packed
         else:
             host = [video_h.pin_memory(), video_h.clone().pin_memory()]
             stage = None
-        bufs = [torch.empty_like(video_d), torch.empty_like(video_d)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        tbufs = [(torch.empty_like(text.input_ids), torch.empty_like(text.attention_mask)) for _ in range(2)]
+        bufs = [torch.empty_like(video_d) for _ in range(RING)]
+        ready = [torch.cuda.Event() for _ in range(RING)]
+        consumed = [torch.cuda.Event() for _ in range(RING)]
+        tbufs = [(torch.empty_like(text.input_ids), torch.empty_like(text.attention_mask)) for _ in range(RING)]
         texts = [BatchEncoding({"input_ids": a, "attention_mask": b}) for a, b in tbufs]
         h2d_events = []
 
-        prep_done = [torch.cuda.Event(), torch.cuda.Event()]      # (raw mode) the prep kernel has consumed stage[i % 2]
+        prep_done = [torch.cuda.Event() for _ in range(RING)]      # (raw mode) the prep kernel has consumed stage[i % RING]
         for e in prep_done:
             e.record()
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        copied = [torch.cuda.Event() for _ in range(RING)]
 
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                if mode == "raw":
-                    copy_stream.wait_event(prep_done[i % 2])                       # stage[i % 2] is free again
+                if raw_like:
+                    copy_stream.wait_event(prep_done[i % RING])                       # stage[i % RING] is free again
                     c0.record(copy_stream)
-                    stage[i % 2].copy_(host[i % 2], non_blocking=True)             # this step's raw scans ...
+                    stage[i % RING].copy_(host[i % 2], non_blocking=True)             # this step's raw scans ...
                 else:
-                    copy_stream.wait_event(consumed[i % 2])
+                    copy_stream.wait_event(consumed[i % RING])
                     c0.record(copy_stream)
-                    bufs[i % 2].copy_(host[i % 2], non_blocking=True)
-                if mode != "raw":
-                    tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                # ... token ids / attention mask
-                    tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
+                    bufs[i % RING].copy_(host[i % 2], non_blocking=True)
+                if not raw_like:
+                    tbufs[i % RING][0].copy_(ids_h, non_blocking=True)                # ... token ids / attention mask
+                    tbufs[i % RING][1].copy_(mask_h, non_blocking=True)
                 c1.record(copy_stream)
                 h2d_events.append((c0, c1))
-                if mode == "raw":
-                    copied[i % 2].record(copy_stream)
+                if raw_like:
+                    copied[i % RING].record(copy_stream)
                 else:
-                    ready[i % 2].record(copy_stream)
-            if mode == "raw":
+                    ready[i % RING].record(copy_stream)
+            if raw_like:
                 # data_prep on the device behind the copy, on its OWN stream: while it waits for SMs between the step's
                 # persistent kernels, the copy engine already moves the next step's scans (on the copy stream it stalled them)
                 with torch.cuda.stream(prep_stream):
-                    prep_stream.wait_event(copied[i % 2])
-                    prep_stream.wait_event(consumed[i % 2])                        # the step that last read bufs / tbufs[i % 2] is done
-                    tbufs[i % 2][0].copy_(ids_h, non_blocking=True)                # token ids / attention mask (64 KB)
-                    tbufs[i % 2][1].copy_(mask_h, non_blocking=True)
-                    preprocess_volumes(stage[i % 2], 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1], out=bufs[i % 2])
-                    prep_done[i % 2].record(prep_stream)
-                    ready[i % 2].record(prep_stream)
+                    prep_stream.wait_event(copied[i % RING])
+                    prep_stream.wait_event(consumed[i % RING])                        # the step that last read bufs / tbufs[i % RING] is done
+                    tbufs[i % RING][0].copy_(ids_h, non_blocking=True)                # token ids / attention mask (64 KB)
+                    tbufs[i % RING][1].copy_(mask_h, non_blocking=True)
+                    src = stage[i % RING]
+                    if mode == "raw12":
+                        ops.unpack12(src, stage16, stage16.numel(), 1024)
+                        src = stage16
+                    preprocess_volumes(src, 1.0, 0.0, RAW_SPACING[0], RAW_SPACING[1], out=bufs[i % RING])
+                    prep_done[i % RING].record(prep_stream)
+                    ready[i % RING].record(prep_stream)
 
         losses = []
-        k = [0]                                   # running step index: step k reads bufs[k % 2], prefetches step k + 1
+        k = [0]                                   # running step index: step k reads bufs[k % RING], prefetches step k + 1
         loss_host = torch.empty(args.steps + 8, dtype=torch.float32).pin_memory()   # one pinned slot per step
         in_flight = []                            # (slot, event) of losses copied back but not yet consumed by the host
 
         def step_e2e(_):
             i = k[0]
             k[0] += 1
-            prefetch(i + 1)                       # next step's inputs: H2D (+ prep) overlaps this step's kernels
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            loss = trainer.step(texts[i % 2], bufs[i % 2])
-            consumed[i % 2].record()
+            prefetch(i + RING - 1)                # inputs RING - 1 steps ahead: H2D (+ prep) overlaps this and the next step's kernels
+            torch.cuda.current_stream().wait_event(ready[i % RING])
+            loss = trainer.step(texts[i % RING], bufs[i % RING])
+            consumed[i % RING].record()
             # D2H read of the step's result, EVERY step (the trainer's `loss.item()`, CTCLIPTrainer.py:346), as an async copy
             # into pinned memory; the host consumes step i-1's value here, while step i is already enqueued. The host never
             # runs more than one step ahead; the last value is consumed right after the closing synchronize.
@@ -322,7 +343,7 @@ def run_ours(args):
             loss_host[slot: slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            if in_flight:
+            if len(in_flight) >= LAG:
                 s_prev, e_prev = in_flight.pop(0)
                 e_prev.synchronize()
                 losses.append(float(loss_host[s_prev]))
@@ -330,8 +351,9 @@ def run_ours(args):
 
         for e in consumed:
             e.record()
-        prefetch(0)
-        for i in range(min(2, args.warmup)):      # the copy pipeline reaches steady state after two steps
+        for j in range(RING - 1):
+            prefetch(j)
+        for i in range(min(RING, args.warmup)):   # the copy pipeline reaches steady state after a few steps
             step_e2e(i)
         h2d_events.clear()
         ms = timed(step_e2e, args.steps) / args.steps
@@ -346,7 +368,9 @@ def run_ours(args):
             dist.all_reduce(gbps, op=dist.ReduceOp.MIN)
         return {"ms": ms, "h2d_bytes": nbytes, "loss": losses[-1] if losses else None, "h2d_GBps_slowest_rank": float(gbps)}
 
-    e2e_modes = ["raw", "fp32"] if production else ["fp32"]
+    # headline: raw scans in the 12-bit transfer format (the fewest bytes over PCIe: at 8 ranks the host, ~22 GB/s per GPU, is
+    # what bounds the end-to-end step); the int16 and the pre-normalised fp32 variants are reported next to it
+    e2e_modes = ["raw12", "raw", "fp32"] if production else ["fp32"]
     if args.e2e_mode != "both":
         e2e_modes = [m for m in e2e_modes if m == args.e2e_mode] or e2e_modes[:1]
     e2e_runs = {m: run_e2e(m) for m in e2e_modes}
@@ -450,7 +474,11 @@ def run_ours(args):
         traffic_note = (f"bytes per launch: dram__bytes_read+write summed over the {tj['launches']} gemm_bf16_kernel launches of one "
                         f"step / launches, from the committed ncu pass profiles/{tfiles[-1].name} "
                         f"(GEMM share of that serialised step: {tj['share_of_step']:.3f})")
-    e2e_note = {"raw": "pinned RAW int16 scans (512x512x320) + token ids + masks copied every step on a copy stream (double "
+    e2e_note = {"raw12": "pinned RAW scans in the 12-bit transfer format (two voxels per three bytes, 126 MB per 512x512x320 scan; "
+                         "data_prep/pack12.py) + token ids + masks copied every step on a copy stream (double buffered); "
+                         "ctclip_unpack12 and the bit-exact data_prep kernel (HU clip/normalise/trilinear resample) run on the "
+                         "device behind the copy; every step's loss is copied to pinned host memory and read one step later",
+                "raw": "pinned RAW int16 scans (512x512x320) + token ids + masks copied every step on a copy stream (double "
                        "buffered); the bit-exact data_prep kernel (HU clip/normalise/trilinear resample) runs on the device "
                        "behind the copy; every step's loss is copied to pinned host memory and read by the host one step later",
                 "fp32": "pinned, already normalised fp32 volumes + token ids + masks, double-buffered copy stream; every step's "
@@ -470,6 +498,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": head["ms"], "h2d_bytes_per_step": head["h2d_bytes"],
                 "d2h_bytes_per_step": 4, "mode": e2e_modes[0], "h2d_GBps_slowest_rank": head["h2d_GBps_slowest_rank"],
                 "note": e2e_note[e2e_modes[0]],
+                **({"raw_int16": {"value": world * B / (e2e_runs["raw"]["ms"] * 1e-3), "ms_per_step": e2e_runs["raw"]["ms"],
+                                  "h2d_bytes_per_step": e2e_runs["raw"]["h2d_bytes"],
+                                  "h2d_GBps_slowest_rank": e2e_runs["raw"]["h2d_GBps_slowest_rank"],
+                                  "note": e2e_note["raw"]}} if "raw" in e2e_runs and e2e_modes[0] != "raw" else {}),
                 **({"fp32_volumes": {"value": world * B / (e2e_runs["fp32"]["ms"] * 1e-3), "ms_per_step": e2e_runs["fp32"]["ms"],
                                      "h2d_bytes_per_step": e2e_runs["fp32"]["h2d_bytes"],
                                      "h2d_GBps_slowest_rank": e2e_runs["fp32"]["h2d_GBps_slowest_rank"],

@@ -116,6 +116,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_t: bool = False, b_t: bool = Fal
     return out
 
 
+def unpack12(packed: torch.Tensor, out: torch.Tensor, n_voxels: int, offset: int = 1024):
+    """12-bit packed raw scans (uint8, n_voxels * 3 / 2 bytes) -> int16 `out` (n_voxels elements); see data_prep/pack12.py"""
+    _req(packed, torch.uint8, "unpack12.packed")
+    _req(out, torch.int16, "unpack12.out")
+    assert packed.is_contiguous() and out.is_contiguous() and packed.numel() * 2 == n_voxels * 3 and out.numel() == n_voxels
+    _call("ctclip_unpack12", _ptr(packed), _ptr(out), _ll(n_voxels), int(offset), _stream())
+    return out
+
+
 def gemm_geglu(a: torch.Tensor, w: torch.Tensor, *, tag: str = ""):
     """FeedForward's first Linear with GEGLU in the epilogue (attention.py:39-48): a [M, K] bf16, w [2 Nh, K] bf16 =
     [x rows | gate rows]. Returns (h [M, 2 Nh] bf16 = [x | gate], kept for the backward, u [M, Nh] bf16 = x * gelu(gate)) —

@@ -310,6 +310,13 @@ typedef struct ctclip_prep_desc {
   int pre_op, post_op;
 } ctclip_prep_desc;
 int ctclip_prep_resample(const ctclip_prep_desc* d, void* stream);
+/* 12-bit transfer format of raw scans (the loaders of data_prep/preprocess_train.py:60-109 and ct_clip/data.py:114-150 hold
+ * int16 / float arrays; CT voxels carry 12 significant bits): `in` holds n_voxels * 3 / 2 bytes, two voxels v = raw + offset
+ * (clamped to [0, 4095]) per three bytes, little endian (b0 = v0 & 0xff, b1 = v0 >> 8 | (v1 & 0xf) << 4, b2 = v1 >> 4);
+ * `out` receives the n_voxels int16 values v - offset that ctclip_prep_resample reads (in_is_i16). n_voxels % 16 == 0.
+ * Host-side packer: ctpa_clip_b200/data_prep/pack12.py. Lossless for the path whenever [-offset, 4095 - offset] covers the
+ * pre-image of the HU window [-1000, 1000] process_file clips to. */
+int ctclip_unpack12(const void* in, void* out, long long n_voxels, int offset, void* stream);
 
 #ifdef __cplusplus
 }

@@ -156,3 +156,18 @@ def test_bias_table_pitch_is_conflict_free():
         for start in range(0, max(1, n - 31)):
             lanes = a[start:start + 32]
             assert len({x % 32 for x in lanes}) == len(lanes), (gh, gw, start)
+
+
+def test_pack12_round_trip_on_the_host():
+    """data_prep/pack12.py: two voxels in three bytes; the inverse restores every value inside [-offset, 4095 - offset] and
+    clamps the rest (which the HU window [-1000, 1000] of process_file would clip anyway)"""
+    import numpy as np
+    from ctpa_clip_b200.data_prep.pack12 import pack12, unpack12_numpy
+    rng = np.random.default_rng(3)
+    raw = rng.integers(-3000, 6000, size=(4, 8, 16), dtype=np.int16)
+    raw.reshape(-1)[:6] = [-1024, 3071, -1025, 3072, 0, -1]
+    for offset in (1024, 0, 2048):
+        packed = pack12(raw, offset)
+        assert packed.dtype.is_floating_point is False and packed.numel() == raw.size * 3 // 2
+        back = unpack12_numpy(packed, offset).reshape(raw.shape)
+        assert (back == np.clip(raw, -offset, 4095 - offset)).all()

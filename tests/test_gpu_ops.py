@@ -125,6 +125,26 @@ def test_layernorm_bwd_ring_kernel_is_bit_identical(ops, dy_bf16, with_add, monk
     close(res[0][2], res[1][2], 1e-4); close(res[0][3], res[1][3], 1e-4)
 
 
+@pytest.mark.parametrize("offset", [1024, 0])
+def test_unpack12_restores_the_raw_scan_and_the_prep_output(ops, offset):
+    """12-bit transfer format: ctclip_unpack12 of the host-packed bytes equals the clamped int16 scan bit for bit, and the
+    data_prep output computed from it is bit-identical to the one computed from the original scan (the clamp lies outside
+    the HU window)"""
+    from ctpa_clip_b200.data_prep.pack12 import pack12, unpack12
+    from ctpa_clip_b200.data_prep import preprocess_volumes
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randint(-1024 if offset else 0, 3072 if offset else 4096, (2, 32, 32, 24), generator=g, dtype=torch.int16)
+    raw.view(-1)[:4] = torch.tensor([-5000, 9000, -1024 if offset else 0, 3071 if offset else 4095], dtype=torch.int16)
+    packed = pack12(raw, offset).cuda()
+    got = unpack12(packed, raw.shape, offset)
+    want = raw.clamp(-offset, 4095 - offset)
+    assert torch.equal(got.cpu(), want)
+    if offset:
+        a = preprocess_volumes(raw.cuda(), 1.0, 0.0, 0.703125, 1.125)
+        b = preprocess_volumes(got, 1.0, 0.0, 0.703125, 1.125)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
 def test_gemm_rejects_bad_alignment(ops):
     from ctpa_clip_b200._lib import CtclipError
     A = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
