@@ -48,7 +48,14 @@ class _Span:
         return False
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> C.c_void_p:
+    """the current torch stream of the current device as a cudaStream_t. torch.cuda.current_stream() builds a Stream object
+    through three layers of Python (14 us per call, 600 calls per step); the raw query is one C call."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
