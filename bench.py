@@ -12,9 +12,10 @@ N>1 keeps 8 volumes per rank by default (weak scaling; N=8 is configs[2], global
 the loss kernel itself, csrc/symm.cu); `--batch 32 / 16` at N = 2 / 4 runs configs[2] literally (global batch 64).
 Prints ONE JSON line on rank 0:
   value        device-resident steps (CUDA events, barrier + synchronize on both sides, max over ranks)
-  e2e          the same steps fed from pinned HOST memory every step: raw int16 scans -> H2D on a copy stream -> bit-exact
-               data_prep kernel on the device -> step -> loss copied back to pinned memory and read by the host
-               (e2e.fp32_volumes: the same with already normalised fp32 volumes, the round-1 definition)
+  e2e          the same steps fed from pinned HOST memory every step: raw scans in the 12-bit transfer format (two voxels per
+               three bytes, data_prep/pack12.py) -> H2D on a copy stream (three-deep ring) -> ctclip_unpack12 + bit-exact
+               data_prep kernel on the device -> step -> loss copied back to pinned memory and read by the host two steps later
+               (e2e.raw_int16: the same with int16 scans; e2e.fp32_volumes: already normalised fp32 volumes, the round-1 definition)
   roofline     all gemm_bf16_kernel launches of one instrumented step against MEASURED_PEAKS.json (+ per-shape table)
   prep         BASELINE configs[3] (data_prep, batch 32) against the measured HBM copy bandwidth
   zero_shot    BASELINE configs[4] (256 volumes x 18 prompt pairs), device-resident and end to end
@@ -241,7 +242,7 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- end to end. Host buffers -> H2D on a copy stream (double buffered) -> step -> loss read back, every step.
+    # ---- end to end. Host buffers -> H2D on a copy stream (RING-deep input ring) -> step -> loss read back, every step.
     # mode "raw" (headline, production config): the host holds RAW int16 scans (512, 512, 320), 168 MB each; the bit-exact
     #   data_prep kernel (HU clip / normalise / trilinear resample, ctclip_prep_resample) runs on the device behind the copy
     #   and hands the step its (B, 1, 240, 480, 480) fp32 volumes — the reference's own order of work (data.py:138-192
@@ -325,7 +326,7 @@ def run_ours(args):
                     ready[i % RING].record(prep_stream)
 
         losses = []
-        k = [0]                                   # running step index: step k reads bufs[k % RING], prefetches step k + 1
+        k = [0]                                   # running step index: step k reads bufs[k % RING], prefetches step k + RING - 1
         loss_host = torch.empty(args.steps + 8, dtype=torch.float32).pin_memory()   # one pinned slot per step
         in_flight = []                            # (slot, event) of losses copied back but not yet consumed by the host
 
@@ -337,8 +338,9 @@ def run_ours(args):
             loss = trainer.step(texts[i % RING], bufs[i % RING])
             consumed[i % RING].record()
             # D2H read of the step's result, EVERY step (the trainer's `loss.item()`, CTCLIPTrainer.py:346), as an async copy
-            # into pinned memory; the host consumes step i-1's value here, while step i is already enqueued. The host never
-            # runs more than one step ahead; the last value is consumed right after the closing synchronize.
+            # into pinned memory; the host consumes step (i - LAG)'s value here, while steps i - LAG + 1 .. i are already
+            # enqueued. The host never runs more than LAG steps ahead; the last values are consumed right after the closing
+            # synchronize.
             slot = i % loss_host.numel()
             loss_host[slot: slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
             ev = torch.cuda.Event()
